@@ -1,0 +1,133 @@
+// TEST INFRASTRUCTURE ONLY (see oracle_rng.h).  Small dense column-major linear algebra for the
+// oracle: stands in for the Eigen 3.4 calls of the reference (LLT, triangularView::solve, GEMM,
+// kroneckerProduct; un-vendored dependency RcppEigen >= 0.3.4, DESCRIPTION:46).  Hand-written
+// loops, no BLAS.
+#ifndef BVHAR_ORACLE_LINALG_H
+#define BVHAR_ORACLE_LINALG_H
+
+#include <algorithm>
+#include <cmath>
+#include <cstddef>
+#include <cstring>
+#include <vector>
+
+namespace orc {
+
+struct Mat {
+  int r = 0, c = 0;
+  std::vector<double> v;
+  Mat() {}
+  Mat(int r_, int c_, double fill = 0.0) : r(r_), c(c_), v((size_t)r_ * c_, fill) {}
+  double& operator()(int i, int j) { return v[(size_t)j * r + i]; }
+  double operator()(int i, int j) const { return v[(size_t)j * r + i]; }
+  double* col(int j) { return v.data() + (size_t)j * r; }
+  const double* col(int j) const { return v.data() + (size_t)j * r; }
+  double* data() { return v.data(); }
+  const double* data() const { return v.data(); }
+  size_t size() const { return v.size(); }
+};
+typedef std::vector<double> Vec;
+
+// C (m x n) = A^T B, A (k x m), B (k x n); cache-blocked over k, inner loop contiguous in k.
+inline void gemm_tn(const Mat& A, const Mat& B, Mat& C) {
+  const int m = A.c, n = B.c, k = A.r;
+  C = Mat(m, n);
+  const int KB = 256;
+  for (int k0 = 0; k0 < k; k0 += KB) {
+    const int k1 = std::min(k, k0 + KB);
+    for (int j = 0; j < n; ++j) {
+      const double* b = B.col(j);
+      for (int i = 0; i < m; ++i) {
+        const double* a = A.col(i);
+        double s = 0;
+        for (int t = k0; t < k1; ++t) s += a[t] * b[t];
+        C(i, j) += s;
+      }
+    }
+  }
+}
+// C (m x n) = A B, A (m x k), B (k x n); axpy form, contiguous in m.
+inline void gemm_nn(const Mat& A, const Mat& B, Mat& C) {
+  const int m = A.r, n = B.c, k = A.c;
+  C = Mat(m, n);
+  for (int j = 0; j < n; ++j) {
+    double* c = C.col(j);
+    for (int t = 0; t < k; ++t) {
+      const double b = B(t, j);
+      if (b == 0.0) continue;
+      const double* a = A.col(t);
+      for (int i = 0; i < m; ++i) c[i] += a[i] * b;
+    }
+  }
+}
+
+// In-place lower Cholesky of the lower triangle of P (d x d col-major) — Eigen::LLT semantics
+// (only the lower triangle is referenced, draw.h:380).  Returns false if a pivot is not positive
+// (Eigen would silently produce NaNs; the oracle keeps going with NaNs as well).
+inline bool chol_lower(Mat& P) {
+  const int d = P.r;
+  bool ok = true;
+  for (int j = 0; j < d; ++j) {
+    double* cj = P.col(j);
+    for (int t = 0; t < j; ++t) {
+      const double ljt = P(j, t);
+      if (ljt == 0.0) continue;
+      const double* ct = P.col(t);
+      for (int i = j; i < d; ++i) cj[i] -= ct[i] * ljt;
+    }
+    double piv = cj[j];
+    if (!(piv > 0.0)) ok = false;
+    piv = std::sqrt(piv);
+    cj[j] = piv;
+    const double inv = 1.0 / piv;
+    for (int i = j + 1; i < d; ++i) cj[i] *= inv;
+  }
+  return ok;
+}
+// Solve L x = b in place.
+inline void solve_lower(const Mat& L, double* x) {
+  const int d = L.r;
+  for (int j = 0; j < d; ++j) {
+    x[j] /= L(j, j);
+    const double xj = x[j];
+    const double* c = L.col(j);
+    for (int i = j + 1; i < d; ++i) x[i] -= c[i] * xj;
+  }
+}
+// Solve L^T x = b in place.
+inline void solve_lower_t(const Mat& L, double* x) {
+  const int d = L.r;
+  for (int j = d - 1; j >= 0; --j) {
+    const double* c = L.col(j);
+    double s = x[j];
+    for (int i = j + 1; i < d; ++i) s -= c[i] * x[i];
+    x[j] = s / c[j];
+  }
+}
+
+// draw.h:372-383 with the standard normals passed in: P = diag(prec) + G (G lower valid),
+// coef = P^-1 rhs + chol(P)^-T z.
+inline void precision_draw(Mat& P, const double* rhs, const double* z, double* coef) {
+  const int d = P.r;
+  chol_lower(P);
+  Vec m(rhs, rhs + d), e(z, z + d);
+  solve_lower(P, m.data());    // llt.solve(): L y = rhs ...
+  solve_lower_t(P, m.data());  // ... L^T mean = y                (draw.h:382)
+  solve_lower_t(P, e.data());  // llt.matrixU().solve(res)        (draw.h:383)
+  for (int i = 0; i < d; ++i) coef[i] = m[i] + e[i];
+}
+
+// draw.h:124-132
+inline Mat build_inv_lower(int dim, const double* a) {
+  Mat L(dim, dim);
+  for (int i = 0; i < dim; ++i) L(i, i) = 1.0;
+  int id = 0;
+  for (int i = 1; i < dim; ++i) {
+    for (int j = 0; j < i; ++j) L(i, j) = a[id + j];
+    id += i;
+  }
+  return L;
+}
+
+}  // namespace orc
+#endif
