@@ -313,6 +313,7 @@ def load_library():
     L.bvhar_cuda_last_error.restype = C.c_char_p
     L.bvhar_cuda_abi_version.restype = C.c_int
     L.bvhar_cuda_device_count.argtypes = [C.POINTER(C.c_int)]
+    L.bvhar_cuda_struct_sizes.argtypes = [C.POINTER(C.c_int64)] * 4
     L.bvhar_cuda_fit_create.argtypes = [C.POINTER(FitDesc), C.POINTER(vp)]
     L.bvhar_cuda_fit_run.argtypes = [vp, PROGRESS_FN, vp]
     L.bvhar_cuda_fit_step.argtypes = [vp, C.c_int, C.c_int]
@@ -331,8 +332,15 @@ def load_library():
     L.bvhar_cuda_forecast_density.argtypes = [C.POINTER(ForecastDesc), c_dp, c_dp]
     L.bvhar_cuda_dgemm_tn.argtypes = [C.c_int, C.c_int64, C.c_int64, C.c_int64, c_dp, C.c_int64, c_dp, C.c_int64, c_dp, C.c_int64]
     L.bvhar_cuda_draw_coef_batched.argtypes = [C.c_int, C.c_int64, C.c_int32, c_dp, c_dp, c_dp, c_dp]
+    L.bvhar_cuda_bench_fp64_peak.argtypes = [C.c_int, C.c_int, c_dp]
+    L.bvhar_cuda_bench_dgemm_tn.argtypes = [C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_int, c_dp]
     if L.bvhar_cuda_abi_version() != ABI_VERSION:
         raise RuntimeError("bvhar_b200: libbvhar_b200.so was built against a different ABI version; rebuild it")
+    sz = [C.c_int64() for _ in range(4)]
+    L.bvhar_cuda_struct_sizes(*[C.byref(v) for v in sz])
+    mine = [C.sizeof(FitDesc), C.sizeof(ChainInit), C.sizeof(ForecastDesc), C.sizeof(PriorParams)]
+    if [v.value for v in sz] != mine:
+        raise RuntimeError(f"bvhar_b200: ctypes struct layout {mine} differs from the library's {[v.value for v in sz]}")
     _LIB = L
     return L
 

@@ -1,0 +1,227 @@
+"""Host-side mirror of the reference's sampler classes, backed by the CUDA engine's C-ABI.
+
+Classes and constructor signatures follow the pybind11 bindings of the reference
+(python/src/bvhar/_src/_cta.cpp:4-38 ``McmcLdlt``, ``McmcLdltGrp``, ``SvMcmc``, ``SvGrpMcmc``;
+:40-208 ``LdltForecast`` ... ``SvGrpVharExpand``), i.e. the template instantiations of
+``bvhar::McmcRun<BaseMcmc, isGroup>`` (triangular.h:1192-1295), ``McmcForecastRun`` and
+``Mcmc{Var,Vhar}forecastRun`` (forecaster.h:494-1121).  ``returnRecords()`` returns one dict per chain
+with the record names of config.h:639-648, 865-867, 967-971, 814-820.
+
+There is no CPU fallback: constructing any of these without the built CUDA library or without a
+GPU raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Any, Dict, List, Optional, Sequence
+
+import numpy as np
+
+from . import _abi
+from ._abi import BvharCudaError, ForecastDesc, PackedFit, REC_ALL, c_dp, c_up, check, load_library
+from ._design import build_design, build_response, build_vhar
+
+
+class CudaFit:
+    """A batch of (window, chain) sampling units living on one GPU."""
+
+    def __init__(self, packed: PackedFit):
+        self.packed = packed
+        self.L = load_library()
+        self._h = C.c_void_p()
+        check(self.L.bvhar_cuda_fit_create(C.byref(packed.desc), C.byref(self._h)))
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self.L.bvhar_cuda_fit_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- driving ----------------------------------------------------------------------------
+    def run(self, progress=None):
+        """num_burn warm-up sweeps, then num_iter - num_burn recorded sweeps (triangular.h:1241-1284)."""
+        if progress is None:
+            cb = _abi.PROGRESS_FN()
+        else:
+            cb = _abi.PROGRESS_FN(lambda ctx, done, total: int(bool(progress(done, total))))
+        check(self.L.bvhar_cuda_fit_run(self._h, cb, None))
+
+    def step(self, n: int = 1, record: bool = False, sync: bool = True):
+        check(self.L.bvhar_cuda_fit_step(self._h, int(n), int(record)))
+        if sync:
+            self.sync()
+
+    def sync(self):
+        check(self.L.bvhar_cuda_fit_sync(self._h))
+
+    def run_stage(self, stage: int, it: int):
+        check(self.L.bvhar_cuda_fit_run_stage(self._h, int(stage), int(it)))
+
+    def last_ms(self) -> float:
+        v = C.c_double()
+        check(self.L.bvhar_cuda_fit_last_ms(self._h, C.byref(v)))
+        return v.value
+
+    def launch_count(self) -> int:
+        v = C.c_int64()
+        check(self.L.bvhar_cuda_fit_launch_count(self._h, C.byref(v)))
+        return v.value
+
+    # -- state (parity tests) ---------------------------------------------------------------
+    def get_state(self, name: str, window: int = 0, chain: int = 0) -> np.ndarray:
+        n = C.c_int64()
+        check(self.L.bvhar_cuda_fit_state_len(self._h, name.encode(), C.byref(n)))
+        ln = n.value
+        if name in ("latent_innov", "lvol_draw", "sqrt_sv"):
+            ln = int(self.packed.win_nrow[window]) * self.packed.dim
+        out = np.empty(ln)
+        check(self.L.bvhar_cuda_fit_get_state(self._h, window, chain, name.encode(), out.ctypes.data_as(c_dp), ln))
+        return out
+
+    def set_state(self, name: str, value, window: int = 0, chain: int = 0):
+        v = np.ascontiguousarray(np.asarray(value, dtype=np.float64).reshape(-1, order="F"))
+        check(self.L.bvhar_cuda_fit_set_state(self._h, window, chain, name.encode(), v.ctypes.data_as(c_dp), v.size))
+
+    # -- records ----------------------------------------------------------------------------
+    def record_names(self) -> List[str]:
+        buf = C.create_string_buffer(4096)
+        check(self.L.bvhar_cuda_fit_record_names(self._h, buf, 4096))
+        return [s for s in buf.value.decode().split("\n") if s]
+
+    def record(self, name: str, window: int = 0, chain: int = 0) -> np.ndarray:
+        r, c = C.c_int64(), C.c_int64()
+        check(self.L.bvhar_cuda_fit_record_dims(self._h, name.encode(), C.byref(r), C.byref(c)))
+        out = np.empty((r.value, c.value), order="F")
+        check(self.L.bvhar_cuda_fit_record(self._h, window, chain, name.encode(), out.ctypes.data_as(c_dp), r.value, c.value))
+        return out
+
+    def records(self, window: int = 0, chain: int = 0) -> Dict[str, np.ndarray]:
+        return {nm: self.record(nm, window, chain) for nm in self.record_names()}
+
+
+class _McmcRun:
+    """``bvhar::McmcRun<BaseMcmc, isGroup>`` (triangular.h:1194-1233)."""
+
+    _is_group = True
+    _sv: Optional[bool] = None
+
+    def __init__(self, num_chains, num_iter, num_burn, thin, x, y, param_cov, param_prior, param_intercept,
+                 param_init, prior_type, grp_id, own_id, cross_id, grp_mat, include_mean, seed_chain,
+                 display_progress=False, nthreads=1, device: int = 0, record_mask: int = REC_ALL):
+        is_sv = "initial_mean" in param_cov
+        if self._sv is not None and is_sv != self._sv:
+            raise ValueError("param_cov does not match the model class (initial_mean selects stochastic volatility)")
+        self._display = bool(display_progress)
+        self._packed = PackedFit(num_chains, num_iter, num_burn, thin, x, y, param_cov, param_prior, param_intercept,
+                                 param_init, prior_type, grp_id, own_id, cross_id, grp_mat, include_mean, seed_chain,
+                                 is_group=self._is_group, device=device, record_mask=record_mask)
+        self._fit = CudaFit(self._packed)
+        self._num_iter = int(num_iter)
+
+    def returnRecords(self) -> List[Dict[str, np.ndarray]]:
+        def progress(done, total):  # 5 % messages of triangular.h:1255-1274
+            if self._display:
+                print(f"[all chains] {done} / {total}", flush=True)
+            return False
+
+        try:
+            self._fit.run(progress if self._display else None)
+        except BvharCudaError as e:
+            if e.status != 3:  # numerical flags do not abort; everything else does
+                raise
+        return [self._fit.records(0, c) for c in range(self._packed.n_chains)]
+
+
+class McmcLdlt(_McmcRun):
+    _is_group, _sv = True, False
+
+
+class McmcLdltGrp(_McmcRun):
+    _is_group, _sv = False, False
+
+
+class SvMcmc(_McmcRun):
+    _is_group, _sv = True, True
+
+
+class SvGrpMcmc(_McmcRun):
+    _is_group, _sv = False, True
+
+
+# ------------------------------------------------------------------------------------------------
+def _stable_rows(coef: np.ndarray, dim: int, nrow: int, har: Optional[np.ndarray]) -> np.ndarray:
+    """``is_stable`` per draw (draw.h:1265-1295): companion-matrix spectral radius < 1."""
+    keep = np.zeros(coef.shape[0], dtype=bool)
+    for i in range(coef.shape[0]):
+        A = coef[i, : nrow * dim].reshape(nrow, dim, order="F")
+        if har is not None:
+            A = har.T @ A
+        m = A.shape[0]
+        comp = np.zeros((m, m))
+        comp[:dim, :] = A.T
+        comp[dim:, : m - dim] = np.eye(m - dim)
+        keep[i] = np.max(np.abs(np.linalg.eigvals(comp))) < 1
+    return keep
+
+
+def forecast_density(units: Sequence[Dict[str, np.ndarray]], last_obs: Sequence[np.ndarray], step: int, var_lag: int,
+                     include_mean: bool, sv_model: bool, seeds, har_trans: Optional[np.ndarray] = None, sv: bool = True,
+                     valid_vec: Optional[np.ndarray] = None, stable: bool = False, sparse: bool = False,
+                     coef_name: str = "alpha", device: int = 0):
+    """Density forecasts of independent units on the GPU (``McmcForecaster::forecastDensity``,
+    forecaster.h:55-85).  Returns (list of step x (S*k) matrices, step-wise ALPL per unit or None)."""
+    L = load_library()
+    dim = last_obs[0].shape[1]
+    sfx = "_sparse_record" if sparse else "_record"
+    coefs, contems, diags, sighs = [], [], [], []
+    nrow = None
+    for rec in units:
+        a = np.asarray(rec[coef_name + sfx], dtype=np.float64)
+        nrow = a.shape[1] // dim
+        full = np.hstack([a, np.asarray(rec["c" + sfx])]) if include_mean else a
+        sel = slice(None)
+        if stable:  # subsetStable, config.h:884-914, 1003-1034
+            hb = None if har_trans is None else har_trans[: 3 * dim, : var_lag * dim]
+            sel = _stable_rows(full, dim, nrow, hb)
+        coefs.append(full[sel]); contems.append(np.asarray(rec["a" + sfx])[sel])
+        if sv_model:
+            h = rec["h_last_record"] if "h_last_record" in rec else np.asarray(rec["h_record"])[:, -dim:]
+            diags.append(np.asarray(h)[sel]); sighs.append(np.asarray(rec["sigh_record"])[sel])
+        else:
+            diags.append(np.asarray(rec["d_record"])[sel])
+    S = coefs[0].shape[0]
+    if any(c.shape[0] != S for c in coefs):
+        raise ValueError("all units must keep the same number of draws")
+    if S == 0:
+        raise ValueError("No stable MCMC draws")
+    U = len(units)
+    f = lambda lst: np.ascontiguousarray(np.concatenate([np.asfortranarray(m).reshape(-1, order="F") for m in lst]))
+    coef_b, contem_b, diag_b = f(coefs), f(contems), f(diags)
+    sigh_b = f(sighs) if sv_model else None
+    last_b = f([np.asarray(lo, dtype=np.float64)[-var_lag:, :] for lo in last_obs])
+    D = ForecastDesc()
+    D.abi_version = _abi.ABI_VERSION; D.device = device; D.n_units = U; D.dim = dim; D.nrow_coef = nrow
+    D.include_mean = int(include_mean); D.cov_type = _abi.COV_SV if sv_model else _abi.COV_LDLT; D.step = int(step)
+    D.var_lag = int(var_lag); D.is_vhar = int(har_trans is not None); D.sv = int(sv); D.get_lpl = int(valid_vec is not None)
+    D.n_draws = S
+    keep = [coef_b, contem_b, diag_b, last_b]
+    D.coef_record = coef_b.ctypes.data_as(c_dp); D.contem_record = contem_b.ctypes.data_as(c_dp)
+    D.diag_record = diag_b.ctypes.data_as(c_dp); D.last_obs = last_b.ctypes.data_as(c_dp)
+    if sv_model:
+        keep.append(sigh_b); D.sigh_record = sigh_b.ctypes.data_as(c_dp)
+    if har_trans is not None:
+        ht = np.asfortranarray(har_trans, dtype=np.float64); keep.append(ht); D.har_trans = ht.ctypes.data_as(c_dp)
+    if valid_vec is not None:
+        vv = np.ascontiguousarray(valid_vec, dtype=np.float64); keep.append(vv); D.valid_vec = vv.ctypes.data_as(c_dp)
+    sd = np.ascontiguousarray(np.asarray(seeds, dtype=np.int64) & 0xFFFFFFFF, dtype=np.uint32); keep.append(sd)
+    D.seed = sd.ctypes.data_as(c_up)
+    out = np.empty(U * step * S * dim)
+    lpl = np.zeros(U * step) if valid_vec is not None else None
+    check(L.bvhar_cuda_forecast_density(C.byref(D), out.ctypes.data_as(c_dp), lpl.ctypes.data_as(c_dp) if lpl is not None else c_dp()))
+    dens = [out[u * step * S * dim:(u + 1) * step * S * dim].reshape(step, S * dim, order="F") for u in range(U)]
+    return dens, (lpl.reshape(U, step) if lpl is not None else None)

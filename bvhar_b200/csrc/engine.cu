@@ -1,0 +1,984 @@
+// engine.cu — host side of the Gibbs engine and the C-ABI of include/bvhar_cuda.h.
+//
+// Replaces the runners of the reference (McmcRun::fit/runGibbs, triangular.h:1217-1284;
+// McmcOutforecastRun::runGibbs, forecaster.h:755-790): instead of one OpenMP task per chain, every
+// (window, chain) unit advances together, one fixed kernel sequence per sweep on one CUDA stream,
+// captured once into a CUDA graph and replayed.  There is no CPU path: every entry point fails with
+// BVHAR_ERR_CUDA when no device is usable.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <set>
+#include <string>
+#include <vector>
+
+#include "../../include/bvhar_cuda.h"
+#include "engine.cuh"
+#include "gemm_tn.cuh"
+#include "kernels.h"
+
+using namespace bvhar;
+
+namespace {
+
+thread_local std::string g_err;
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+#define CU(expr)                                                                                         \
+  do {                                                                                                   \
+    cudaError_t e__ = (expr);                                                                            \
+    if (e__ != cudaSuccess)                                                                              \
+      return fail(BVHAR_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__));                  \
+  } while (0)
+
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  cudaError_t alloc(size_t count) {
+    n = count;
+    if (count == 0) return cudaSuccess;
+    cudaError_t e = cudaMalloc(&p, count * sizeof(T));
+    if (e == cudaSuccess) e = cudaMemset(p, 0, count * sizeof(T));
+    return e;
+  }
+  cudaError_t upload(const std::vector<T>& h) {
+    cudaError_t e = alloc(h.size());
+    if (e != cudaSuccess || h.empty()) return e;
+    return cudaMemcpy(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice);
+  }
+  ~DevBuf() {
+    if (p) cudaFree(p);
+  }
+};
+
+struct RecordSpec {
+  std::string name;
+  int cols;
+  double** slot;
+};
+
+}  // namespace
+
+struct bvhar_fit {
+  Dims D{};
+  DevPtrs P{};
+  PriorConst PC{};
+  RecPtrs R{};
+  int device = 0;
+  int num_iter = 0, num_burn = 0, thin = 1;
+  uint32_t rec_mask = 0;
+  cudaStream_t st = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaGraphExec_t graph[2] = {nullptr, nullptr};
+  double last_ms = 0.0;
+  int64_t launches = 0;
+  int launches_per_sweep[2] = {0, 0};
+  uint32_t sweeps_done = 0;
+  int rec_filled = 0;
+  size_t smem_limit = 0;
+  std::vector<int> win_row0, win_n;
+  std::vector<long long> win_off;
+  // device storage
+  DevBuf<double> X, XT, Y, XX, xnorm, XtX, XtY, prior_mean, sig_shp, sig_scl, sv_mean, sv_prec, ssvs_s1, ssvs_s2;
+  DevBuf<int> d_row0, d_n, grp_idx, grp_cnt, own_flag, flags, rec_row, gKg, gMg;
+  DevBuf<long long> d_off, g1_b, g1_c, g2_b, g2_c, g3_a, g3_b, g3_y;
+  DevBuf<uint32_t> seeds, iter;
+  DevBuf<double> H, Z, Dinv, YLD, S, Cm, Acoef, alpha, cvec, prec, contem, L, chol_prec, sparse_coef, sparse_contem;
+  DevBuf<double> lvol_init, lvol_sig, diag, znorm, hN[4], hG[3], hq[4], hs, vscratch, gscratch;
+  std::map<std::string, std::unique_ptr<DevBuf<double>>> rec;
+  std::vector<RecordSpec> rec_order;
+  GemmArgs g1{}, g2{}, g3{};
+  bool g3_aligned = true;
+  bool timed = false;
+
+  ~bvhar_fit() {
+    cudaSetDevice(device);
+    for (auto& g : graph)
+      if (g) cudaGraphExecDestroy(g);
+    if (ev0) cudaEventDestroy(ev0);
+    if (ev1) cudaEventDestroy(ev1);
+    if (st) cudaStreamDestroy(st);
+  }
+
+  int enqueue_sweep(bool record, bool count) {
+    int nl = 0;
+    CU(launch_bump(P, 1, 0, st)); ++nl;
+    if (D.prior != 1) { CU(launch_prior(D, P, PC, 0, st)); ++nl; }
+    if (D.sv) {
+      CU(launch_sv_prep(D, P, st)); ++nl;
+      CU(launch_dgemm_tn(g1, st)); ++nl;
+      CU(launch_dgemm_tn(g2, st)); ++nl;
+    }
+    CU(launch_coef(D, P, vscratch.p, smem_limit, st)); ++nl;
+    if (D.prior != 1) { CU(launch_prior(D, P, PC, 1, st)); ++nl; }
+    CU(launch_dgemm_tn(g3, st)); ++nl;
+    if (D.k > 1) { CU(launch_impact(D, P, gscratch.p, st)); ++nl; }
+    if (D.sv) { CU(launch_sv_state(D, P, st)); nl += 3; }
+    else { CU(launch_ldlt_state(D, P, st)); ++nl; }
+    if (record) {
+      CU(launch_record(D, P, R, st)); ++nl;
+      CU(launch_bump(P, 0, 1, st)); ++nl;
+    }
+    if (count) launches_per_sweep[record ? 1 : 0] = nl;
+    return 0;
+  }
+
+  // n sweeps: the first sweep of each kind runs eagerly (sets function attributes, validates the
+  // launch configuration), the sequence is then captured once and replayed.
+  int step(int n, bool record) {
+    CU(cudaSetDevice(device));
+    const int gi = record ? 1 : 0;
+    CU(cudaEventRecord(ev0, st));
+    for (int s = 0; s < n; ++s) {
+      if (record && rec_filled >= R.cap) return fail(BVHAR_ERR_BAD_ARG, "record buffers are full (num_iter - num_burn draws)");
+      if (!graph[gi] && launches_per_sweep[gi] == 0) {
+        int rc = enqueue_sweep(record, true);
+        if (rc) return rc;
+      } else {
+        if (!graph[gi]) {
+          cudaGraph_t g;
+          CU(cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
+          int rc = enqueue_sweep(record, false);
+          cudaError_t ce = cudaStreamEndCapture(st, &g);
+          if (rc) return rc;
+          CU(ce);
+          CU(cudaGraphInstantiate(&graph[gi], g, 0));
+          cudaGraphDestroy(g);
+        }
+        CU(cudaGraphLaunch(graph[gi], st));
+      }
+      launches += launches_per_sweep[gi];
+      ++sweeps_done;
+      if (record) ++rec_filled;
+    }
+    CU(cudaEventRecord(ev1, st));
+    timed = true;
+    return 0;
+  }
+  int sync() {
+    CU(cudaSetDevice(device));
+    CU(cudaStreamSynchronize(st));
+    if (timed) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, ev0, ev1) == cudaSuccess) last_ms = ms;
+      else cudaGetLastError();
+    }
+    std::vector<int> fl(D.U);
+    CU(cudaMemcpy(fl.data(), flags.p, sizeof(int) * D.U, cudaMemcpyDeviceToHost));
+    for (int u = 0; u < D.U; ++u)
+      if (fl[u]) {
+        char buf[160];
+        snprintf(buf, sizeof buf, "non-positive-definite precision in unit %d (window %d, chain %d), flag %d", u, u / D.C, u % D.C, fl[u]);
+        return fail(BVHAR_ERR_NUMERICAL, buf);
+      }
+    return 0;
+  }
+};
+
+namespace {
+
+int round_even(int x) { return (x + 1) & ~1; }
+
+int build(const bvhar_fit_desc* d, bvhar_fit** out) {
+  if (!d || !out) return fail(BVHAR_ERR_BAD_ARG, "null descriptor");
+  if (d->abi_version != BVHAR_CUDA_ABI_VERSION) return fail(BVHAR_ERR_BAD_ARG, "descriptor ABI version mismatch");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(BVHAR_ERR_CUDA, "no CUDA device available: the bvhar_b200 engine has no CPU fallback");
+  if (d->device < 0 || d->device >= ndev) return fail(BVHAR_ERR_BAD_ARG, "device ordinal out of range");
+  if (d->n_windows < 1 || d->n_chains < 1 || d->dim < 1 || d->dim_design < 1) return fail(BVHAR_ERR_BAD_ARG, "empty problem");
+  if (d->prior_type < 1 || d->prior_type > 7) return fail(BVHAR_ERR_BAD_ARG, "prior_type must be 1..7");
+  if (d->num_burn < 0 || d->num_iter < d->num_burn) return fail(BVHAR_ERR_BAD_ARG, "need 0 <= num_burn <= num_iter");
+  if (!d->x || !d->y || !d->win_row0 || !d->win_nrow || !d->grp_mat || !d->grp_id || !d->init || !d->seed_chain || !d->sig_shape || !d->sig_scale)
+    return fail(BVHAR_ERR_BAD_ARG, "missing required pointer in descriptor");
+  CU(cudaSetDevice(d->device));
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, d->device));
+  if (prop.major < 10) return fail(BVHAR_ERR_CUDA, "bvhar_b200 is built for sm_100a (B200) only");
+
+  std::unique_ptr<bvhar_fit> F(new bvhar_fit);
+  F->device = d->device;
+  F->smem_limit = prop.sharedMemPerBlockOptin;
+  F->num_iter = d->num_iter; F->num_burn = d->num_burn; F->thin = d->thin < 1 ? 1 : d->thin;
+  F->rec_mask = d->record_mask;
+  Dims& D = F->D;
+  D.W = d->n_windows; D.C = d->n_chains; D.U = D.W * D.C;
+  D.k = d->dim; D.d = d->dim_design; D.mean = d->include_mean != 0;
+  D.sv = d->cov_type == BVHAR_COV_SV; D.ggl = d->is_group != 0; D.prior = d->prior_type;
+  D.q = D.k * (D.k - 1) / 2;
+  D.N = D.k * D.d - (D.mean ? D.k : 0);
+  D.nrow = D.N / D.k;
+  D.G = d->n_grp;
+  D.Pp = D.d * (D.d + 1) / 2;
+  D.ldS = round_even(D.Pp);
+  D.ldX = round_even(D.d);
+  D.ldXX = round_even(D.Pp);
+  D.T = (int)d->n_rows_total;
+  D.ldT = round_even(D.T);
+  D.M = D.C * D.k;
+  D.ldM = round_even(D.M);
+  if (D.G < 1 || D.G > 64) return fail(BVHAR_ERR_UNSUPPORTED, "number of coefficient groups must be in 1..64");
+  if (D.nrow * D.k != D.N) return fail(BVHAR_ERR_BAD_ARG, "dim_design inconsistent with dim / include_mean");
+  const bvhar_prior_params& pp = d->prior;
+  PriorConst& PC = F->PC;
+  PC.hmn_shape = pp.hmn_shape; PC.hmn_rate = pp.hmn_rate; PC.hmn_grid = pp.hmn_grid_size;
+  PC.ssvs_chol_s1 = pp.ssvs_chol_s1; PC.ssvs_chol_s2 = pp.ssvs_chol_s2;
+  PC.ssvs_coef_slab_shape = pp.ssvs_coef_slab_shape; PC.ssvs_coef_slab_scl = pp.ssvs_coef_slab_scl;
+  PC.ssvs_chol_slab_shape = pp.ssvs_chol_slab_shape; PC.ssvs_chol_slab_scl = pp.ssvs_chol_slab_scl;
+  PC.ssvs_coef_grid = pp.ssvs_coef_grid; PC.ssvs_chol_grid = pp.ssvs_chol_grid;
+  PC.ng_shape_sd = pp.ng_shape_sd; PC.ng_group_shape = pp.ng_group_shape; PC.ng_group_scale = pp.ng_group_scale;
+  PC.ng_global_shape = pp.ng_global_shape; PC.ng_global_scale = pp.ng_global_scale;
+  PC.ng_cg_shape = pp.ng_contem_global_shape; PC.ng_cg_scale = pp.ng_contem_global_scale;
+  PC.dl_grid = pp.dl_grid_size; PC.dl_shape = pp.dl_shape; PC.dl_scale = pp.dl_scale;
+  PC.gdp_grid_shape = pp.gdp_grid_shape; PC.gdp_grid_rate = pp.gdp_grid_rate;
+  const int maxgrid = std::max({PC.hmn_grid, PC.ssvs_coef_grid, PC.ssvs_chol_grid, PC.dl_grid, PC.gdp_grid_shape, PC.gdp_grid_rate});
+  if (maxgrid > 512) return fail(BVHAR_ERR_UNSUPPORTED, "griddy-Gibbs grids are limited to 512 points");
+  auto need_grid = [&](int g, const char* nm) { return g < 1 ? fail(BVHAR_ERR_BAD_ARG, std::string(nm) + " must be >= 1") : 0; };
+  if (D.prior == 2 && (need_grid(PC.ssvs_coef_grid, "coef_grid") || need_grid(PC.ssvs_chol_grid, "chol_grid"))) return BVHAR_ERR_BAD_ARG;
+  if (D.prior == 6 && need_grid(PC.dl_grid, "grid_size")) return BVHAR_ERR_BAD_ARG;
+  if (D.prior == 7 && (need_grid(PC.gdp_grid_shape, "grid_shape") || need_grid(PC.gdp_grid_rate, "grid_rate"))) return BVHAR_ERR_BAD_ARG;
+
+  // windows
+  F->win_row0.assign(d->win_row0, d->win_row0 + D.W);
+  F->win_n.assign(d->win_nrow, d->win_nrow + D.W);
+  F->win_off.resize(D.W);
+  long long off = 0;
+  D.nmax = 0;
+  for (int w = 0; w < D.W; ++w) {
+    if (F->win_n[w] < 1 || F->win_row0[w] < 0 || F->win_row0[w] + F->win_n[w] > D.T)
+      return fail(BVHAR_ERR_BAD_ARG, "window rows outside the design matrix");
+    F->win_off[w] = off;
+    off += (long long)F->win_n[w] * D.ldM;
+    D.nmax = std::max(D.nmax, F->win_n[w]);
+  }
+  const long long tm_total = off;
+
+  const int k = D.k, dd = D.d, N = D.N, q = D.q, G = D.G, U = D.U, nrow = D.nrow;
+  const int64_t ld = d->n_rows_total;
+  // ---- shared data ----
+  std::vector<double> hX((size_t)D.T * D.ldX, 0.0), hXT((size_t)dd * D.ldT, 0.0), hY((size_t)D.T * k);
+  for (int a = 0; a < dd; ++a)
+    for (int t = 0; t < D.T; ++t) {
+      const double v = d->x[(size_t)a * ld + t];
+      hX[(size_t)t * D.ldX + a] = v;
+      hXT[(size_t)a * D.ldT + t] = v;
+    }
+  for (int j = 0; j < k; ++j)
+    for (int t = 0; t < D.T; ++t) hY[(size_t)t * k + j] = d->y[(size_t)j * ld + t];
+  CU(F->X.upload(hX)); CU(F->XT.upload(hXT)); CU(F->Y.upload(hY));
+  std::vector<double> hxn((size_t)D.W * dd, 0.0);
+  for (int w = 0; w < D.W; ++w)
+    for (int a = 0; a < dd; ++a) {
+      double s = 0;
+      const double* col = d->x + (size_t)a * ld + F->win_row0[w];
+      for (int t = 0; t < F->win_n[w]; ++t) s += col[t] * col[t];
+      hxn[(size_t)w * dd + a] = s;
+    }
+  CU(F->xnorm.upload(hxn));
+  CU(F->d_row0.upload(F->win_row0)); CU(F->d_n.upload(F->win_n)); CU(F->d_off.upload(F->win_off));
+  // groups
+  std::vector<int> gidx(N), gcnt(G, 0), ownf(N, 0);
+  std::set<int> own(d->own_id, d->own_id + d->n_own);
+  for (int e = 0; e < N; ++e) {
+    int g = -1;
+    for (int t = 0; t < G; ++t)
+      if (d->grp_id[t] == d->grp_mat[e]) { g = t; break; }
+    if (g < 0) return fail(BVHAR_ERR_BAD_ARG, "grp_mat holds an id that is not in grp_id");
+    gidx[e] = g;
+    ++gcnt[g];
+    ownf[e] = own.count(d->grp_mat[e]) ? 1 : 0;
+  }
+  CU(F->grp_idx.upload(gidx)); CU(F->grp_cnt.upload(gcnt)); CU(F->own_flag.upload(ownf));
+  // prior mean / fixed precisions, internal (j*d + a) layout
+  std::vector<double> pmean((size_t)k * dd, 0.0), pprec0((size_t)k * dd, 0.0);
+  const bool minn = D.prior == 1 || D.prior == 4;
+  if (minn && (!pp.minn_prior_mean || !pp.minn_prior_prec)) return fail(BVHAR_ERR_BAD_ARG, "Minnesota prior moments missing");
+  for (int j = 0; j < k; ++j) {
+    for (int a = 0; a < nrow; ++a)
+      if (minn) { pmean[(size_t)j * dd + a] = pp.minn_prior_mean[j * nrow + a]; pprec0[(size_t)j * dd + a] = pp.minn_prior_prec[j * nrow + a]; }
+    if (D.mean) {
+      if (!d->mean_non) return fail(BVHAR_ERR_BAD_ARG, "mean_non missing");
+      pmean[(size_t)j * dd + nrow] = d->mean_non[j];
+      pprec0[(size_t)j * dd + nrow] = 1.0 / (d->sd_non * d->sd_non);
+    }
+  }
+  CU(F->prior_mean.upload(pmean));
+  CU(F->sig_shp.upload(std::vector<double>(d->sig_shape, d->sig_shape + k)));
+  CU(F->sig_scl.upload(std::vector<double>(d->sig_scale, d->sig_scale + k)));
+  if (D.sv) {
+    if (!d->sv_init_mean || !d->sv_init_prec) return fail(BVHAR_ERR_BAD_ARG, "SV prior (initial_mean / initial_prec) missing");
+    CU(F->sv_mean.upload(std::vector<double>(d->sv_init_mean, d->sv_init_mean + k)));
+    std::vector<double> pr((size_t)k * k);
+    for (int i = 0; i < k; ++i)
+      for (int m = 0; m < k; ++m) pr[(size_t)i * k + m] = d->sv_init_prec[(size_t)m * k + i];
+    CU(F->sv_prec.upload(pr));
+  }
+  if (D.prior == 2) {
+    if (!pp.ssvs_coef_s1 || !pp.ssvs_coef_s2) return fail(BVHAR_ERR_BAD_ARG, "SSVS coef_s1 / coef_s2 missing");
+    CU(F->ssvs_s1.upload(std::vector<double>(pp.ssvs_coef_s1, pp.ssvs_coef_s1 + G)));
+    CU(F->ssvs_s2.upload(std::vector<double>(pp.ssvs_coef_s2, pp.ssvs_coef_s2 + G)));
+  }
+  std::vector<uint32_t> hseed(d->seed_chain, d->seed_chain + U);
+  CU(F->seeds.upload(hseed));
+  CU(F->iter.alloc(1)); CU(F->rec_row.alloc(1)); CU(F->flags.alloc(U));
+
+  // ---- per-unit state from the chain inits (McmcTriangular ctor tri.h:40-71 and prior ctors) ----
+  std::vector<double> hA((size_t)D.W * dd * D.ldM, 0.0), halpha((size_t)U * N), hc((size_t)U * k, 0.0), hprec((size_t)U * k * dd);
+  std::vector<double> hcontem((size_t)U * q), hL((size_t)U * k * k, 0.0), hcp((size_t)U * q, 1.0);
+  std::vector<double> hH, hli, hls, hdiag;
+  if (D.sv) { hH.assign((size_t)tm_total, 0.0); hli.resize((size_t)U * k); hls.resize((size_t)U * k); }
+  else hdiag.resize((size_t)U * k);
+  std::vector<double> hhN[4], hhG[3], hhq[4], hhs((size_t)U * HS_SLOTS, 0.0);
+  for (auto& v : hhN) v.assign((size_t)U * N, 0.0);
+  for (auto& v : hhG) v.assign((size_t)U * G, 0.0);
+  for (auto& v : hhq) v.assign((size_t)U * q, 0.0);
+  for (int w = 0; w < D.W; ++w)
+    for (int c = 0; c < D.C; ++c) {
+      const int u = w * D.C + c;
+      const bvhar_chain_init& in = d->init[c];
+      if (!in.init_coef || (q > 0 && !in.init_contem)) return fail(BVHAR_ERR_BAD_ARG, "init_coef / init_contem missing");
+      for (int j = 0; j < k; ++j)
+        for (int a = 0; a < dd; ++a) {
+          const double v = in.init_coef[(size_t)j * dd + a];
+          hA[((size_t)w * dd + a) * D.ldM + (size_t)c * k + j] = v;
+          if (a < nrow) halpha[(size_t)u * N + j * nrow + a] = v;
+          else hc[(size_t)u * k + j] = v;
+          hprec[(size_t)u * k * dd + j * dd + a] = pprec0[(size_t)j * dd + a];
+        }
+      for (int e = 0; e < q; ++e) hcontem[(size_t)u * q + e] = in.init_contem[e];
+      for (int i = 0; i < k; ++i) {
+        hL[((size_t)u * k + i) * k + i] = 1.0;
+        for (int m = 0; m < i; ++m) hL[((size_t)u * k + i) * k + m] = in.init_contem[i * (i - 1) / 2 + m];
+      }
+      if (D.sv) {
+        if (!in.lvol_init || !in.lvol_sig) return fail(BVHAR_ERR_BAD_ARG, "lvol_init / lvol_sig missing");
+        const bool rep = d->lvol_from_init || !in.lvol;
+        if (!rep && F->win_n[w] != F->win_n[0]) return fail(BVHAR_ERR_BAD_ARG, "lvol inits need equal window lengths (use lvol_from_init)");
+        for (int i = 0; i < k; ++i) {
+          hli[(size_t)u * k + i] = in.lvol_init[i];
+          hls[(size_t)u * k + i] = in.lvol_sig[i];
+          for (int t = 0; t < F->win_n[w]; ++t)
+            hH[(size_t)F->win_off[w] + (size_t)t * D.ldM + (size_t)c * k + i] = rep ? in.lvol_init[i] : in.lvol[(size_t)i * F->win_n[0] + t];
+        }
+      } else {
+        if (!in.init_diag) return fail(BVHAR_ERR_BAD_ARG, "init_diag missing");
+        for (int i = 0; i < k; ++i) hdiag[(size_t)u * k + i] = in.init_diag[i];
+      }
+      double* s = &hhs[(size_t)u * HS_SLOTS];
+      auto cpN = [&](int slot, const double* src) { if (src) std::copy(src, src + N, hhN[slot].begin() + (size_t)u * N); };
+      auto cpG = [&](int slot, const double* src) { if (src) std::copy(src, src + G, hhG[slot].begin() + (size_t)u * G); };
+      auto cpq = [&](int slot, const double* src) { if (src) std::copy(src, src + q, hhq[slot].begin() + (size_t)u * q); };
+      auto need = [&](const void* p, const char* nm) { return p ? 0 : fail(BVHAR_ERR_BAD_ARG, std::string("param_init lacks ") + nm); };
+      switch (D.prior) {
+        case 4:  // tri.h:478-494
+          s[HS_OWN_LAMBDA] = in.own_lambda; s[HS_CROSS_LAMBDA] = in.cross_lambda; s[HS_CONTEM_LAMBDA] = in.contem_lambda;
+          for (int j = 0; j < k; ++j)
+            for (int a = 0; a < nrow; ++a) hprec[(size_t)u * k * dd + j * dd + a] /= in.own_lambda;
+          for (int e = 0; e < q; ++e) hcp[(size_t)u * q + e] /= in.contem_lambda;
+          break;
+        case 2:  // tri.h:563-577
+          if (need(in.coef_dummy, "init_coef_dummy") || need(in.coef_mixture, "coef_mixture") || need(in.coef_slab, "coef_slab") ||
+              (q > 0 && (need(in.chol_mixture, "chol_mixture") || need(in.contem_slab, "contem_slab")))) return BVHAR_ERR_BAD_ARG;
+          cpN(0, in.coef_dummy); cpN(1, in.coef_slab); cpG(0, in.coef_mixture);
+          for (int e = 0; e < q; ++e) hhq[0][(size_t)u * q + e] = 1.0;
+          cpq(1, in.contem_slab); cpq(2, in.chol_mixture);
+          s[HS_SPIKE] = in.coef_spike_scl; s[HS_CONTEM_SPIKE] = in.coef_spike_scl;  // tri.h:569
+          break;
+        case 3:  // tri.h:659-669
+          if (need(in.local_sparsity, "local_sparsity") || need(in.group_sparsity, "group_sparsity") ||
+              (q > 0 && need(in.contem_local_sparsity, "contem_local_sparsity"))) return BVHAR_ERR_BAD_ARG;
+          cpN(0, in.local_sparsity); cpG(0, in.group_sparsity); cpq(0, in.contem_local_sparsity);
+          s[HS_GLOBAL] = D.ggl ? in.global_sparsity : 1.0; s[HS_CONTEM_GLOBAL] = in.contem_global_sparsity;
+          break;
+        case 5:  // tri.h:757-770
+          if (need(in.local_sparsity, "local_sparsity") || need(in.group_sparsity, "group_sparsity") || need(in.local_shape, "local_shape") ||
+              (q > 0 && need(in.contem_local_sparsity, "contem_local_sparsity"))) return BVHAR_ERR_BAD_ARG;
+          cpN(0, in.local_sparsity); cpG(0, in.group_sparsity); cpG(1, in.local_shape);
+          for (int e = 0; e < q; ++e) hhq[0][(size_t)u * q + e] = in.contem_global_sparsity * in.contem_local_sparsity[e];
+          s[HS_GLOBAL] = D.ggl ? in.global_sparsity : 1.0; s[HS_CONTEM_GLOBAL] = in.contem_global_sparsity; s[HS_CONTEM_SHAPE] = in.contem_shape;
+          break;
+        case 6:  // tri.h:852-863
+          if (need(in.local_sparsity, "local_sparsity") || (q > 0 && need(in.contem_local_sparsity, "contem_local_sparsity"))) return BVHAR_ERR_BAD_ARG;
+          cpN(0, in.local_sparsity); cpq(0, in.contem_local_sparsity);
+          s[HS_GLOBAL] = D.ggl ? in.global_sparsity : 1.0; s[HS_CONTEM_GLOBAL] = in.contem_global_sparsity;
+          break;
+        case 7:  // tri.h:941-951
+          if (need(in.local_sparsity, "local_sparsity") || need(in.group_rate, "group_rate") ||
+              (q > 0 && (need(in.contem_local_sparsity, "contem_local_sparsity") || need(in.contem_rate, "contem_rate")))) return BVHAR_ERR_BAD_ARG;
+          cpN(0, in.local_sparsity); cpG(0, in.group_rate); cpq(0, in.contem_local_sparsity); cpq(1, in.contem_rate);
+          s[HS_GSHAPE] = in.gamma_shape; s[HS_GRATE] = in.gamma_rate; s[HS_CGSHAPE] = in.contem_gamma_shape; s[HS_CGRATE] = in.contem_gamma_rate;
+          break;
+        default: break;
+      }
+    }
+  CU(F->Acoef.upload(hA)); CU(F->alpha.upload(halpha)); CU(F->cvec.upload(hc)); CU(F->prec.upload(hprec));
+  CU(F->contem.upload(hcontem)); CU(F->L.upload(hL)); CU(F->chol_prec.upload(hcp));
+  CU(F->sparse_coef.alloc((size_t)U * dd * k)); CU(F->sparse_contem.alloc((size_t)U * q)); CU(F->znorm.alloc((size_t)U * k));
+  CU(F->Z.alloc((size_t)tm_total));
+  if (D.sv) {
+    CU(F->H.upload(hH)); CU(F->lvol_init.upload(hli)); CU(F->lvol_sig.upload(hls));
+    CU(F->Dinv.alloc((size_t)tm_total)); CU(F->YLD.alloc((size_t)tm_total));
+    CU(F->S.alloc((size_t)U * k * D.ldS)); CU(F->Cm.alloc((size_t)U * k * D.ldX));
+    CU(F->XX.alloc((size_t)D.T * D.ldXX));
+  } else {
+    CU(F->diag.upload(hdiag));
+  }
+  for (int i = 0; i < 4; ++i) CU(F->hN[i].upload(hhN[i]));
+  for (int i = 0; i < 3; ++i) CU(F->hG[i].upload(hhG[i]));
+  for (int i = 0; i < 4; ++i) CU(F->hq[i].upload(hhq[i]));
+  CU(F->hs.upload(hhs));
+
+  DevPtrs& P = F->P;
+  P.X = F->X.p; P.XT = F->XT.p; P.Y = F->Y.p; P.XX = F->XX.p; P.xnorm = F->xnorm.p;
+  P.win_row0 = F->d_row0.p; P.win_n = F->d_n.p; P.win_off = F->d_off.p;
+  P.grp_idx = F->grp_idx.p; P.grp_cnt = F->grp_cnt.p; P.own_flag = F->own_flag.p; P.prior_mean = F->prior_mean.p;
+  P.sig_shp = F->sig_shp.p; P.sig_scl = F->sig_scl.p; P.sv_mean = F->sv_mean.p; P.sv_prec = F->sv_prec.p;
+  P.ssvs_s1 = F->ssvs_s1.p; P.ssvs_s2 = F->ssvs_s2.p; P.seeds = F->seeds.p;
+  P.H = F->H.p; P.Z = F->Z.p; P.Dinv = F->Dinv.p; P.YLD = F->YLD.p;
+  P.S = F->S.p; P.Cm = F->Cm.p; P.Acoef = F->Acoef.p; P.alpha = F->alpha.p; P.cvec = F->cvec.p; P.prec = F->prec.p;
+  P.contem = F->contem.p; P.L = F->L.p; P.chol_prec = F->chol_prec.p; P.sparse_coef = F->sparse_coef.p;
+  P.sparse_contem = F->sparse_contem.p; P.lvol_init = F->lvol_init.p; P.lvol_sig = F->lvol_sig.p; P.diag = F->diag.p;
+  P.znorm = F->znorm.p;
+  P.hN0 = F->hN[0].p; P.hN1 = F->hN[1].p; P.hN2 = F->hN[2].p; P.hN3 = F->hN[3].p;
+  P.hG0 = F->hG[0].p; P.hG1 = F->hG[1].p; P.hG2 = F->hG[2].p;
+  P.hq0 = F->hq[0].p; P.hq1 = F->hq[1].p; P.hq2 = F->hq[2].p; P.hq3 = F->hq[3].p;
+  P.hs = F->hs.p; P.iter = F->iter.p; P.rec_row = F->rec_row.p; P.flags = F->flags.p;
+
+  CU(cudaStreamCreateWithFlags(&F->st, cudaStreamNonBlocking));
+  CU(cudaEventCreate(&F->ev0)); CU(cudaEventCreate(&F->ev1));
+
+  // ---- contraction descriptors ----
+  std::vector<long long> g1b(D.W), g1c(D.W), g2b(D.W), g2c(D.W), g3a(D.W), g3b(D.W), g3y(D.W);
+  for (int w = 0; w < D.W; ++w) {
+    g1b[w] = (long long)F->win_row0[w] * D.ldXX; g1c[w] = (long long)w * D.M * D.ldS;
+    g2b[w] = (long long)F->win_row0[w] * D.ldX;  g2c[w] = (long long)w * D.M * D.ldX;
+    g3a[w] = F->win_row0[w]; g3b[w] = (long long)w * dd * D.ldM; g3y[w] = (long long)F->win_row0[w] * k;
+    if (F->win_row0[w] & 1) F->g3_aligned = false;
+  }
+  CU(F->g1_b.upload(g1b)); CU(F->g1_c.upload(g1c)); CU(F->g2_b.upload(g2b)); CU(F->g2_c.upload(g2c));
+  CU(F->g3_a.upload(g3a)); CU(F->g3_b.upload(g3b)); CU(F->g3_y.upload(g3y));
+  CU(F->gKg.upload(F->win_n)); CU(F->gMg.upload(F->win_n));
+  GemmArgs& g1 = F->g1;
+  g1.A = P.Dinv; g1.B = P.XX; g1.C = P.S; g1.M = D.M; g1.N = D.Pp; g1.K = 0; g1.lda = D.ldM; g1.ldb = D.ldXX; g1.ldc = D.ldS;
+  g1.groups = D.W; g1.a_off = F->d_off.p; g1.b_off = F->g1_b.p; g1.c_off = F->g1_c.p; g1.Kg = F->gKg.p; g1.Mg = nullptr;
+  g1.epi = EPI_STORE; g1.aligned16 = 1;
+  GemmArgs& g2 = F->g2;
+  g2 = g1;
+  g2.A = P.YLD; g2.B = P.X; g2.C = P.Cm; g2.N = dd; g2.ldb = D.ldX; g2.ldc = D.ldX; g2.b_off = F->g2_b.p; g2.c_off = F->g2_c.p;
+  GemmArgs& g3 = F->g3;
+  g3.A = P.XT; g3.B = P.Acoef; g3.C = P.Z; g3.M = D.nmax; g3.N = D.M; g3.K = dd; g3.lda = D.ldT; g3.ldb = D.ldM; g3.ldc = D.ldM;
+  g3.groups = D.W; g3.a_off = F->g3_a.p; g3.b_off = F->g3_b.p; g3.c_off = F->d_off.p; g3.Kg = nullptr; g3.Mg = F->gMg.p;
+  g3.epi = EPI_Y_MINUS; g3.Y = P.Y; g3.y_off = F->g3_y.p; g3.ldy = k; g3.ymod = k; g3.aligned16 = F->g3_aligned ? 1 : 0;
+
+  // ---- scratch + setup kernels ----
+  bool need_v = false;
+  int ch_plan = 0;
+  if (!coef_plan(D, F->smem_limit, &ch_plan, &need_v))
+    return fail(BVHAR_ERR_UNSUPPORTED, "dim_design too large for the shared-memory Cholesky of this build (packed d(d+1)/2 doubles must fit 227 KB)");
+  if (need_v) CU(F->vscratch.alloc((size_t)U * 2 * k * dd));
+  CU(F->gscratch.alloc((size_t)U * impact_gsize(D)));
+  if ((size_t)(2 * 16 * k + 8 * (k * (k + 1) / 2 + 3 * k)) * sizeof(double) > F->smem_limit)
+    return fail(BVHAR_ERR_UNSUPPORTED, "dim too large for the shared-memory contemporaneous draw of this build");
+  if (D.sv) CU(launch_build_xx(D, P, F->XX.p, F->st));
+  else {
+    // X'X (packed) and X'Y per window through the same contraction kernel
+    CU(F->XtX.alloc((size_t)D.W * D.ldS)); CU(F->XtY.alloc((size_t)D.W * dd * k));
+    DevBuf<double> full;
+    CU(full.alloc((size_t)D.W * dd * dd));
+    std::vector<long long> bo(D.W), co(D.W), yo(D.W), cy(D.W);
+    for (int w = 0; w < D.W; ++w) { bo[w] = (long long)F->win_row0[w] * D.ldX; co[w] = (long long)w * dd * dd; yo[w] = (long long)F->win_row0[w] * k; cy[w] = (long long)w * dd * k; }
+    DevBuf<long long> dbo, dco, dyo, dcy;
+    CU(dbo.upload(bo)); CU(dco.upload(co)); CU(dyo.upload(yo)); CU(dcy.upload(cy));
+    GemmArgs g{};
+    g.A = P.X; g.B = P.X; g.C = full.p; g.M = dd; g.N = dd; g.lda = D.ldX; g.ldb = D.ldX; g.ldc = dd; g.groups = D.W;
+    g.a_off = dbo.p; g.b_off = dbo.p; g.c_off = dco.p; g.Kg = F->gKg.p; g.epi = EPI_STORE; g.aligned16 = 1;
+    CU(launch_dgemm_tn(g, F->st));
+    GemmArgs gy = g;
+    gy.B = P.Y; gy.b_off = dyo.p; gy.ldb = k; gy.N = k; gy.C = F->XtY.p; gy.ldc = k; gy.c_off = dcy.p; gy.aligned16 = (k % 2 == 0) ? 1 : 0;
+    CU(launch_dgemm_tn(gy, F->st));
+    CU(cudaStreamSynchronize(F->st));
+    std::vector<double> hf((size_t)D.W * dd * dd), hp((size_t)D.W * D.ldS, 0.0);
+    CU(cudaMemcpy(hf.data(), full.p, hf.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    for (int w = 0; w < D.W; ++w)
+      for (int a = 0; a < dd; ++a)
+        for (int b = 0; b <= a; ++b) hp[(size_t)w * D.ldS + a * (a + 1) / 2 + b] = hf[(size_t)w * dd * dd + a * dd + b];
+    CU(cudaMemcpy(F->XtX.p, hp.data(), hp.size() * sizeof(double), cudaMemcpyHostToDevice));
+    P.XtX = F->XtX.p; P.XtY = F->XtY.p;
+  }
+  // latent_innov = y - x * coef_mat (tri.h:57)
+  CU(launch_dgemm_tn(F->g3, F->st));
+  CU(cudaStreamSynchronize(F->st));
+
+  // ---- record buffers ----
+  RecPtrs& R = F->R;
+  std::memset(&R, 0, sizeof R);
+  R.cap = F->num_iter - F->num_burn;
+  const uint32_t m = F->rec_mask;
+  auto add = [&](const char* nm, int cols, double** slot) -> int {
+    auto buf = std::make_unique<DevBuf<double>>();
+    CU(buf->alloc((size_t)U * std::max(R.cap, 1) * cols));
+    *slot = buf->p;
+    F->rec[nm] = std::move(buf);
+    F->rec_order.push_back({nm, cols, slot});
+    return 0;
+  };
+#define ADD(nm, cols, slot) do { int rc__ = add(nm, cols, slot); if (rc__) return rc__; } while (0)
+  if (m & BVHAR_REC_COEF) {
+    ADD("alpha_record", N, &R.alpha); ADD("a_record", q, &R.a);
+    if (D.mean) ADD("c_record", k, &R.c);
+    if (!D.sv) ADD("d_record", k, &R.d);
+  }
+  if (D.sv) {
+    if (m & BVHAR_REC_LVOL) ADD("h_record", D.nmax * k, &R.h);
+    else if (m & BVHAR_REC_LVOL_LAST) ADD("h_last_record", k, &R.h_last);
+    if (m & BVHAR_REC_COEF) { ADD("h0_record", k, &R.h0); ADD("sigh_record", k, &R.sigh); }
+  }
+  if (m & BVHAR_REC_SPARSE) {
+    ADD("alpha_sparse_record", N, &R.alpha_sparse); ADD("a_sparse_record", q, &R.a_sparse);
+    if (D.mean) ADD("c_sparse_record", k, &R.c_sparse);
+  }
+  if (m & BVHAR_REC_PRIOR) {
+    switch (D.prior) {
+      case 2: ADD("gamma_record", N, &R.gamma); break;
+      case 3: ADD("lambda_record", N, &R.lambda); ADD("eta_record", G, &R.eta); ADD("tau_record", 1, &R.tau); ADD("kappa_record", N, &R.kappa); break;
+      case 5: ADD("lambda_record", N, &R.lambda); ADD("eta_record", G, &R.eta); ADD("tau_record", 1, &R.tau); break;
+      case 6: ADD("lambda_record", N, &R.lambda); ADD("tau_record", 1, &R.tau); break;
+      default: break;
+    }
+  }
+#undef ADD
+  *out = F.release();
+  return 0;
+}
+
+// ---- state views (names of the reference's members; column-major as Eigen) ----
+struct View {
+  enum Kind { UNIT_VEC, COEF_MAT, CHOL, TM, SQRT_SV, PREC, SCALAR } kind;
+  double* base;   // device base (unit-major vector or [t][m] array)
+  int len;        // per-unit length for UNIT_VEC
+  int slot;       // SCALAR slot
+};
+bool find_view(bvhar_fit* F, const std::string& nm, View& v, int64_t& len) {
+  const Dims& D = F->D;
+  DevPtrs& P = F->P;
+  auto uv = [&](double* b, int l) { v = {View::UNIT_VEC, b, l, 0}; len = l; return true; };
+  auto sc = [&](int slot) { v = {View::SCALAR, P.hs, 1, slot}; len = 1; return true; };
+  if (nm == "coef_mat") { v = {View::COEF_MAT, P.Acoef, 0, 0}; len = (int64_t)D.d * D.k; return true; }
+  if (nm == "chol_lower") { v = {View::CHOL, P.L, 0, 0}; len = (int64_t)D.k * D.k; return true; }
+  if (nm == "latent_innov") { v = {View::TM, P.Z, 0, 0}; len = -1; return true; }
+  if (nm == "lvol_draw" && D.sv) { v = {View::TM, P.H, 0, 0}; len = -1; return true; }
+  if (nm == "sqrt_sv" && D.sv) { v = {View::SQRT_SV, P.Dinv, 0, 0}; len = -1; return true; }
+  if (nm == "prior_alpha_prec") { v = {View::PREC, P.prec, 0, 0}; len = (int64_t)D.k * D.d; return true; }
+  if (nm == "contem_coef") return uv(P.contem, D.q);
+  if (nm == "prior_chol_prec") return uv(P.chol_prec, D.q);
+  if (nm == "sparse_coef") return uv(P.sparse_coef, D.d * D.k);
+  if (nm == "sparse_contem") return uv(P.sparse_contem, D.q);
+  if (nm == "alpha") return uv(P.alpha, D.N);
+  if (nm == "diag_vec" && !D.sv) return uv(P.diag, D.k);
+  if (nm == "lvol_init" && D.sv) return uv(P.lvol_init, D.k);
+  if (nm == "lvol_sig" && D.sv) return uv(P.lvol_sig, D.k);
+  switch (D.prior) {
+    case 2:
+      if (nm == "coef_dummy") return uv(P.hN0, D.N);
+      if (nm == "coef_slab") return uv(P.hN1, D.N);
+      if (nm == "coef_weight") return uv(P.hG0, D.G);
+      if (nm == "contem_dummy") return uv(P.hq0, D.q);
+      if (nm == "contem_slab") return uv(P.hq1, D.q);
+      if (nm == "contem_weight") return uv(P.hq2, D.q);
+      if (nm == "spike_scl") return sc(HS_SPIKE);
+      if (nm == "contem_spike_scl") return sc(HS_CONTEM_SPIKE);
+      break;
+    case 3:
+      if (nm == "local_lev") return uv(P.hN0, D.N);
+      if (nm == "latent_local") return uv(P.hN1, D.N);
+      if (nm == "shrink_fac") return uv(P.hN2, D.N);
+      if (nm == "group_lev") return uv(P.hG0, D.G);
+      if (nm == "latent_group") return uv(P.hG1, D.G);
+      if (nm == "contem_local_lev") return uv(P.hq0, D.q);
+      if (nm == "latent_contem_local") return uv(P.hq1, D.q);
+      if (nm == "global_lev") return sc(HS_GLOBAL);
+      if (nm == "latent_global") return sc(HS_LATENT_GLOBAL);
+      if (nm == "contem_global_lev") return sc(HS_CONTEM_GLOBAL);
+      if (nm == "latent_contem_global") return sc(HS_LATENT_CONTEM_GLOBAL);
+      break;
+    case 4:
+      if (nm == "own_lambda") return sc(HS_OWN_LAMBDA);
+      if (nm == "contem_lambda") return sc(HS_CONTEM_LAMBDA);
+      break;
+    case 5:
+      if (nm == "local_lev") return uv(P.hN0, D.N);
+      if (nm == "group_lev") return uv(P.hG0, D.G);
+      if (nm == "local_shape") return uv(P.hG1, D.G);
+      if (nm == "contem_fac") return uv(P.hq0, D.q);
+      if (nm == "global_lev") return sc(HS_GLOBAL);
+      if (nm == "contem_global_lev") return sc(HS_CONTEM_GLOBAL);
+      if (nm == "contem_shape") return sc(HS_CONTEM_SHAPE);
+      break;
+    case 6:
+      if (nm == "local_lev") return uv(P.hN0, D.N);
+      if (nm == "latent_local") return uv(P.hN1, D.N);
+      if (nm == "group_lev") return uv(P.hG0, D.G);
+      if (nm == "contem_local_lev") return uv(P.hq0, D.q);
+      if (nm == "latent_contem_local") return uv(P.hq1, D.q);
+      if (nm == "global_lev") return sc(HS_GLOBAL);
+      if (nm == "contem_global_lev") return sc(HS_CONTEM_GLOBAL);
+      if (nm == "dir_concen") return sc(HS_DIR);
+      if (nm == "contem_dir_concen") return sc(HS_CONTEM_DIR);
+      break;
+    case 7:
+      if (nm == "local_lev") return uv(P.hN0, D.N);
+      if (nm == "group_rate") return uv(P.hG0, D.G);
+      if (nm == "contem_fac") return uv(P.hq0, D.q);
+      if (nm == "contem_rate") return uv(P.hq1, D.q);
+      if (nm == "coef_gamma_shape") return sc(HS_GSHAPE);
+      if (nm == "coef_gamma_rate") return sc(HS_GRATE);
+      if (nm == "contem_gamma_shape") return sc(HS_CGSHAPE);
+      if (nm == "contem_gamma_rate") return sc(HS_CGRATE);
+      break;
+    default: break;
+  }
+  return false;
+}
+
+// moves one unit's view between the device layout and a column-major host vector
+int view_io(bvhar_fit* F, const View& v, int w, int c, double* host, int64_t len, bool to_host) {
+  const Dims& D = F->D;
+  const int u = w * D.C + c, k = D.k, dd = D.d, n = F->win_n[w];
+  const cudaMemcpyKind dir = to_host ? cudaMemcpyDeviceToHost : cudaMemcpyHostToDevice;
+  switch (v.kind) {
+    case View::UNIT_VEC:
+      if (len != v.len) return fail(BVHAR_ERR_BAD_ARG, "state length mismatch");
+      if (to_host) CU(cudaMemcpy(host, v.base + (size_t)u * v.len, sizeof(double) * v.len, dir));
+      else CU(cudaMemcpy(v.base + (size_t)u * v.len, host, sizeof(double) * v.len, dir));
+      return 0;
+    case View::SCALAR:
+      if (len != 1) return fail(BVHAR_ERR_BAD_ARG, "state length mismatch");
+      if (to_host) CU(cudaMemcpy(host, v.base + (size_t)u * HS_SLOTS + v.slot, sizeof(double), dir));
+      else CU(cudaMemcpy(v.base + (size_t)u * HS_SLOTS + v.slot, host, sizeof(double), dir));
+      return 0;
+    case View::COEF_MAT: {  // host d x k column-major <-> Acoef[w][a][c*k + j]
+      if (len != (int64_t)dd * k) return fail(BVHAR_ERR_BAD_ARG, "state length mismatch");
+      std::vector<double> tmp((size_t)dd * k);
+      double* dev = v.base + (size_t)w * dd * D.ldM + (size_t)c * k;
+      if (to_host) {
+        CU(cudaMemcpy2D(tmp.data(), sizeof(double) * k, dev, sizeof(double) * D.ldM, sizeof(double) * k, dd, dir));
+        for (int a = 0; a < dd; ++a) for (int j = 0; j < k; ++j) host[(size_t)j * dd + a] = tmp[(size_t)a * k + j];
+      } else {
+        for (int a = 0; a < dd; ++a) for (int j = 0; j < k; ++j) tmp[(size_t)a * k + j] = host[(size_t)j * dd + a];
+        CU(cudaMemcpy2D(dev, sizeof(double) * D.ldM, tmp.data(), sizeof(double) * k, sizeof(double) * k, dd, dir));
+        // keep coef_vec (alpha / constants) coherent with coef_mat
+        std::vector<double> al(D.N), cv(k, 0.0);
+        for (int j = 0; j < k; ++j) {
+          for (int a = 0; a < D.nrow; ++a) al[(size_t)j * D.nrow + a] = host[(size_t)j * dd + a];
+          if (D.mean) cv[j] = host[(size_t)j * dd + D.nrow];
+        }
+        CU(cudaMemcpy(F->P.alpha + (size_t)u * D.N, al.data(), sizeof(double) * D.N, dir));
+        CU(cudaMemcpy(F->P.cvec + (size_t)u * k, cv.data(), sizeof(double) * k, dir));
+      }
+      return 0;
+    }
+    case View::CHOL: {  // host k x k column-major <-> L[u][i][m] row-major
+      if (len != (int64_t)k * k) return fail(BVHAR_ERR_BAD_ARG, "state length mismatch");
+      std::vector<double> tmp((size_t)k * k);
+      if (to_host) {
+        CU(cudaMemcpy(tmp.data(), v.base + (size_t)u * k * k, sizeof(double) * k * k, dir));
+        for (int i = 0; i < k; ++i) for (int m2 = 0; m2 < k; ++m2) host[(size_t)m2 * k + i] = tmp[(size_t)i * k + m2];
+      } else {
+        for (int i = 0; i < k; ++i) for (int m2 = 0; m2 < k; ++m2) tmp[(size_t)i * k + m2] = host[(size_t)m2 * k + i];
+        CU(cudaMemcpy(v.base + (size_t)u * k * k, tmp.data(), sizeof(double) * k * k, dir));
+      }
+      return 0;
+    }
+    case View::PREC: {  // host: head N alpha order + tail k constants <-> internal (j*d + a)
+      if (len != (int64_t)k * dd) return fail(BVHAR_ERR_BAD_ARG, "state length mismatch");
+      std::vector<double> tmp((size_t)k * dd);
+      if (to_host) {
+        CU(cudaMemcpy(tmp.data(), v.base + (size_t)u * k * dd, sizeof(double) * k * dd, dir));
+        for (int j = 0; j < k; ++j) {
+          for (int a = 0; a < D.nrow; ++a) host[(size_t)j * D.nrow + a] = tmp[(size_t)j * dd + a];
+          if (D.mean) host[D.N + j] = tmp[(size_t)j * dd + D.nrow];
+        }
+      } else {
+        for (int j = 0; j < k; ++j) {
+          for (int a = 0; a < D.nrow; ++a) tmp[(size_t)j * dd + a] = host[(size_t)j * D.nrow + a];
+          if (D.mean) tmp[(size_t)j * dd + D.nrow] = host[D.N + j];
+        }
+        CU(cudaMemcpy(v.base + (size_t)u * k * dd, tmp.data(), sizeof(double) * k * dd, dir));
+      }
+      return 0;
+    }
+    case View::TM:
+    case View::SQRT_SV: {  // host n x k column-major <-> [t][c*k + i]
+      if (len != (int64_t)n * k) return fail(BVHAR_ERR_BAD_ARG, "state length mismatch");
+      std::vector<double> tmp((size_t)n * k);
+      double* dev = v.base + F->win_off[w] + (size_t)c * k;
+      if (to_host) {
+        CU(cudaMemcpy2D(tmp.data(), sizeof(double) * k, dev, sizeof(double) * D.ldM, sizeof(double) * k, n, dir));
+        for (int t = 0; t < n; ++t)
+          for (int i = 0; i < k; ++i) {
+            const double x = tmp[(size_t)t * k + i];
+            host[(size_t)i * n + t] = v.kind == View::SQRT_SV ? 1.0 / std::sqrt(x) : x;
+          }
+      } else {
+        for (int t = 0; t < n; ++t)
+          for (int i = 0; i < k; ++i) {
+            const double x = host[(size_t)i * n + t];
+            tmp[(size_t)t * k + i] = v.kind == View::SQRT_SV ? 1.0 / (x * x) : x;
+          }
+        CU(cudaMemcpy2D(dev, sizeof(double) * D.ldM, tmp.data(), sizeof(double) * k, sizeof(double) * k, n, dir));
+      }
+      return 0;
+    }
+  }
+  return fail(BVHAR_ERR_BAD_ARG, "unknown view");
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* bvhar_cuda_last_error(void) { return g_err.c_str(); }
+int bvhar_cuda_abi_version(void) { return BVHAR_CUDA_ABI_VERSION; }
+int bvhar_cuda_device_count(int* count) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (count) *count = e == cudaSuccess ? n : 0;
+  if (e != cudaSuccess) return fail(BVHAR_ERR_CUDA, cudaGetErrorString(e));
+  return 0;
+}
+int bvhar_cuda_struct_sizes(int64_t* fit_desc, int64_t* chain_init, int64_t* forecast_desc, int64_t* prior_params) {
+  if (fit_desc) *fit_desc = sizeof(bvhar_fit_desc);
+  if (chain_init) *chain_init = sizeof(bvhar_chain_init);
+  if (forecast_desc) *forecast_desc = sizeof(bvhar_forecast_desc);
+  if (prior_params) *prior_params = sizeof(bvhar_prior_params);
+  return 0;
+}
+
+int bvhar_cuda_fit_create(const bvhar_fit_desc* desc, bvhar_fit** out) { return build(desc, out); }
+
+int bvhar_cuda_fit_step(bvhar_fit* fit, int n_sweeps, int record) {
+  if (!fit || n_sweeps < 0) return fail(BVHAR_ERR_BAD_ARG, "bad fit handle or sweep count");
+  return fit->step(n_sweeps, record != 0);
+}
+int bvhar_cuda_fit_sync(bvhar_fit* fit) {
+  if (!fit) return fail(BVHAR_ERR_BAD_ARG, "null fit handle");
+  return fit->sync();
+}
+int bvhar_cuda_fit_run(bvhar_fit* fit, bvhar_progress_fn progress, void* ctx) {
+  if (!fit) return fail(BVHAR_ERR_BAD_ARG, "null fit handle");
+  const int total = fit->num_iter, burn = fit->num_burn;
+  int freq = total / 20;  // 5 %, triangular.h:1248-1251
+  if (freq == 0) freq = 1;
+  int done = (int)fit->sweeps_done;
+  float ms_total = 0.f;
+  while (done < total) {
+    const bool rec = done >= burn;
+    int chunk = std::min(freq - done % freq, (rec ? total : burn) - done);
+    int rc = fit->step(chunk, rec);
+    if (rc) return rc;
+    done += chunk;
+    if (progress) {
+      rc = fit->sync();
+      ms_total += (float)fit->last_ms;
+      if (rc) return rc;
+      if (progress(ctx, done, total)) return fail(BVHAR_ERR_INTERRUPTED, "interrupted by the progress callback");
+    }
+  }
+  int rc = fit->sync();
+  if (progress) fit->last_ms = ms_total;
+  return rc;
+}
+int bvhar_cuda_fit_last_ms(bvhar_fit* fit, double* ms) {
+  if (!fit || !ms) return fail(BVHAR_ERR_BAD_ARG, "null argument");
+  *ms = fit->last_ms;
+  return 0;
+}
+int bvhar_cuda_fit_launch_count(bvhar_fit* fit, int64_t* launches) {
+  if (!fit || !launches) return fail(BVHAR_ERR_BAD_ARG, "null argument");
+  *launches = fit->launches;
+  return 0;
+}
+
+int bvhar_cuda_fit_record_dims(bvhar_fit* fit, const char* name, int64_t* rows, int64_t* cols) {
+  if (!fit || !name) return fail(BVHAR_ERR_BAD_ARG, "null argument");
+  for (auto& r : fit->rec_order)
+    if (r.name == name) {
+      if (rows) *rows = (fit->rec_filled + fit->thin - 1) / fit->thin;
+      if (cols) *cols = r.cols;
+      return 0;
+    }
+  return fail(BVHAR_ERR_BAD_ARG, std::string("no record named ") + name);
+}
+int bvhar_cuda_fit_record(bvhar_fit* fit, int window, int chain, const char* name, double* out, int64_t rows, int64_t cols) {
+  if (!fit || !name || !out) return fail(BVHAR_ERR_BAD_ARG, "null argument");
+  const Dims& D = fit->D;
+  if (window < 0 || window >= D.W || chain < 0 || chain >= D.C) return fail(BVHAR_ERR_BAD_ARG, "window / chain out of range");
+  CU(cudaSetDevice(fit->device));
+  CU(cudaStreamSynchronize(fit->st));
+  for (auto& r : fit->rec_order)
+    if (r.name == name) {
+      const int64_t kept = (fit->rec_filled + fit->thin - 1) / fit->thin;
+      if (rows != kept || cols != r.cols) return fail(BVHAR_ERR_BAD_ARG, "record dims mismatch");
+      if (kept == 0) return 0;
+      const int u = window * D.C + chain;
+      std::vector<double> tmp((size_t)fit->rec_filled * r.cols);
+      CU(cudaMemcpy(tmp.data(), *r.slot + (size_t)u * fit->R.cap * r.cols, tmp.size() * sizeof(double), cudaMemcpyDeviceToHost));
+      // thin_record draw.h:1297-1310: rows 0, thin, 2 thin, ... of the kept draws
+      for (int64_t j = 0; j < cols; ++j)
+        for (int64_t i = 0; i < rows; ++i) out[j * rows + i] = tmp[(size_t)(i * fit->thin) * r.cols + j];
+      return 0;
+    }
+  return fail(BVHAR_ERR_BAD_ARG, std::string("no record named ") + name);
+}
+int bvhar_cuda_fit_record_names(bvhar_fit* fit, char* buf, int64_t buflen) {
+  if (!fit || !buf) return fail(BVHAR_ERR_BAD_ARG, "null argument");
+  std::string s;
+  for (auto& r : fit->rec_order) { s += r.name; s += '\n'; }
+  if ((int64_t)s.size() + 1 > buflen) return fail(BVHAR_ERR_BAD_ARG, "buffer too small");
+  std::memcpy(buf, s.c_str(), s.size() + 1);
+  return 0;
+}
+
+int bvhar_cuda_fit_state_len(bvhar_fit* fit, const char* name, int64_t* len) {
+  if (!fit || !name || !len) return fail(BVHAR_ERR_BAD_ARG, "null argument");
+  View v;
+  int64_t l = 0;
+  if (!find_view(fit, name, v, l)) return fail(BVHAR_ERR_BAD_ARG, std::string("no state named ") + name);
+  *len = l < 0 ? (int64_t)fit->win_n[0] * fit->D.k : l;
+  return 0;
+}
+static int state_io(bvhar_fit* fit, int window, int chain, const char* name, double* buf, int64_t len, bool to_host) {
+  if (!fit || !name || !buf) return fail(BVHAR_ERR_BAD_ARG, "null argument");
+  const Dims& D = fit->D;
+  if (window < 0 || window >= D.W || chain < 0 || chain >= D.C) return fail(BVHAR_ERR_BAD_ARG, "window / chain out of range");
+  CU(cudaSetDevice(fit->device));
+  CU(cudaStreamSynchronize(fit->st));
+  View v;
+  int64_t l = 0;
+  if (!find_view(fit, name, v, l)) return fail(BVHAR_ERR_BAD_ARG, std::string("no state named ") + name);
+  return view_io(fit, v, window, chain, buf, len, to_host);
+}
+int bvhar_cuda_fit_get_state(bvhar_fit* fit, int window, int chain, const char* name, double* out, int64_t len) {
+  return state_io(fit, window, chain, name, out, len, true);
+}
+int bvhar_cuda_fit_set_state(bvhar_fit* fit, int window, int chain, const char* name, const double* in, int64_t len) {
+  return state_io(fit, window, chain, name, const_cast<double*>(in), len, false);
+}
+int bvhar_cuda_fit_run_stage(bvhar_fit* fit, int stage, int iter) {
+  if (!fit) return fail(BVHAR_ERR_BAD_ARG, "null fit handle");
+  CU(cudaSetDevice(fit->device));
+  const uint32_t it = (uint32_t)iter;
+  CU(cudaMemcpyAsync(fit->iter.p, &it, sizeof it, cudaMemcpyHostToDevice, fit->st));
+  CU(cudaStreamSynchronize(fit->st));
+  const Dims& D = fit->D;
+  switch (stage) {
+    case 1: CU(launch_prior(D, fit->P, fit->PC, 0, fit->st)); break;
+    case 2: break;  // alpha_penalty is a constant of the group structure here
+    case 3: if (D.sv) CU(launch_sv_prep(D, fit->P, fit->st)); break;
+    case 4:
+      if (D.sv) { CU(launch_dgemm_tn(fit->g1, fit->st)); CU(launch_dgemm_tn(fit->g2, fit->st)); }
+      CU(launch_coef(D, fit->P, fit->vscratch.p, fit->smem_limit, fit->st));
+      break;
+    case 5: CU(launch_prior(D, fit->P, fit->PC, 1, fit->st)); break;
+    case 6: CU(launch_dgemm_tn(fit->g3, fit->st)); break;
+    case 7: if (D.k > 1) CU(launch_impact(D, fit->P, fit->gscratch.p, fit->st)); break;
+    case 8: break;  // chol_lower is rebuilt inside the contemporaneous draw
+    case 9:
+      if (D.sv) CU(launch_sv_state(D, fit->P, fit->st));
+      else CU(launch_ldlt_state(D, fit->P, fit->st));
+      break;
+    default: return fail(BVHAR_ERR_BAD_ARG, "stage must be 1..9");
+  }
+  return fit->sync();
+}
+
+void bvhar_cuda_fit_destroy(bvhar_fit* fit) { delete fit; }
+
+// ---- density forecast -------------------------------------------------------------------
+int bvhar_cuda_forecast_density(const bvhar_forecast_desc* d, double* out_density, double* out_lpl) {
+  if (!d || !out_density) return fail(BVHAR_ERR_BAD_ARG, "null argument");
+  if (d->abi_version != BVHAR_CUDA_ABI_VERSION) return fail(BVHAR_ERR_BAD_ARG, "descriptor ABI version mismatch");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(BVHAR_ERR_CUDA, "no CUDA device available: no CPU fallback");
+  if (d->n_draws < 1) return fail(BVHAR_ERR_BAD_ARG, "No stable MCMC draws");  // forecaster.h:286, 322
+  if (d->step < 1 || d->step > 64) return fail(BVHAR_ERR_UNSUPPORTED, "forecast step must be in 1..64");
+  CU(cudaSetDevice(d->device));
+  const int k = d->dim, S = d->n_draws, U = d->n_units, q = k * (k - 1) / 2;
+  const int ncoef = d->nrow_coef * k + (d->include_mean ? k : 0);
+  ForecastArgs A{};
+  A.n_units = U; A.k = k; A.nrow = d->nrow_coef; A.mean = d->include_mean; A.sv_model = d->cov_type == BVHAR_COV_SV;
+  A.step = d->step; A.p = d->var_lag; A.is_vhar = d->is_vhar; A.sv = d->sv; A.get_lpl = d->get_lpl && d->valid_vec && out_lpl; A.S = S;
+  A.har_r = 3 * k + (d->include_mean ? 1 : 0); A.har_c = d->var_lag * k + (d->include_mean ? 1 : 0);
+  DevBuf<double> har, coef, contem, diag, sigh, last, valid, out, lpl;
+  DevBuf<uint32_t> seed;
+  auto up = [&](DevBuf<double>& b, const double* src, size_t n) -> cudaError_t {
+    cudaError_t e = b.alloc(n);
+    if (e != cudaSuccess || n == 0) return e;
+    return cudaMemcpy(b.p, src, n * sizeof(double), cudaMemcpyHostToDevice);
+  };
+  if (d->is_vhar) { if (!d->har_trans) return fail(BVHAR_ERR_BAD_ARG, "har_trans missing"); CU(up(har, d->har_trans, (size_t)A.har_r * A.har_c)); }
+  CU(up(coef, d->coef_record, (size_t)U * S * ncoef));
+  CU(up(contem, d->contem_record, (size_t)U * S * q));
+  CU(up(diag, d->diag_record, (size_t)U * S * k));
+  if (A.sv_model) CU(up(sigh, d->sigh_record, (size_t)U * S * k));
+  CU(up(last, d->last_obs, (size_t)U * d->var_lag * k));
+  if (A.get_lpl) CU(up(valid, d->valid_vec, k));
+  CU(seed.upload(std::vector<uint32_t>(d->seed, d->seed + U)));
+  CU(out.alloc((size_t)U * S * k * d->step));
+  if (A.get_lpl) CU(lpl.alloc((size_t)U * d->step));
+  A.har = har.p; A.coef = coef.p; A.contem = contem.p; A.diag = diag.p; A.sigh = sigh.p; A.last_obs = last.p;
+  A.valid = valid.p; A.seed = seed.p; A.out = out.p; A.lpl = lpl.p;
+  CU(launch_forecast(A, 0));
+  CU(cudaDeviceSynchronize());
+  CU(cudaMemcpy(out_density, out.p, out.n * sizeof(double), cudaMemcpyDeviceToHost));
+  if (A.get_lpl) CU(cudaMemcpy(out_lpl, lpl.p, lpl.n * sizeof(double), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+// ---- building blocks ------------------------------------------------------------------------
+int bvhar_cuda_dgemm_tn(int device, int64_t M, int64_t N, int64_t K, const double* A, int64_t lda, const double* B,
+                        int64_t ldb, double* C, int64_t ldc) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(BVHAR_ERR_CUDA, "no CUDA device available: no CPU fallback");
+  CU(cudaSetDevice(device));
+  DevBuf<double> dA, dB, dC;
+  const int64_t la = (lda + 1) & ~1LL, lb = (ldb + 1) & ~1LL;
+  CU(dA.alloc((size_t)K * la)); CU(dB.alloc((size_t)K * lb)); CU(dC.alloc((size_t)M * ldc));
+  CU(cudaMemcpy2D(dA.p, la * sizeof(double), A, lda * sizeof(double), M * sizeof(double), K, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy2D(dB.p, lb * sizeof(double), B, ldb * sizeof(double), N * sizeof(double), K, cudaMemcpyHostToDevice));
+  GemmArgs g{};
+  g.A = dA.p; g.B = dB.p; g.C = dC.p; g.M = (int)M; g.N = (int)N; g.K = (int)K; g.lda = (int)la; g.ldb = (int)lb; g.ldc = (int)ldc;
+  g.groups = 1; g.epi = EPI_STORE; g.aligned16 = 1;
+  CU(launch_dgemm_tn(g, 0));
+  CU(cudaDeviceSynchronize());
+  CU(cudaMemcpy(C, dC.p, (size_t)M * ldc * sizeof(double), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int bvhar_cuda_draw_coef_batched(int device, int64_t batch, int32_t d, const double* P_packed, const double* b, const double* z,
+                                 double* out) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(BVHAR_ERR_CUDA, "no CUDA device available: no CPU fallback");
+  if (batch < 1 || d < 1) return fail(BVHAR_ERR_BAD_ARG, "empty batch");
+  CU(cudaSetDevice(device));
+  const size_t np = (size_t)d * (d + 1) / 2;
+  DevBuf<double> dP, db, dz, dout;
+  CU(dP.alloc(batch * np)); CU(db.alloc((size_t)batch * d)); CU(dz.alloc((size_t)batch * d)); CU(dout.alloc((size_t)batch * d));
+  CU(cudaMemcpy(dP.p, P_packed, batch * np * sizeof(double), cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(db.p, b, (size_t)batch * d * sizeof(double), cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(dz.p, z, (size_t)batch * d * sizeof(double), cudaMemcpyHostToDevice));
+  cudaError_t e = launch_draw_coef_batched(batch, d, dP.p, db.p, dz.p, dout.p, 0);
+  if (e == cudaErrorInvalidConfiguration) return fail(BVHAR_ERR_UNSUPPORTED, "d too large for the shared-memory Cholesky");
+  CU(e);
+  CU(cudaDeviceSynchronize());
+  CU(cudaMemcpy(out, dout.p, (size_t)batch * d * sizeof(double), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+}  // extern "C"

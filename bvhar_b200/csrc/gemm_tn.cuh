@@ -1,0 +1,191 @@
+// gemm_tn.cuh — grouped fp64 "TN" contraction on the tensor pipe (DMMA mma.sync.m8n8k4.f64).
+//
+//   C_g[M x N] = epilogue( A_g^T B_g ),   A_g stored K_g x M row-major, B_g stored K_g x N row-major
+//
+// One launch covers every window group g (blockIdx.z).  This single kernel carries the three
+// time-dimension contractions of a sweep (DESIGN.md "Kernels"):
+//   G1  S  = Dinv' * XX      SV-weighted Gram  X' diag(1/s_i^2) X  for every (unit, equation)
+//                            (replaces the Kronecker-design Gram of triangular.h:286 + draw.h:380)
+//   G2  Cm = YLD' * X        X' diag(1/s_i^2) (Y L_i')             (triangular.h:297, draw.h:382)
+//   G3  Z  = Y - XT' * A     latent_innov = y - x * coef_mat        (triangular.h:342)
+// tcgen05.mma has no f64 kind, so the FP64 tensor path on sm_100a is the legacy DMMA mma.sync.
+//
+// Tiling: 128 x 128 x 16 CTA tile, 8 warps (2 x 4), 64 x 32 warp tile = 8 x 4 DMMA fragments,
+// cp.async (LDGSTS) 3-stage pipeline, smem row pitch BM+4 doubles => conflict-free fragment loads.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace bvhar {
+
+enum GemmEpilogue { EPI_STORE = 0, EPI_Y_MINUS = 1 };
+
+struct GemmArgs {
+  const double* A;
+  const double* B;
+  double* C;
+  int M, N, K;        // K used when Kg == nullptr
+  int lda, ldb, ldc;
+  int groups;
+  const long long* a_off;  // per group element offsets (nullptr => 0)
+  const long long* b_off;
+  const long long* c_off;
+  const int* Kg;           // per group K
+  const int* Mg;           // per group M (nullptr => M); grid.y covers max M
+  int epi;
+  const double* Y;         // EPI_Y_MINUS: C[r][c] = Y[y_off[g] + r * ldy + (c % ymod)] - acc
+  const long long* y_off;
+  int ldy, ymod;
+  int aligned16;           // all of A/B offsets and leading dimensions are even (16-byte chunks legal)
+};
+
+constexpr int GBM = 128, GBN = 128, GBK = 16, GSTAGES = 3, GPAD = 4;
+constexpr int GEMM_THREADS = 256;
+constexpr size_t GEMM_SMEM = (size_t)GSTAGES * GBK * ((GBM + GPAD) + (GBN + GPAD)) * sizeof(double);
+
+__device__ __forceinline__ void cp_async16(void* dst, const void* src, int src_bytes) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(d), "l"(src), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async8(void* dst, const void* src, int src_bytes) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(d), "l"(src), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+__device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(d0), "+d"(d1)
+               : "d"(a), "d"(b));
+}
+
+// Loads a GBK x 128 tile (rows k0.., cols c0..) of a row-major matrix into smem [GBK][128 + GPAD].
+template <bool ALIGNED16>
+__device__ __forceinline__ void gemm_load_tile(double* sm, const double* __restrict__ g, int ld, int k0, int c0, int K,
+                                               int ncols, int tid) {
+  if (ALIGNED16) {
+#pragma unroll
+    for (int i = 0; i < (GBK * 64) / GEMM_THREADS; ++i) {
+      const int c = tid + i * GEMM_THREADS;
+      const int row = c >> 6, col = (c & 63) << 1;
+      const bool ok = (k0 + row < K) && (c0 + col < ncols);  // ncols rounded up to even by the caller
+      const double* src = ok ? g + (size_t)(k0 + row) * ld + c0 + col : g;
+      cp_async16(sm + row * (128 + GPAD) + col, src, ok ? 16 : 0);
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < (GBK * 128) / GEMM_THREADS; ++i) {
+      const int c = tid + i * GEMM_THREADS;
+      const int row = c >> 7, col = c & 127;
+      const bool ok = (k0 + row < K) && (c0 + col < ncols);
+      const double* src = ok ? g + (size_t)(k0 + row) * ld + c0 + col : g;
+      cp_async8(sm + row * (128 + GPAD) + col, src, ok ? 8 : 0);
+    }
+  }
+}
+
+template <bool ALIGNED16>
+__global__ void __launch_bounds__(GEMM_THREADS, 1) dgemm_tn_kernel(const GemmArgs g) {
+  extern __shared__ __align__(16) unsigned char gemm_smem_raw[];
+  double* As = reinterpret_cast<double*>(gemm_smem_raw);
+  double* Bs = As + GSTAGES * GBK * (GBM + GPAD);
+  const int grp = blockIdx.z;
+  const int K = g.Kg ? g.Kg[grp] : g.K;
+  const int M = g.Mg ? g.Mg[grp] : g.M;
+  if ((int)blockIdx.y * GBM >= M) return;
+  const double* A = g.A + (g.a_off ? g.a_off[grp] : 0);
+  const double* B = g.B + (g.b_off ? g.b_off[grp] : 0);
+  double* C = g.C + (g.c_off ? g.c_off[grp] : 0);
+  const int m0 = blockIdx.y * GBM, n0 = blockIdx.x * GBN;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm0 = (warp >> 2) * 64, wn0 = (warp & 3) * 32;
+  const int fr = lane >> 2, fc = lane & 3;  // fragment row (0..7) / k index (0..3)
+  const int Mld = ALIGNED16 ? ((M + 1) & ~1) : M;
+  const int Nld = ALIGNED16 ? ((g.N + 1) & ~1) : g.N;
+
+  double acc[8][4][2];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+  const int nk = (K + GBK - 1) / GBK;
+#pragma unroll
+  for (int s = 0; s < GSTAGES - 1; ++s) {
+    if (s < nk) {
+      gemm_load_tile<ALIGNED16>(As + s * GBK * (GBM + GPAD), A, g.lda, s * GBK, m0, K, Mld, tid);
+      gemm_load_tile<ALIGNED16>(Bs + s * GBK * (GBN + GPAD), B, g.ldb, s * GBK, n0, K, Nld, tid);
+    }
+    cp_async_commit();
+  }
+  for (int kt = 0; kt < nk; ++kt) {
+    cp_async_wait<GSTAGES - 2>();
+    __syncthreads();
+    {  // prefetch tile kt + STAGES - 1 into the slot freed at iteration kt - 1
+      const int nx = kt + GSTAGES - 1;
+      if (nx < nk) {
+        const int s = nx % GSTAGES;
+        gemm_load_tile<ALIGNED16>(As + s * GBK * (GBM + GPAD), A, g.lda, nx * GBK, m0, K, Mld, tid);
+        gemm_load_tile<ALIGNED16>(Bs + s * GBK * (GBN + GPAD), B, g.ldb, nx * GBK, n0, K, Nld, tid);
+      }
+      cp_async_commit();
+    }
+    const double* as = As + (kt % GSTAGES) * GBK * (GBM + GPAD);
+    const double* bs = Bs + (kt % GSTAGES) * GBK * (GBN + GPAD);
+#pragma unroll
+    for (int kk = 0; kk < GBK; kk += 4) {
+      double af[8], bf[4];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) af[i] = as[(kk + fc) * (GBM + GPAD) + wm0 + i * 8 + fr];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) bf[j] = bs[(kk + fc) * (GBN + GPAD) + wn0 + j * 8 + fr];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+    }
+  }
+  cp_async_wait<0>();
+
+  const long long yoff = (g.epi == EPI_Y_MINUS && g.y_off) ? g.y_off[grp] : 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int row = m0 + wm0 + i * 8 + fr;
+    if (row >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int col = n0 + wn0 + j * 8 + fc * 2;
+      double v0 = acc[i][j][0], v1 = acc[i][j][1];
+      if (g.epi == EPI_Y_MINUS) {
+        if (col < g.N) v0 = g.Y[yoff + (size_t)row * g.ldy + (col % g.ymod)] - v0;
+        if (col + 1 < g.N) v1 = g.Y[yoff + (size_t)row * g.ldy + ((col + 1) % g.ymod)] - v1;
+      }
+      double* dst = C + (size_t)row * g.ldc + col;
+      if (col + 1 < g.N && ((g.ldc & 1) == 0) && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+        *reinterpret_cast<double2*>(dst) = make_double2(v0, v1);
+      } else {
+        if (col < g.N) dst[0] = v0;
+        if (col + 1 < g.N) dst[1] = v1;
+      }
+    }
+  }
+}
+
+inline cudaError_t launch_dgemm_tn(const GemmArgs& g, cudaStream_t st) {
+  dim3 grid((g.N + GBN - 1) / GBN, (g.M + GBM - 1) / GBM, g.groups);
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(dgemm_tn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM);
+    cudaFuncSetAttribute(dgemm_tn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM);
+    configured = true;
+  }
+  if (g.aligned16)
+    dgemm_tn_kernel<true><<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(g);
+  else
+    dgemm_tn_kernel<false><<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(g);
+  return cudaGetLastError();
+}
+
+}  // namespace bvhar

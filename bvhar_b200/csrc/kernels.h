@@ -1,0 +1,33 @@
+// kernels.h — host-callable launch wrappers of the sweep kernels (definitions in kernels_*.cu).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "engine.cuh"
+
+namespace bvhar {
+
+cudaError_t launch_sv_prep(const Dims& D, const DevPtrs& P, cudaStream_t st);
+bool coef_plan(const Dims& D, size_t smem_limit, int* CH_out, bool* vglobal_out);
+cudaError_t launch_coef(const Dims& D, const DevPtrs& P, double* vscratch, size_t smem_limit, cudaStream_t st);
+cudaError_t launch_draw_coef_batched(long long batch, int d, const double* Pp, const double* b, const double* z, double* out,
+                                     cudaStream_t st);
+int impact_gsize(const Dims& D);
+cudaError_t launch_impact(const Dims& D, const DevPtrs& P, double* gscratch, cudaStream_t st);
+cudaError_t launch_sv_state(const Dims& D, const DevPtrs& P, cudaStream_t st);
+cudaError_t launch_ldlt_state(const Dims& D, const DevPtrs& P, cudaStream_t st);
+cudaError_t launch_record(const Dims& D, const DevPtrs& P, const RecPtrs& R, cudaStream_t st);
+cudaError_t launch_bump(const DevPtrs& P, int bump_iter, int bump_rec, cudaStream_t st);
+// prior hyper-parameter updaters (kernels_prior.cu): side 0 = updateCoefPrec, 1 = updateImpactPrec
+cudaError_t launch_prior(const Dims& D, const DevPtrs& P, const PriorConst& C, int side, cudaStream_t st);
+// setup helpers (kernels_setup.cu)
+cudaError_t launch_build_xx(const Dims& D, const DevPtrs& P, double* XX, cudaStream_t st);
+// forecast (kernels_forecast.cu)
+struct ForecastArgs {
+  int n_units, k, nrow, mean, sv_model, step, p, is_vhar, sv, get_lpl, S, har_r, har_c;
+  const double *har, *coef, *contem, *diag, *sigh, *last_obs, *valid;
+  const uint32_t* seed;
+  double *out, *lpl;
+};
+cudaError_t launch_forecast(const ForecastArgs& A, cudaStream_t st);
+
+}  // namespace bvhar

@@ -1,0 +1,137 @@
+// kernels_setup.cu — one-off device-side setup and the forecast kernel.
+#include "engine.cuh"
+#include "kernels.h"
+#include "rng.cuh"
+
+namespace bvhar {
+
+// XX[t][p(a,b)] = x_ta * x_tb for a >= b: the shared right operand of the G1 contraction
+// (every chain of every window reuses it; rolling / expanding windows are row ranges).
+__global__ void __launch_bounds__(256) build_xx_kernel(const Dims D, const double* __restrict__ X, double* __restrict__ XX) {
+  const int t = blockIdx.x;
+  const double* x = X + (size_t)t * D.ldX;
+  double* o = XX + (size_t)t * D.ldXX;
+  for (int p = threadIdx.x; p < D.ldXX; p += blockDim.x) {
+    double v = 0.0;
+    if (p < D.Pp) {
+      int a = (int)((sqrt(8.0 * p + 1.0) - 1.0) * 0.5);
+      while (tri_idx(a + 1, 0) <= p) ++a;
+      while (tri_idx(a, 0) > p) --a;
+      const int b = p - tri_idx(a, 0);
+      v = x[a] * x[b];
+    }
+    o[p] = v;
+  }
+}
+cudaError_t launch_build_xx(const Dims& D, const DevPtrs& P, double* XX, cudaStream_t st) {
+  build_xx_kernel<<<D.T, 256, 0, st>>>(D, P.X, XX);
+  return cudaGetLastError();
+}
+
+// Density forecast of one (unit, draw) per thread: McmcForecaster::forecastOut fc.h:162-190,
+// RegForecaster fc.h:206-222, SvForecaster fc.h:239-262, computeMean fc.h:300-302 / 338-340.
+// Philox key (seed_forecast[unit], unit), iteration = draw index, stages ST_FORECAST_H / _Y,
+// element h * k + j.
+__global__ void __launch_bounds__(128) forecast_kernel(const ForecastArgs A) {
+  extern __shared__ __align__(16) double sm[];
+  const int u = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int k = A.k, nrow = A.nrow, S = A.S, p = A.p, step = A.step;
+  const int ncoef = nrow * k + (A.mean ? k : 0), q = k * (k - 1) / 2;
+  const int dd = p * k + (A.mean ? 1 : 0);
+  // per-thread workspace in shared memory: last_pvec (dd), tmp ((p-1)k), post_mean (k), sv (k), z (k), hx (har_r)
+  const int per = dd + (p - 1) * k + 3 * k + (A.is_vhar ? A.har_r : 0);
+  double* ws = sm + (size_t)threadIdx.x * per;
+  double* last_pvec = ws;
+  double* tmp = last_pvec + dd;
+  double* pm = tmp + (p - 1) * k;
+  double* svu = pm + k;
+  double* zn = svu + k;
+  double* hx = zn + k;
+  __shared__ double lpl_acc[64];
+  for (int h = threadIdx.x; h < step && h < 64; h += blockDim.x) lpl_acc[h] = 0.0;
+  __syncthreads();
+  if (i < S) {
+    const double* coef = A.coef + (size_t)u * S * ncoef;
+    const double* arec = A.contem + (size_t)u * S * q;
+    const double* dg = A.diag + (size_t)u * S * k;
+    const double* sg = A.sv_model ? A.sigh + (size_t)u * S * k : nullptr;
+    const double* last = A.last_obs + (size_t)u * p * k;
+    const Philox rng(A.seed[u], (uint32_t)u, (uint32_t)i);
+    for (int l = 0; l < p; ++l)
+      for (int j = 0; j < k; ++j) last_pvec[l * k + j] = last[(size_t)j * p + (p - 1 - l)];
+    if (A.mean) last_pvec[dd - 1] = 1.0;
+    for (int j = 0; j < k; ++j) pm[j] = last_pvec[j];
+    for (int e = 0; e < (p - 1) * k; ++e) tmp[e] = last_pvec[k + e];
+    for (int j = 0; j < k; ++j) svu[j] = A.sv_model ? dg[(size_t)j * S + i] : sqrt(dg[(size_t)j * S + i]);
+    for (int h = 0; h < step; ++h) {
+      for (int e = 0; e < (p - 1) * k; ++e) last_pvec[k + e] = tmp[e];
+      for (int j = 0; j < k; ++j) last_pvec[j] = pm[j];
+      if (A.is_vhar) {
+        for (int r = 0; r < A.har_r; ++r) {
+          double s = 0.0;
+          for (int c = 0; c < A.har_c; ++c) {
+            const double hv = A.har[(size_t)c * A.har_r + r];
+            if (hv != 0.0) s += hv * last_pvec[c];
+          }
+          hx[r] = s;
+        }
+      }
+      const double* xin = A.is_vhar ? hx : last_pvec;
+      for (int j = 0; j < k; ++j) {
+        double s = 0.0;
+        for (int r = 0; r < nrow; ++r) s += coef[(size_t)(j * nrow + r) * S + i] * xin[r];
+        if (A.mean) s += coef[(size_t)(nrow * k + j) * S + i] * xin[nrow];
+        pm[j] = s;
+      }
+      if (A.sv_model) {
+        if (A.sv)
+          for (int j = 0; j < k; ++j) svu[j] += rng.normal_elem(ST_FORECAST_H, (uint32_t)(h * k + j)) * sqrt(sg[(size_t)j * S + i]);
+        for (int j = 0; j < k; ++j) zn[j] = rng.normal_elem(ST_FORECAST_Y, (uint32_t)(h * k + j)) * exp(svu[j] / 2);
+      } else {
+        for (int j = 0; j < k; ++j) zn[j] = rng.normal_elem(ST_FORECAST_Y, (uint32_t)(h * k + j)) * svu[j];
+      }
+      // post_mean += L^-1 e  (unit-lower solve, fc.h:168); L row j = contem[j(j-1)/2 ...]
+      for (int j = 0; j < k; ++j) {
+        double s = zn[j];
+        const int id = j * (j - 1) / 2;
+        for (int m = 0; m < j; ++m) s -= arec[(size_t)(id + m) * S + i] * zn[m];
+        zn[j] = s;
+      }
+      for (int j = 0; j < k; ++j) {
+        pm[j] += zn[j];
+        A.out[((size_t)u * S * k + (size_t)i * k + j) * step + h] = pm[j];
+      }
+      if (A.get_lpl && A.valid) {  // fc.h:221 / 261, signs as written
+        double quad = 0.0, lg = 0.0;
+        for (int j = 0; j < k; ++j) {
+          double s = pm[j] - A.valid[j];
+          const int id = j * (j - 1) / 2;
+          for (int m = 0; m < j; ++m) s += arec[(size_t)(id + m) * S + i] * (pm[m] - A.valid[m]);
+          if (A.sv_model) { s *= exp(-svu[j] / 2); lg += svu[j] / 2; }
+          else { s /= svu[j]; lg += log(svu[j]); }
+          quad += s * s;
+        }
+        const double val = lg - k * log(2 * 3.14159265358979323846) / 2 - quad / 2;
+        if (h < 64) atomicAdd(&lpl_acc[h], val);
+      }
+      for (int e = 0; e < (p - 1) * k; ++e) tmp[e] = last_pvec[e];
+    }
+  }
+  __syncthreads();
+  if (A.lpl)
+    for (int h = threadIdx.x; h < step && h < 64; h += blockDim.x) atomicAdd(&A.lpl[(size_t)u * step + h], lpl_acc[h] / S);
+}
+cudaError_t launch_forecast(const ForecastArgs& A, cudaStream_t st) {
+  const int dd = A.p * A.k + (A.mean ? 1 : 0);
+  const int per = dd + (A.p - 1) * A.k + 3 * A.k + (A.is_vhar ? A.har_r : 0);
+  int threads = 128;
+  while (threads > 32 && (size_t)threads * per * sizeof(double) > 200 * 1024) threads >>= 1;
+  const size_t smem = (size_t)threads * per * sizeof(double);
+  if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
+  cudaFuncSetAttribute(forecast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  forecast_kernel<<<dim3((A.S + threads - 1) / threads, A.n_units), threads, smem, st>>>(A);
+  return cudaGetLastError();
+}
+
+}  // namespace bvhar

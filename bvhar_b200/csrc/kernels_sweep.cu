@@ -1,0 +1,749 @@
+// kernels_sweep.cu — the per-iteration updaters of the corrected-triangular Gibbs sweep
+// (McmcTriangular::doPosteriorDraws, inst/include/bvhar/src/bayes/triangular/triangular.h:102-115)
+// as sm_100a kernels.  One kernel (or one contraction + one kernel) per updater:
+//
+//   stage 3  updateSv      sv_prep_kernel      tri.h:409           elementwise, HBM-bound
+//   stage 4  updateCoef    G1/G2 contractions + coef_kernel        tri.h:281-316, draw.h:372-383, 417-430
+//   stage 6  updateLatent  G3 contraction                          tri.h:342
+//   stage 7  updateImpact  impact_kernel       tri.h:322-336, draw.h:398-415   (+ stage 8 updateChol, draw.h:124-132)
+//   stage 9  updateState   SV:   sv_mix_kernel + sv_solve_kernel + sv_finish_kernel   tri.h:400-408, draw.h:440-537
+//                          LDLT: ldlt_state_kernel                                    tri.h:371, draw.h:1244-1259
+//   records                record_kernel       config.h:850-857, 955-965, 796-804
+//
+// Arithmetic follows the "efficient" formulation proved equal to the reference's in
+// oracle/bvhar_oracle.cpp (update_coef_efficient, varsv_ht_efficient) and DESIGN.md.
+#include "engine.cuh"
+#include "kernels.h"
+#include "rng.cuh"
+
+namespace bvhar {
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+// Sum over the block; every thread gets the result.  `scratch` holds >= 33 doubles.
+__device__ double block_sum(double v, double* scratch) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) scratch[warp] = v;
+  __syncthreads();
+  if (warp == 0) {
+    double t = lane < nw ? scratch[lane] : 0.0;
+    t = warp_sum(t);
+    if (lane == 0) scratch[32] = t;
+  }
+  __syncthreads();
+  return scratch[32];
+}
+
+// ------------------------------------------------------------------ stage 3: updateSv (SV)
+// Dinv = exp(-h) = 1 / sqrt_sv^2 and YLD = (Y L')_{t,i} * Dinv, both in [t][m] contraction layout.
+__global__ void __launch_bounds__(256) sv_prep_kernel(const Dims D, const DevPtrs P) {
+  const int w = blockIdx.y;
+  const int n = P.win_n[w], row0 = P.win_row0[w];
+  const long long off = P.win_off[w];
+  const long long total = (long long)n * D.M;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int t = (int)(e / D.M), m = (int)(e % D.M);
+    const int c = m / D.k, i = m % D.k;
+    const int u = w * D.C + c;
+    const long long at = off + (long long)t * D.ldM + m;
+    const double dinv = exp(-P.H[at]);
+    const double* Lr = P.L + ((size_t)u * D.k + i) * D.k;
+    const double* y = P.Y + (size_t)(row0 + t) * D.k;
+    double yl = 0.0;
+    for (int m2 = 0; m2 <= i; ++m2) yl += Lr[m2] * y[m2];
+    P.Dinv[at] = dinv;
+    P.YLD[at] = yl * dinv;
+  }
+}
+
+// ------------------------------------------------------------------ packed Cholesky / solves
+// Right-looking Cholesky of a packed-lower (row-major packed) matrix in shared memory, whole block.
+__device__ void chol_packed_block(double* Pk, int d, int* bad) {
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
+  for (int c = 0; c < d; ++c) {
+    const int cc = tri_idx(c, c);
+    __syncthreads();
+    const double p = Pk[cc];
+    __syncthreads();
+    const double piv = sqrt(p), inv = 1.0 / piv;
+    if (tid == 0) {
+      Pk[cc] = piv;
+      if (!(p > 0.0)) *bad = 1;
+    }
+    for (int a = c + 1 + tid; a < d; a += nt) Pk[tri_idx(a, c)] *= inv;
+    __syncthreads();
+    for (int a = c + 1 + warp; a < d; a += nw) {
+      const double lac = Pk[tri_idx(a, c)];
+      const int ra = a * (a + 1) / 2;
+      for (int b = c + 1 + lane; b <= a; b += 32) Pk[ra + b] -= lac * Pk[tri_idx(b, c)];
+    }
+  }
+  __syncthreads();
+}
+// Same for one warp (small matrices), packed-lower in shared or global memory.
+__device__ void chol_packed_warp(double* Pk, int d, int* bad) {
+  const int lane = threadIdx.x & 31;
+  for (int c = 0; c < d; ++c) {
+    const int cc = tri_idx(c, c);
+    __syncwarp();
+    const double p = Pk[cc];
+    __syncwarp();
+    const double piv = sqrt(p), inv = 1.0 / piv;
+    if (lane == 0) {
+      Pk[cc] = piv;
+      if (!(p > 0.0)) *bad = 1;
+    }
+    for (int a = c + 1 + lane; a < d; a += 32) Pk[tri_idx(a, c)] *= inv;
+    __syncwarp();
+    for (int a = c + 1; a < d; ++a) {
+      const double lac = Pk[tri_idx(a, c)];
+      const int ra = a * (a + 1) / 2;
+      for (int b = c + 1 + lane; b <= a; b += 32) Pk[ra + b] -= lac * Pk[tri_idx(b, c)];
+    }
+  }
+  __syncwarp();
+}
+// One warp: x <- L^-T (L^-1 r + z), i.e. mean + chol(P)^-T z of draw.h:382-383.  x, r, z length d.
+__device__ void precision_solve_warp(const double* Lp, int d, const double* r, const double* z, double* x) {
+  const int lane = threadIdx.x & 31;
+  for (int a = 0; a < d; ++a) {  // forward, row-oriented
+    const int ra = a * (a + 1) / 2;
+    double s = 0.0;
+    for (int b = lane; b < a; b += 32) s += Lp[ra + b] * x[b];
+    s = warp_sum(s);
+    if (lane == 0) x[a] = (r[a] - s) / Lp[ra + a];
+    __syncwarp();
+  }
+  for (int a = lane; a < d; a += 32) x[a] += z[a];
+  __syncwarp();
+  for (int c = d - 1; c >= 0; --c) {  // backward with L^T, column c of L
+    double s = 0.0;
+    for (int a = c + 1 + lane; a < d; a += 32) s += Lp[tri_idx(a, c)] * x[a];
+    s = warp_sum(s);
+    if (lane == 0) x[c] = (x[c] - s) / Lp[tri_idx(c, c)];
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------ stage 4: updateCoef
+// One CTA per unit; equations j = 0..k-1 in order (the draw of equation j conditions on this
+// sweep's draws of equations < j, tri.h:283, 297):
+//   P_j = diag(prec_j) + sum_{i>=j} L_ij^2 S_i
+//   b_j = prec_j o mean_j + sum_{i>=j} L_ij (C_i - S_i v_i),   v_i = sum_{m<=i, m != j} L_im a_m
+//   a_j = P_j^-1 b_j + chol(P_j)^-T z,  z ~ N(0, I_d)  (Philox stage ST_COEF_Z, element j*d + a)
+// SV:   S_i, C_i come from the G1/G2 contractions.  LDLT: S_i = X'X / d_i, C_i = X'Y L_i' / d_i.
+// The packed S_i are streamed through shared memory in row chunks of <= CH doubles; the symmetric
+// product S_i v is split into a row pass (warp per row) and a column pass (thread per column).
+template <bool SV>
+__global__ void __launch_bounds__(256) coef_kernel(const Dims D, const DevPtrs P, const int CH, double* vscratch) {
+  extern __shared__ __align__(16) double sm[];
+  const int u = blockIdx.x, w = u / D.C, c = u % D.C;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int k = D.k, d = D.d, Pp = D.Pp, ldM = D.ldM;
+  double* Pk = sm;
+  double* Sbuf = Pk + ((Pp + 1) & ~1);
+  double* Lsm = Sbuf + CH;
+  double* rhs = Lsm + k * k;
+  double* outv = rhs + d;
+  double* lo = outv + d;
+  double* up = lo + d;
+  double* zz = up + d;
+  double* vs = zz + d;     // scaled vector of the current contribution
+  double* wl = vs + d;     // per-i weights (k)
+  double* V = vscratch ? vscratch + (size_t)u * 2 * k * d : wl + k;
+  double* Asm = V + k * d;
+  __shared__ int bad;
+  if (tid == 0) bad = 0;
+  const Philox rng(P.seeds[u], (uint32_t)u, *P.iter);
+
+  for (int e = tid; e < k * k; e += blockDim.x) Lsm[e] = P.L[(size_t)u * k * k + e];
+  double* Ac = P.Acoef + (size_t)w * d * ldM + (size_t)c * k;
+  for (int e = tid; e < d * k; e += blockDim.x) {
+    const int a = e / k, j = e % k;
+    Asm[j * d + a] = Ac[(size_t)a * ldM + j];
+  }
+  __syncthreads();
+  for (int e = tid; e < k * d; e += blockDim.x) {
+    const int i = e / d, a = e % d;
+    double s = 0.0;
+    for (int m = 0; m <= i; ++m) s += Lsm[i * k + m] * Asm[m * d + a];
+    V[e] = s;
+  }
+  __syncthreads();
+
+  const double* prec_u = P.prec + (size_t)u * k * d;
+  const double* xn = P.xnorm + (size_t)w * d;
+  for (int j = 0; j < k; ++j) {
+    // drop equation j from v_i (coef_mat.col(j).setZero(), tri.h:283)
+    for (int e = tid; e < (k - j) * d; e += blockDim.x) {
+      const int i = j + e / d, a = e % d;
+      V[i * d + a] -= Lsm[i * k + j] * Asm[j * d + a];
+    }
+    for (int p = tid; p < Pp; p += blockDim.x) Pk[p] = 0.0;
+    for (int a = tid; a < d; a += blockDim.x) {
+      lo[a] = 0.0;
+      up[a] = 0.0;
+      zz[a] = rng.normal_elem(ST_COEF_Z, (uint32_t)(j * d + a));
+    }
+    if (!SV) {
+      for (int i = j + tid; i < k; i += blockDim.x) wl[i] = Lsm[i * k + j] / P.diag[(size_t)u * k + i];
+    }
+    __syncthreads();
+    const int ni = SV ? (k - j) : 1;
+    for (int ii = 0; ii < ni; ++ii) {
+      const int i = j + ii;
+      const double* Sg;
+      double w2;
+      __syncthreads();  // passes of the previous contribution are done reading vs
+      if (SV) {
+        const double lij = Lsm[i * k + j];
+        Sg = P.S + ((size_t)u * k + i) * D.ldS;
+        w2 = lij * lij;
+        for (int a = tid; a < d; a += blockDim.x) vs[a] = lij * V[i * d + a];
+      } else {
+        Sg = P.XtX + (size_t)w * D.ldS;
+        double ws = 0.0;
+        for (int i2 = j; i2 < k; ++i2) ws += Lsm[i2 * k + j] * wl[i2];
+        w2 = ws;
+        for (int a = tid; a < d; a += blockDim.x) {
+          double s = 0.0;
+          for (int i2 = j; i2 < k; ++i2) s += wl[i2] * V[i2 * d + a];
+          vs[a] = s;
+        }
+      }
+      int a0 = 0;
+      while (a0 < d) {
+        int a1 = a0 + 1;  // rows [a0, a1) with packed length <= CH
+        while (a1 < d && tri_idx(a1 + 1, 0) - tri_idx(a0, 0) <= CH) ++a1;
+        const int p0 = tri_idx(a0, 0), p1 = tri_idx(a1, 0);
+        __syncthreads();  // previous chunk consumed; vs visible
+        for (int p = p0 + tid; p < p1; p += blockDim.x) {
+          const double s = Sg[p];
+          Sbuf[p - p0] = s;
+          Pk[p] += w2 * s;
+        }
+        __syncthreads();
+        for (int a = a0 + warp; a < a1; a += (blockDim.x >> 5)) {  // row pass: sum_{b<=a} S_ab v_b
+          const double* row = Sbuf + (tri_idx(a, 0) - p0);
+          double s = 0.0;
+          for (int b = lane; b <= a; b += 32) s += row[b] * vs[b];
+          s = warp_sum(s);
+          if (lane == 0) lo[a] += s;
+        }
+        for (int b = tid; b < a1 - 1; b += blockDim.x) {  // column pass: sum_{a>b, a in chunk} S_ab v_a
+          double s = 0.0;
+          for (int a = max(a0, b + 1); a < a1; ++a) s += Sbuf[tri_idx(a, b) - p0] * vs[a];
+          up[b] += s;
+        }
+        a0 = a1;
+      }
+    }
+    __syncthreads();
+    // right-hand side and prior diagonal
+    for (int a = tid; a < d; a += blockDim.x) {
+      double ct = 0.0;
+      if (SV) {
+        for (int i = j; i < k; ++i) ct += Lsm[i * k + j] * P.Cm[((size_t)u * k + i) * D.ldX + a];
+      } else {
+        const double* xty = P.XtY + ((size_t)w * d + a) * k;
+        for (int i = j; i < k; ++i) {
+          double s = 0.0;
+          for (int m = 0; m <= i; ++m) s += xty[m] * Lsm[i * k + m];
+          ct += wl[i] * s;
+        }
+      }
+      const double pr = prec_u[j * d + a];
+      rhs[a] = pr * P.prior_mean[j * d + a] + ct - lo[a] - up[a];
+      Pk[tri_idx(a, a)] += pr;
+    }
+    chol_packed_block(Pk, d, &bad);
+    if (warp == 0) precision_solve_warp(Pk, d, rhs, zz, outv);
+    __syncthreads();
+    for (int a = tid; a < d; a += blockDim.x) {
+      const double val = outv[a];
+      Asm[j * d + a] = val;
+      Ac[(size_t)a * ldM + j] = val;
+      double pen = 0.0;
+      if (a < D.nrow) {
+        P.alpha[(size_t)u * D.N + j * D.nrow + a] = val;
+        pen = P.own_flag[j * D.nrow + a] ? 0.0 : 1.0;
+      } else {
+        P.cvec[(size_t)u * k + j] = val;
+      }
+      const double fit = fabs(val) * xn[a];  // draw_mn_savs, draw.h:417-430
+      P.sparse_coef[(size_t)u * d * k + j * d + a] = val * fmax(fit - pen / (val * val), 0.0) / fit;
+    }
+    for (int e = tid; e < (k - j) * d; e += blockDim.x) {
+      const int i = j + e / d, a = e % d;
+      V[i * d + a] += Lsm[i * k + j] * outv[a];
+    }
+    __syncthreads();
+  }
+  if (tid == 0 && bad) atomicOr(&P.flags[u], 1);
+}
+
+// ------------------------------------------------------------------ stage 7 (+8): updateImpact
+__device__ __forceinline__ int impact_row_off(int j) {  // sum_{j'<j} (j'(j'+1)/2 + j')
+  return ((j - 1) * j * (2 * j - 1) / 6 + 3 * (j - 1) * j / 2) / 2;
+}
+// Row j of L: regress Z_j / s_j on Z_{<j} / s_j with prior N(0, diag(1/prec)) (tri.h:322-336).
+// Phase 1 accumulates, for every pair b <= a, sum_t dinv_tj z_ta z_tb for all j >= a (SV) or the
+// plain Z'Z (LDLT) into gscratch; phase 2 factorises and draws each row with one warp.
+template <bool SV, int KJ>
+__global__ void __launch_bounds__(256) impact_kernel(const Dims D, const DevPtrs P, double* gscratch, const int gsize) {
+  extern __shared__ __align__(16) double sm[];
+  const int u = blockIdx.x, w = u / D.C, c = u % D.C;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+  const int k = D.k, ldM = D.ldM, q = D.q;
+  const int n = P.win_n[w];
+  const long long off = P.win_off[w] + (long long)c * k;
+  constexpr int TT = 16;
+  double* zt = sm;            // [TT][k]
+  double* dt = zt + TT * k;   // [TT][k]
+  double* wbuf = dt + TT * k; // per-warp packed matrices
+  double* G = gscratch + (size_t)u * gsize;
+  __shared__ int bad;
+  if (tid == 0) bad = 0;
+  const int npairs = k * (k + 1) / 2;
+  for (int pbase = 0; pbase < npairs; pbase += blockDim.x) {
+    const int pid = pbase + tid;
+    int a = 0, b = 0;
+    const bool active = pid < npairs;
+    if (active) {
+      a = (int)((sqrt(8.0 * pid + 1.0) - 1.0) * 0.5);
+      while (tri_idx(a + 1, 0) <= pid) ++a;
+      while (tri_idx(a, 0) > pid) --a;
+      b = pid - tri_idx(a, 0);
+    }
+    for (int jbase = 0; jbase < (SV ? k : 1); jbase += KJ) {
+      double acc[KJ];
+#pragma unroll
+      for (int jj = 0; jj < KJ; ++jj) acc[jj] = 0.0;
+      double nrm = 0.0;
+      for (int t0 = 0; t0 < n; t0 += TT) {
+        __syncthreads();
+        for (int e = tid; e < TT * k; e += blockDim.x) {
+          const int tt = e / k, m = e % k;
+          const bool ok = t0 + tt < n;
+          const long long at = off + (long long)(t0 + tt) * ldM + m;
+          zt[e] = ok ? P.Z[at] : 0.0;
+          if (SV) dt[e] = ok ? P.Dinv[at] : 0.0;
+        }
+        __syncthreads();
+        if (active) {
+#pragma unroll 4
+          for (int tt = 0; tt < TT; ++tt) {
+            const double pz = zt[tt * k + a] * zt[tt * k + b];
+            if (SV) {
+#pragma unroll
+              for (int jj = 0; jj < KJ; ++jj) {
+                const int j = jbase + jj;
+                if (j < k) acc[jj] = fma(dt[tt * k + j], pz, acc[jj]);
+              }
+            } else {
+              acc[0] += pz;
+            }
+            nrm += pz;
+          }
+        }
+      }
+      if (active) {
+        if (SV) {
+#pragma unroll
+          for (int jj = 0; jj < KJ; ++jj) {
+            const int j = jbase + jj;
+            if (j >= k) continue;
+            if (j > a) G[impact_row_off(j) + tri_idx(a, b)] = acc[jj];            // Gram of row j
+            else if (j == a && b < a) G[impact_row_off(j) + j * (j + 1) / 2 + b] = acc[jj];  // rhs of row a
+          }
+        } else {
+          G[tri_idx(a, b)] = acc[0];
+        }
+        if (a == b && jbase == 0) P.znorm[(size_t)u * k + a] = nrm;
+      }
+    }
+  }
+  __threadfence_block();
+  __syncthreads();
+  // phase 2: one warp per row
+  const Philox rng(P.seeds[u], (uint32_t)u, *P.iter);
+  const int wstride = k * (k + 1) / 2 + 3 * k;
+  double* Pw = wbuf + (size_t)warp * wstride;
+  double* r = Pw + k * (k + 1) / 2;
+  double* z = r + k;
+  double* x = z + k;
+  double* Lu = P.L + (size_t)u * k * k;
+  if (tid < k) {  // row 0 of L (build_inv_lower, draw.h:124-132)
+    Lu[tid] = tid == 0 ? 1.0 : 0.0;
+  }
+  for (int j = 1 + warp; j < k; j += nw) {
+    const int id = j * (j - 1) / 2;
+    const double inv_dj = SV ? 1.0 : 1.0 / P.diag[(size_t)u * k + j];
+    const double* Gj = SV ? G + impact_row_off(j) : G;
+    for (int p = lane; p < j * (j + 1) / 2; p += 32) Pw[p] = Gj[p] * inv_dj;
+    __syncwarp();
+    for (int b = lane; b < j; b += 32) {
+      const double pr = P.chol_prec[(size_t)u * q + id + b];
+      Pw[tri_idx(b, b)] += pr;
+      const double g = SV ? Gj[j * (j + 1) / 2 + b] : G[tri_idx(j, b)] * inv_dj;
+      r[b] = g;  // prior_chol_mean = 0 (tri.h:52)
+      z[b] = rng.normal_elem(ST_IMPACT_Z, (uint32_t)(id + b));
+    }
+    __syncwarp();
+    chol_packed_warp(Pw, j, &bad);
+    precision_solve_warp(Pw, j, r, z, x);
+    __syncwarp();
+    for (int b = lane; b < k; b += 32) {
+      double val = b == j ? 1.0 : 0.0;
+      if (b < j) {
+        val = x[b];
+        P.contem[(size_t)u * q + id + b] = val;
+        const double fit = fabs(val) * P.znorm[(size_t)u * k + b];  // draw_savs, draw.h:398-415
+        P.sparse_contem[(size_t)u * q + id + b] = val * fmax(fit - 1.0 / (val * val), 0.0) / fit;
+      }
+      Lu[j * k + b] = val;
+    }
+    __syncwarp();
+  }
+  if (tid == 0 && bad) atomicOr(&P.flags[u], 2);
+}
+
+// ------------------------------------------------------------------ stage 9 (LDLT): updateState
+// d_i = 1 / Gamma(shape_i + floor(n/2), 1 / (scl_i + ||(Z L')_i||^2 / 2))   (draw.h:1244-1259)
+__global__ void __launch_bounds__(128) ldlt_state_kernel(const Dims D, const DevPtrs P) {
+  __shared__ double scratch[40];
+  const int u = blockIdx.x, w = u / D.C, c = u % D.C;
+  const int k = D.k, n = P.win_n[w];
+  const long long off = P.win_off[w] + (long long)c * k;
+  const Philox rng(P.seeds[u], (uint32_t)u, *P.iter);
+  const double* Lu = P.L + (size_t)u * k * k;
+  for (int i = 0; i < k; ++i) {
+    double ss = 0.0;
+    for (int t = threadIdx.x; t < n; t += blockDim.x) {
+      const double* z = P.Z + off + (long long)t * D.ldM;
+      double uu = 0.0;
+      for (int m = 0; m <= i; ++m) uu += Lu[i * k + m] * z[m];
+      ss += uu * uu;
+    }
+    ss = block_sum(ss, scratch);
+    if (threadIdx.x == 0)
+      P.diag[(size_t)u * k + i] = 1.0 / rng.gamma(ST_LDLT_DIAG, (uint32_t)i, P.sig_shp[i] + (double)(n / 2), 1.0 / (P.sig_scl[i] + ss / 2));
+  }
+}
+
+// ------------------------------------------------------------------ stage 9 (SV): updateState
+__constant__ double c_ksc_p[7] = {0.0073, 0.10556, 0.00002, 0.04395, 0.34001, 0.24566, 0.2575};       // draw.h:445
+__constant__ double c_ksc_m[7] = {-10.12999, -3.97281, -8.56686, 2.77786, 0.61942, 1.79518, -1.08819}; // draw.h:447
+__constant__ double c_ksc_v[7] = {5.79596, 2.61369, 5.17950, 0.16735, 0.64009, 0.34023, 1.26261};      // draw.h:450
+
+// Mixture indicators (draw.h:458-468) for every (t, series): y* = log((Z L')^2 + 1e-4) (tri.h:401-402),
+// s_t by inverse CDF on the normalised 7-component weights; leaves the tridiagonal system's
+// diagonal term 1/v_s in Dinv and right-hand-side term (y* - m_s)/v_s in YLD.
+__global__ void __launch_bounds__(256) sv_mix_kernel(const Dims D, const DevPtrs P) {
+  const int w = blockIdx.y;
+  const int n = P.win_n[w];
+  const long long off = P.win_off[w];
+  const long long total = (long long)n * D.M;
+  const uint32_t it = *P.iter;
+  const uint32_t nh = (uint32_t)((n + 1) / 2);
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int t = (int)(e / D.M), m = (int)(e % D.M);
+    const int c = m / D.k, i = m % D.k;
+    const int u = w * D.C + c;
+    const long long rowat = off + (long long)t * D.ldM;
+    const double* Lr = P.L + ((size_t)u * D.k + i) * D.k;
+    const double* z = P.Z + rowat + (long long)c * D.k;
+    double uu = 0.0;
+    for (int m2 = 0; m2 <= i; ++m2) uu += Lr[m2] * z[m2];
+    const double ystar = log(uu * uu + .0001);
+    const double h = P.H[rowat + m];
+    const Philox rng(P.seeds[u], (uint32_t)u, it);
+    double ua, ub;
+    rng.uniform_pair(ST_SV_MIX_U, (uint32_t)i * nh + ((uint32_t)t >> 1), 0, ua, ub);
+    const double uni = (t & 1) ? ub : ua;
+    double pdf[7], tot = 0.0;
+#pragma unroll
+    for (int cc = 0; cc < 7; ++cc) {
+      const double mm = c_ksc_m[cc] - 1.2704, sd = sqrt(c_ksc_v[cc]);
+      const double ee = (ystar - h - mm) / sd;
+      pdf[cc] = exp(-ee * ee / 2) * c_ksc_p[cc] / (sd * sqrt(2 * 3.14159265358979323846));
+      tot += pdf[cc];
+    }
+    double cum = 0.0;
+    int cnt = 0;
+#pragma unroll
+    for (int cc = 0; cc < 7; ++cc) {
+      cum += pdf[cc] / tot;
+      if (uni < cum) ++cnt;
+    }
+    int s = 7 - cnt;
+    if (s > 6) s = 6;
+    const double iv = 1.0 / c_ksc_v[s];
+    P.Dinv[rowat + m] = iv;
+    P.YLD[rowat + m] = (ystar - (c_ksc_m[s] - 1.2704)) * iv;
+  }
+}
+
+// h_i ~ N(K^-1 b, K^-1) with the tridiagonal K = H'H / sig + diag(1/v_s) (draw.h:469-487): one thread
+// per series runs the bidiagonal Cholesky forward, then the combined mean + noise back substitution.
+// All accesses are [t][m]: coalesced across the series of a window.
+__global__ void __launch_bounds__(128) sv_solve_kernel(const Dims D, const DevPtrs P) {
+  const int w = blockIdx.y;
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= D.M) return;
+  const int n = P.win_n[w];
+  const long long off = P.win_off[w] + m;
+  const int c = m / D.k, i = m % D.k;
+  const int u = w * D.C + c;
+  const double isig = 1.0 / P.lvol_sig[(size_t)u * D.k + i];
+  const double h0 = P.lvol_init[(size_t)u * D.k + i];
+  const Philox rng(P.seeds[u], (uint32_t)u, *P.iter);
+  const uint32_t nh = (uint32_t)((n + 1) / 2);
+  double lprev = 1.0, yprev = 0.0;
+  for (int t = 0; t < n; ++t) {
+    const long long at = off + (long long)t * D.ldM;
+    const double dg = (t < n - 1 ? 2.0 : 1.0) * isig + P.Dinv[at];
+    const double b = (t == 0 ? h0 * isig : 0.0) + P.YLD[at];
+    double l, y;
+    if (t == 0) {
+      l = sqrt(dg);
+      y = b / l;
+    } else {
+      const double e = -isig / lprev;
+      l = sqrt(dg - e * e);
+      y = (b - e * yprev) / l;
+    }
+    P.Dinv[at] = l;
+    P.YLD[at] = y;
+    lprev = l;
+    yprev = y;
+  }
+  double next = 0.0, zkeep = 0.0;
+  for (int t = n - 1; t >= 0; --t) {
+    const long long at = off + (long long)t * D.ldM;
+    const double l = P.Dinv[at];
+    double z;
+    if ((t & 1) || t == n - 1) {  // pair (t even, t odd): fetch both lanes once
+      double z0, z1;
+      rng.normal_pair(ST_SV_H_Z, (uint32_t)i * nh + ((uint32_t)t >> 1), 0, z0, z1);
+      z = (t & 1) ? z1 : z0;
+      zkeep = z0;
+    } else {
+      z = zkeep;
+    }
+    double v = P.YLD[at] + z;
+    if (t < n - 1) v -= (-isig / l) * next;  // e_{t+1} = -isig / l_t
+    next = v / l;
+    P.H[at] = next;
+  }
+}
+
+// varsv_sigh (draw.h:498-512, the squared increments are summed over ALL series, integer n/2) and
+// varsv_h0 (draw.h:523-537, dense k x k precision).
+__global__ void __launch_bounds__(128) sv_finish_kernel(const Dims D, const DevPtrs P) {
+  extern __shared__ __align__(16) double sm[];
+  __shared__ double scratch[40];
+  __shared__ int bad;
+  const int u = blockIdx.x, w = u / D.C, c = u % D.C;
+  const int k = D.k, n = P.win_n[w];
+  const long long off = P.win_off[w] + (long long)c * k;
+  const Philox rng(P.seeds[u], (uint32_t)u, *P.iter);
+  double* Kp = sm;                      // packed k(k+1)/2
+  double* r = Kp + k * (k + 1) / 2;
+  double* z = r + k;
+  double* x = z + k;
+  double* sig = x + k;
+  if (threadIdx.x == 0) bad = 0;
+  double ss = 0.0;
+  for (int e = threadIdx.x; e < n * k; e += blockDim.x) {
+    const int t = e / k, i = e % k;
+    const double cur = P.H[off + (long long)t * D.ldM + i];
+    const double prev = t == 0 ? P.lvol_init[(size_t)u * k + i] : P.H[off + (long long)(t - 1) * D.ldM + i];
+    ss += (cur - prev) * (cur - prev);
+  }
+  ss = block_sum(ss, scratch);
+  for (int i = threadIdx.x; i < k; i += blockDim.x) {
+    const double s = 1.0 / rng.gamma(ST_SV_SIGH, (uint32_t)i, P.sig_shp[i] + (double)(n / 2), 1.0 / (P.sig_scl[i] + ss / 2));
+    sig[i] = s;
+    P.lvol_sig[(size_t)u * k + i] = s;
+  }
+  __syncthreads();
+  for (int p = threadIdx.x; p < k * (k + 1) / 2; p += blockDim.x) {
+    int a = (int)((sqrt(8.0 * p + 1.0) - 1.0) * 0.5);
+    while (tri_idx(a + 1, 0) <= p) ++a;
+    while (tri_idx(a, 0) > p) --a;
+    const int b = p - tri_idx(a, 0);
+    Kp[p] = P.sv_prec[a * k + b] + (a == b ? 1.0 / sig[a] : 0.0);
+  }
+  for (int i = threadIdx.x; i < k; i += blockDim.x) {
+    double s = 0.0;
+    for (int m = 0; m < k; ++m) s += P.sv_prec[i * k + m] * P.sv_mean[m];
+    r[i] = s + P.H[off + i] / sig[i];
+    z[i] = rng.normal_elem(ST_SV_H0_Z, (uint32_t)i);
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    chol_packed_warp(Kp, k, &bad);
+    precision_solve_warp(Kp, k, r, z, x);
+    __syncwarp();
+    for (int i = threadIdx.x; i < k; i += 32) P.lvol_init[(size_t)u * k + i] = x[i];
+  }
+  if (threadIdx.x == 0 && bad) atomicOr(&P.flags[u], 4);
+}
+
+// ------------------------------------------------------------------ records
+// updateRecords: row `rec_row` of every record matrix <- current state (config.h:850-857, 955-965,
+// 796-804 and the prior records config.h:1071-1076, 1122-1125, 1183-1188, 1229-1233).
+__global__ void __launch_bounds__(256) record_kernel(const Dims D, const DevPtrs P, const RecPtrs R) {
+  const int u = blockIdx.x, w = u / D.C, c = u % D.C;
+  const int row = *P.rec_row;
+  if (row >= R.cap) return;
+  const int k = D.k, d = D.d, N = D.N, q = D.q, G = D.G, nrow = D.nrow;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const size_t ur = (size_t)u * R.cap + row;
+  if (R.alpha) for (int e = tid; e < N; e += nt) R.alpha[ur * N + e] = P.alpha[(size_t)u * N + e];
+  if (R.c) for (int e = tid; e < k; e += nt) R.c[ur * k + e] = P.cvec[(size_t)u * k + e];
+  if (R.a) for (int e = tid; e < q; e += nt) R.a[ur * q + e] = P.contem[(size_t)u * q + e];
+  if (R.d) for (int e = tid; e < k; e += nt) R.d[ur * k + e] = P.diag[(size_t)u * k + e];
+  if (R.h0) for (int e = tid; e < k; e += nt) R.h0[ur * k + e] = P.lvol_init[(size_t)u * k + e];
+  if (R.sigh) for (int e = tid; e < k; e += nt) R.sigh[ur * k + e] = P.lvol_sig[(size_t)u * k + e];
+  if (R.h || R.h_last) {
+    const int n = P.win_n[w];
+    const long long off = P.win_off[w] + (long long)c * k;
+    if (R.h)  // lvol_draw.transpose().reshaped(): time-major, k contiguous (config.h:962)
+      for (int e = tid; e < n * k; e += nt) R.h[ur * ((size_t)D.nmax * k) + e] = P.H[off + (long long)(e / k) * D.ldM + (e % k)];
+    if (R.h_last)
+      for (int e = tid; e < k; e += nt) R.h_last[ur * k + e] = P.H[off + (long long)(n - 1) * D.ldM + e];
+  }
+  if (R.alpha_sparse)
+    for (int e = tid; e < N; e += nt) R.alpha_sparse[ur * N + e] = P.sparse_coef[(size_t)u * d * k + (e / nrow) * d + (e % nrow)];
+  if (R.c_sparse) for (int e = tid; e < k; e += nt) R.c_sparse[ur * k + e] = P.sparse_coef[(size_t)u * d * k + e * d + nrow];
+  if (R.a_sparse) for (int e = tid; e < q; e += nt) R.a_sparse[ur * q + e] = P.sparse_contem[(size_t)u * q + e];
+  if (R.gamma) for (int e = tid; e < N; e += nt) R.gamma[ur * N + e] = P.hN0[(size_t)u * N + e];
+  if (R.lambda) for (int e = tid; e < N; e += nt) R.lambda[ur * N + e] = P.hN0[(size_t)u * N + e];
+  if (R.eta) for (int e = tid; e < G; e += nt) R.eta[ur * G + e] = P.hG0[(size_t)u * G + e];
+  if (R.tau && tid == 0) R.tau[ur] = P.hs[(size_t)u * HS_SLOTS + HS_GLOBAL];
+  if (R.kappa) for (int e = tid; e < N; e += nt) R.kappa[ur * N + e] = P.hN2[(size_t)u * N + e];
+}
+__global__ void bump_kernel(uint32_t* iter, int* rec_row, int bump_iter, int bump_rec) {
+  if (bump_iter) *iter += 1u;
+  if (bump_rec) *rec_row += 1;
+}
+
+// ------------------------------------------------------------------ launch wrappers
+static size_t coef_smem(const Dims& D, int CH, bool vglobal) {
+  size_t n = ((D.Pp + 1) & ~1) + CH + (size_t)D.k * D.k + 6 * (size_t)D.d + D.k;
+  if (!vglobal) n += 2 * (size_t)D.k * D.d;
+  return n * sizeof(double);
+}
+bool coef_plan(const Dims& D, size_t smem_limit, int* CH_out, bool* vglobal_out) {
+  int CH = D.Pp < 4096 ? D.Pp : 4096;
+  if (CH < D.d) CH = D.d;
+  bool vglobal = false;
+  if (coef_smem(D, CH, false) > smem_limit) vglobal = true;
+  if (coef_smem(D, CH, vglobal) > smem_limit) {
+    CH = D.d;
+    if (coef_smem(D, CH, vglobal) > smem_limit) return false;
+  }
+  *CH_out = CH;
+  *vglobal_out = vglobal;
+  return true;
+}
+cudaError_t launch_coef(const Dims& D, const DevPtrs& P, double* vscratch, size_t smem_limit, cudaStream_t st) {
+  int CH = 0;
+  bool vglobal = false;
+  if (!coef_plan(D, smem_limit, &CH, &vglobal)) return cudaErrorInvalidConfiguration;
+  if (vglobal && !vscratch) return cudaErrorInvalidValue;
+  const size_t smem = coef_smem(D, CH, vglobal);
+  if (D.sv) {
+    cudaFuncSetAttribute(coef_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    coef_kernel<true><<<D.U, 256, smem, st>>>(D, P, CH, vglobal ? vscratch : nullptr);
+  } else {
+    cudaFuncSetAttribute(coef_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    coef_kernel<false><<<D.U, 256, smem, st>>>(D, P, CH, vglobal ? vscratch : nullptr);
+  }
+  return cudaGetLastError();
+}
+// Batched precision draw (building block exported for stage-level parity tests): one CTA per system.
+__global__ void __launch_bounds__(256) draw_coef_batched_kernel(int d, const double* __restrict__ Pp, const double* __restrict__ b,
+                                                                const double* __restrict__ z, double* __restrict__ out) {
+  extern __shared__ __align__(16) double sm[];
+  const int np = d * (d + 1) / 2;
+  double* Pk = sm;
+  double* r = Pk + np;
+  double* zz = r + d;
+  double* x = zz + d;
+  __shared__ int bad;
+  const size_t s = blockIdx.x;
+  for (int p = threadIdx.x; p < np; p += blockDim.x) Pk[p] = Pp[s * np + p];
+  for (int a = threadIdx.x; a < d; a += blockDim.x) { r[a] = b[s * d + a]; zz[a] = z[s * d + a]; }
+  if (threadIdx.x == 0) bad = 0;
+  chol_packed_block(Pk, d, &bad);
+  if (threadIdx.x < 32) precision_solve_warp(Pk, d, r, zz, x);
+  __syncthreads();
+  for (int a = threadIdx.x; a < d; a += blockDim.x) out[s * d + a] = x[a];
+}
+cudaError_t launch_draw_coef_batched(long long batch, int d, const double* Pp, const double* b, const double* z, double* out,
+                                     cudaStream_t st) {
+  const size_t smem = ((size_t)d * (d + 1) / 2 + 3 * d) * sizeof(double);
+  if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
+  cudaFuncSetAttribute(draw_coef_batched_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  draw_coef_batched_kernel<<<(unsigned)batch, 256, smem, st>>>(d, Pp, b, z, out);
+  return cudaGetLastError();
+}
+int impact_gsize(const Dims& D) {
+  const int k = D.k;
+  if (!D.sv) return k * (k + 1) / 2;
+  return ((k - 1) * k * (2 * k - 1) / 6 + 3 * (k - 1) * k / 2) / 2 + 8;
+}
+cudaError_t launch_impact(const Dims& D, const DevPtrs& P, double* gscratch, cudaStream_t st) {
+  const int k = D.k;
+  const int nw = 8;
+  const size_t smem = (2 * 16 * (size_t)k + (size_t)nw * (k * (k + 1) / 2 + 3 * k)) * sizeof(double);
+  const int gs = impact_gsize(D);
+  if (D.sv) {
+    cudaFuncSetAttribute(impact_kernel<true, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    impact_kernel<true, 32><<<D.U, 256, smem, st>>>(D, P, gscratch, gs);
+  } else {
+    cudaFuncSetAttribute(impact_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    impact_kernel<false, 1><<<D.U, 256, smem, st>>>(D, P, gscratch, gs);
+  }
+  return cudaGetLastError();
+}
+cudaError_t launch_sv_prep(const Dims& D, const DevPtrs& P, cudaStream_t st) {
+  const long long total = (long long)D.nmax * D.M;
+  int bx = (int)((total + 255) / 256);
+  if (bx > 148 * 16) bx = 148 * 16;
+  sv_prep_kernel<<<dim3(bx, D.W), 256, 0, st>>>(D, P);
+  return cudaGetLastError();
+}
+cudaError_t launch_sv_state(const Dims& D, const DevPtrs& P, cudaStream_t st) {
+  const long long total = (long long)D.nmax * D.M;
+  int bx = (int)((total + 255) / 256);
+  if (bx > 148 * 16) bx = 148 * 16;
+  sv_mix_kernel<<<dim3(bx, D.W), 256, 0, st>>>(D, P);
+  sv_solve_kernel<<<dim3((D.M + 127) / 128, D.W), 128, 0, st>>>(D, P);
+  const size_t smem = ((size_t)D.k * (D.k + 1) / 2 + 4 * D.k) * sizeof(double);
+  cudaFuncSetAttribute(sv_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  sv_finish_kernel<<<D.U, 128, smem, st>>>(D, P);
+  return cudaGetLastError();
+}
+cudaError_t launch_ldlt_state(const Dims& D, const DevPtrs& P, cudaStream_t st) {
+  ldlt_state_kernel<<<D.U, 128, 0, st>>>(D, P);
+  return cudaGetLastError();
+}
+cudaError_t launch_record(const Dims& D, const DevPtrs& P, const RecPtrs& R, cudaStream_t st) {
+  record_kernel<<<D.U, 256, 0, st>>>(D, P, R);
+  return cudaGetLastError();
+}
+cudaError_t launch_bump(const DevPtrs& P, int bump_iter, int bump_rec, cudaStream_t st) {
+  bump_kernel<<<1, 1, 0, st>>>(P.iter, P.rec_row, bump_iter, bump_rec);
+  return cudaGetLastError();
+}
+
+}  // namespace bvhar

@@ -183,6 +183,8 @@ typedef int (*bvhar_progress_fn)(void* ctx, int done, int total);
 const char* bvhar_cuda_last_error(void);
 int bvhar_cuda_abi_version(void);
 int bvhar_cuda_device_count(int* count);
+/* sizeof() of the descriptor structs as compiled, so that FFI mirrors can verify their layout. */
+int bvhar_cuda_struct_sizes(int64_t* fit_desc, int64_t* chain_init, int64_t* forecast_desc, int64_t* prior_params);
 
 int bvhar_cuda_fit_create(const bvhar_fit_desc* desc, bvhar_fit** out);
 /* Run num_burn warm-up sweeps and num_iter - num_burn recorded sweeps for every unit
@@ -263,6 +265,12 @@ int bvhar_cuda_dgemm_tn(int device, int64_t M, int64_t N, int64_t K, const doubl
  * lower (d(d+1)/2, row-major packed), mean = P^-1 b, out = mean + chol(P)^-T z. */
 int bvhar_cuda_draw_coef_batched(int device, int64_t batch, int32_t d, const double* P_packed,
                                  const double* b, const double* z, double* out);
+
+/* ---- device-resident micro-benchmarks (roofline denominators; bench.py) ---------------------- */
+/* mode 0: fp64 FMA issue peak, mode 1: fp64 DMMA (mma.sync.m8n8k4) issue peak, in TFLOP/s. */
+int bvhar_cuda_bench_fp64_peak(int device, int mode, double* tflops);
+/* The TN contraction kernel alone on synthetic device-resident operands, CUDA-event timed. */
+int bvhar_cuda_bench_dgemm_tn(int device, int64_t M, int64_t N, int64_t K, int iters, double* ms_per_launch);
 
 #ifdef __cplusplus
 }

@@ -614,10 +614,11 @@ struct Chain {
     Vec u(n), z(n), ys(n);
     for (int i = 0; i < k; ++i) {
       if (rng.philox) {
-        for (int t = 0; t < n; ++t) {
-          rng.uniform_vec(ST_SV_MIX_U, (uint32_t)(t * k + i), 1, &u[t]);
-          rng.normal_vec(ST_SV_H_Z, (uint32_t)(t * k + i), 1, &z[t]);
-        }
+        // element (series i, time t) = i * 2*ceil(n/2) + t: the two lanes of a Philox pair are
+        // consecutive time points of the same series (DESIGN.md "Random streams")
+        const uint32_t base = (uint32_t)i * 2u * (uint32_t)((n + 1) / 2);
+        rng.uniform_vec(ST_SV_MIX_U, base, n, u.data());
+        rng.normal_vec(ST_SV_H_Z, base, n, z.data());
       } else {  // reference order: n uniforms then n normals (draw.h:458-460, 479-481)
         rng.uniform_vec(ST_SV_MIX_U, 0, n, u.data());
         rng.normal_vec(ST_SV_H_Z, 0, n, z.data());
