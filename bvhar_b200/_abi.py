@@ -319,9 +319,12 @@ def load_library():
     L.bvhar_cuda_fit_step.argtypes = [vp, C.c_int, C.c_int]
     L.bvhar_cuda_fit_sync.argtypes = [vp]
     L.bvhar_cuda_fit_last_ms.argtypes = [vp, c_dp]
+    L.bvhar_cuda_fit_set_profiling.argtypes = [vp, C.c_int]
+    L.bvhar_cuda_fit_profile.argtypes = [vp, C.c_char_p, C.c_int64]
     L.bvhar_cuda_fit_launch_count.argtypes = [vp, C.POINTER(C.c_int64)]
     L.bvhar_cuda_fit_record_dims.argtypes = [vp, C.c_char_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     L.bvhar_cuda_fit_record.argtypes = [vp, C.c_int, C.c_int, C.c_char_p, c_dp, C.c_int64, C.c_int64]
+    L.bvhar_cuda_fit_record_all.argtypes = [vp, C.c_char_p, c_dp, C.c_int64, C.c_int64, C.c_int64]
     L.bvhar_cuda_fit_record_names.argtypes = [vp, C.c_char_p, C.c_int64]
     L.bvhar_cuda_fit_state_len.argtypes = [vp, C.c_char_p, C.POINTER(C.c_int64)]
     L.bvhar_cuda_fit_get_state.argtypes = [vp, C.c_int, C.c_int, C.c_char_p, c_dp, C.c_int64]

@@ -67,6 +67,19 @@ class CudaFit:
         check(self.L.bvhar_cuda_fit_last_ms(self._h, C.byref(v)))
         return v.value
 
+    def set_profiling(self, on: bool):
+        check(self.L.bvhar_cuda_fit_set_profiling(self._h, int(on)))
+
+    def profile(self) -> Dict[str, Any]:
+        """{kernel name: (launches, total ms)} accumulated while profiling was on."""
+        buf = C.create_string_buffer(8192)
+        check(self.L.bvhar_cuda_fit_profile(self._h, buf, 8192))
+        out = {}
+        for line in buf.value.decode().splitlines():
+            nm, cnt, ms = line.split()
+            out[nm] = (int(cnt), float(ms))
+        return out
+
     def launch_count(self) -> int:
         v = C.c_int64()
         check(self.L.bvhar_cuda_fit_launch_count(self._h, C.byref(v)))
@@ -98,6 +111,15 @@ class CudaFit:
         check(self.L.bvhar_cuda_fit_record_dims(self._h, name.encode(), C.byref(r), C.byref(c)))
         out = np.empty((r.value, c.value), order="F")
         check(self.L.bvhar_cuda_fit_record(self._h, window, chain, name.encode(), out.ctypes.data_as(c_dp), r.value, c.value))
+        return out
+
+    def record_all(self, name: str) -> np.ndarray:
+        """ndarray[unit, draw, column] of one record for every unit (one bulk device-to-host copy)."""
+        r, c = C.c_int64(), C.c_int64()
+        check(self.L.bvhar_cuda_fit_record_dims(self._h, name.encode(), C.byref(r), C.byref(c)))
+        U = self.packed.n_windows * self.packed.n_chains
+        out = np.empty((U, r.value, c.value))
+        check(self.L.bvhar_cuda_fit_record_all(self._h, name.encode(), out.ctypes.data_as(c_dp), U, r.value, c.value))
         return out
 
     def records(self, window: int = 0, chain: int = 0) -> Dict[str, np.ndarray]:

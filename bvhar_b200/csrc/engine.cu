@@ -96,11 +96,39 @@ struct bvhar_fit {
   GemmArgs g1{}, g2{}, g3{};
   bool g3_aligned = true;
   bool timed = false;
+  // per-kernel profiling (eager launches bracketed by CUDA events on the engine's stream)
+  bool profiling = false;
+  struct ProfEv { int id; cudaEvent_t a, b; };
+  std::vector<ProfEv> prof_pending;
+  std::vector<cudaEvent_t> prof_pool;
+  std::vector<std::string> prof_names;
+  std::vector<double> prof_ms;
+  std::vector<long long> prof_cnt;
+  int prof_id(const char* nm) {
+    for (size_t i = 0; i < prof_names.size(); ++i) if (prof_names[i] == nm) return (int)i;
+    prof_names.push_back(nm); prof_ms.push_back(0.0); prof_cnt.push_back(0);
+    return (int)prof_names.size() - 1;
+  }
+  cudaEvent_t prof_event() {
+    if (!prof_pool.empty()) { cudaEvent_t e = prof_pool.back(); prof_pool.pop_back(); return e; }
+    cudaEvent_t e; cudaEventCreate(&e); return e;
+  }
+  void prof_collect() {
+    for (auto& pe : prof_pending) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, pe.a, pe.b) == cudaSuccess) { prof_ms[pe.id] += ms; prof_cnt[pe.id] += 1; }
+      else cudaGetLastError();
+      prof_pool.push_back(pe.a); prof_pool.push_back(pe.b);
+    }
+    prof_pending.clear();
+  }
 
   ~bvhar_fit() {
     cudaSetDevice(device);
     for (auto& g : graph)
       if (g) cudaGraphExecDestroy(g);
+    for (auto& pe : prof_pending) { cudaEventDestroy(pe.a); cudaEventDestroy(pe.b); }
+    for (auto& e : prof_pool) cudaEventDestroy(e);
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
     if (st) cudaStreamDestroy(st);
@@ -108,23 +136,32 @@ struct bvhar_fit {
 
   int enqueue_sweep(bool record, bool count) {
     int nl = 0;
-    CU(launch_bump(P, 1, 0, st)); ++nl;
-    if (D.prior != 1) { CU(launch_prior(D, P, PC, 0, st)); ++nl; }
+#define LAUNCH(name, expr)                                                   \
+    do {                                                                       \
+      cudaEvent_t ea__ = nullptr, eb__ = nullptr;                              \
+      if (profiling) { ea__ = prof_event(); eb__ = prof_event(); cudaEventRecord(ea__, st); } \
+      CU(expr);                                                                \
+      if (profiling) { cudaEventRecord(eb__, st); prof_pending.push_back({prof_id(name), ea__, eb__}); } \
+      ++nl;                                                                    \
+    } while (0)
+    LAUNCH("bump", launch_bump(P, 1, 0, st));
+    if (D.prior != 1) LAUNCH("prior_coef", launch_prior(D, P, PC, 0, st));
     if (D.sv) {
-      CU(launch_sv_prep(D, P, st)); ++nl;
-      CU(launch_dgemm_tn(g1, st)); ++nl;
-      CU(launch_dgemm_tn(g2, st)); ++nl;
+      LAUNCH("sv_prep", launch_sv_prep(D, P, st));
+      LAUNCH("gram_S_dmma", launch_dgemm_tn(g1, st));
+      LAUNCH("gram_C_dmma", launch_dgemm_tn(g2, st));
     }
-    CU(launch_coef(D, P, vscratch.p, smem_limit, st)); ++nl;
-    if (D.prior != 1) { CU(launch_prior(D, P, PC, 1, st)); ++nl; }
-    CU(launch_dgemm_tn(g3, st)); ++nl;
-    if (D.k > 1) { CU(launch_impact(D, P, gscratch.p, st)); ++nl; }
-    if (D.sv) { CU(launch_sv_state(D, P, st)); nl += 3; }
-    else { CU(launch_ldlt_state(D, P, st)); ++nl; }
+    LAUNCH("coef_draw", launch_coef(D, P, vscratch.p, smem_limit, st));
+    if (D.prior != 1) LAUNCH("prior_contem", launch_prior(D, P, PC, 1, st));
+    LAUNCH("latent_dmma", launch_dgemm_tn(g3, st));
+    if (D.k > 1) LAUNCH("impact_draw", launch_impact(D, P, gscratch.p, st));
+    if (D.sv) { LAUNCH("sv_state", launch_sv_state(D, P, st)); nl += 2; }
+    else LAUNCH("ldlt_state", launch_ldlt_state(D, P, st));
     if (record) {
-      CU(launch_record(D, P, R, st)); ++nl;
-      CU(launch_bump(P, 0, 1, st)); ++nl;
+      LAUNCH("record", launch_record(D, P, R, st));
+      LAUNCH("bump", launch_bump(P, 0, 1, st));
     }
+#undef LAUNCH
     if (count) launches_per_sweep[record ? 1 : 0] = nl;
     return 0;
   }
@@ -137,7 +174,7 @@ struct bvhar_fit {
     CU(cudaEventRecord(ev0, st));
     for (int s = 0; s < n; ++s) {
       if (record && rec_filled >= R.cap) return fail(BVHAR_ERR_BAD_ARG, "record buffers are full (num_iter - num_burn draws)");
-      if (!graph[gi] && launches_per_sweep[gi] == 0) {
+      if (profiling || (!graph[gi] && launches_per_sweep[gi] == 0)) {
         int rc = enqueue_sweep(record, true);
         if (rc) return rc;
       } else {
@@ -164,6 +201,7 @@ struct bvhar_fit {
   int sync() {
     CU(cudaSetDevice(device));
     CU(cudaStreamSynchronize(st));
+    prof_collect();
     if (timed) {
       float ms = 0.f;
       if (cudaEventElapsedTime(&ms, ev0, ev1) == cudaSuccess) last_ms = ms;
@@ -799,6 +837,24 @@ int bvhar_cuda_fit_last_ms(bvhar_fit* fit, double* ms) {
   *ms = fit->last_ms;
   return 0;
 }
+int bvhar_cuda_fit_set_profiling(bvhar_fit* fit, int on) {
+  if (!fit) return fail(BVHAR_ERR_BAD_ARG, "null fit handle");
+  fit->profiling = on != 0;
+  if (on) { std::fill(fit->prof_ms.begin(), fit->prof_ms.end(), 0.0); std::fill(fit->prof_cnt.begin(), fit->prof_cnt.end(), 0LL); }
+  return 0;
+}
+int bvhar_cuda_fit_profile(bvhar_fit* fit, char* buf, int64_t buflen) {
+  if (!fit || !buf) return fail(BVHAR_ERR_BAD_ARG, "null argument");
+  std::string s;
+  char line[160];
+  for (size_t i = 0; i < fit->prof_names.size(); ++i) {
+    snprintf(line, sizeof line, "%s %lld %.6f\n", fit->prof_names[i].c_str(), fit->prof_cnt[i], fit->prof_ms[i]);
+    s += line;
+  }
+  if ((int64_t)s.size() + 1 > buflen) return fail(BVHAR_ERR_BAD_ARG, "buffer too small");
+  std::memcpy(buf, s.c_str(), s.size() + 1);
+  return 0;
+}
 int bvhar_cuda_fit_launch_count(bvhar_fit* fit, int64_t* launches) {
   if (!fit || !launches) return fail(BVHAR_ERR_BAD_ARG, "null argument");
   *launches = fit->launches;
@@ -832,6 +888,30 @@ int bvhar_cuda_fit_record(bvhar_fit* fit, int window, int chain, const char* nam
       // thin_record draw.h:1297-1310: rows 0, thin, 2 thin, ... of the kept draws
       for (int64_t j = 0; j < cols; ++j)
         for (int64_t i = 0; i < rows; ++i) out[j * rows + i] = tmp[(size_t)(i * fit->thin) * r.cols + j];
+      return 0;
+    }
+  return fail(BVHAR_ERR_BAD_ARG, std::string("no record named ") + name);
+}
+// Every unit's record at once: out[unit][kept draw][column] (C order), i.e. the device layout, moved with
+// one 2-D copy per unit (a single flat copy when nothing was thinned or left unfilled).
+int bvhar_cuda_fit_record_all(bvhar_fit* fit, const char* name, double* out, int64_t units, int64_t rows, int64_t cols) {
+  if (!fit || !name || !out) return fail(BVHAR_ERR_BAD_ARG, "null argument");
+  const Dims& D = fit->D;
+  CU(cudaSetDevice(fit->device));
+  CU(cudaStreamSynchronize(fit->st));
+  for (auto& r : fit->rec_order)
+    if (r.name == name) {
+      const int64_t kept = (fit->rec_filled + fit->thin - 1) / fit->thin;
+      if (units != D.U || rows != kept || cols != r.cols) return fail(BVHAR_ERR_BAD_ARG, "record dims mismatch");
+      if (kept == 0) return 0;
+      const size_t row_b = (size_t)r.cols * sizeof(double);
+      if (fit->thin == 1 && fit->rec_filled == fit->R.cap) {
+        CU(cudaMemcpy(out, *r.slot, (size_t)D.U * kept * row_b, cudaMemcpyDeviceToHost));
+      } else {
+        for (int u = 0; u < D.U; ++u)
+          CU(cudaMemcpy2D(out + (size_t)u * kept * r.cols, row_b, *r.slot + (size_t)u * fit->R.cap * r.cols, row_b * fit->thin, row_b,
+                          (size_t)kept, cudaMemcpyDeviceToHost));
+      }
       return 0;
     }
   return fail(BVHAR_ERR_BAD_ARG, std::string("no record named ") + name);

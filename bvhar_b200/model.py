@@ -1,0 +1,314 @@
+"""Bayesian VAR / VHAR front end on the CUDA Gibbs engine.
+
+``VarBayes`` and ``VharBayes`` keep the constructor arguments, attributes and method names of the
+reference's Python classes (python/src/bvhar/model/_bayes.py:17-181 ``_AutoregBayes``, :183-664
+``VarBayes``, :666-1113 ``VharBayes``; R: ``var_bayes()`` R/var-bayes.R:81, ``vhar_bayes()``
+R/vhar-bayes.R, ``forecast_roll()/forecast_expand()`` R/summary-forecast.R:412-588).  What differs is
+underneath: every chain of ``fit()`` and every (window, chain) refit of ``roll_forecast()`` /
+``expand_forecast()`` runs as one batch of units on the GPU.
+
+Draws are kept as ``{record name: ndarray[chain, draw, column]}`` in ``param_`` (the reference builds
+a pandas frame of the same columns, _misc.py:122-148); ``to_frame()`` produces that frame on demand.
+"""
+from __future__ import annotations
+
+import warnings
+from math import floor
+from typing import Dict, List, Optional
+
+import numpy as np
+
+from . import _abi
+from ._abi import REC_ALL, REC_COEF, REC_LVOL_LAST, REC_SPARSE, PackedFit
+from ._design import build_design, build_grpmat, build_response, build_vhar, build_vhar_design
+from ._engine import CudaFit, forecast_density
+from ._spec import (PRIOR_TYPE, DlConfig, GdpConfig, HorseshoeConfig, InterceptConfig, LdltConfig, MinnesotaConfig,
+                    NgConfig, SsvsConfig, SvConfig, _BayesConfig, make_inits)
+
+
+def _check_np(data) -> np.ndarray:
+    arr = np.asarray(data.values if hasattr(data, "values") else data)
+    if arr.ndim != 2:
+        raise ValueError("Numpy array must be 2-dim.")
+    if not np.issubdtype(arr.dtype, np.number) or np.issubdtype(arr.dtype, np.bool_):
+        raise ValueError("All elements should be numeric.")
+    return np.asfortranarray(arr, dtype=np.float64)
+
+
+class _AutoregBayes:
+    def __init__(self, data, lag, p, n_chain=1, n_iter=1000, n_burn=None, n_thin=1, bayes_config=None, cov_config=None,
+                 intercept_config=None, fit_intercept=True, minnesota="longrun", ggl=True, verbose=False, seed=None,
+                 device: int = 0, record_mask: int = REC_ALL):
+        self.y_ = _check_np(data)
+        self.n_features_in_ = self.y_.shape[1]
+        self.p_ = p
+        self.lag_ = lag
+        if self.y_.shape[0] <= self.lag_:
+            raise ValueError(f"'data' rows must be larger than 'lag' = {self.lag_}")
+        self.chains_ = int(n_chain)
+        self.iter_ = int(n_iter)
+        self.burn_ = int(floor(n_iter / 2) if n_burn is None else n_burn)
+        self.thin_ = int(n_thin)
+        self.fit_intercept = fit_intercept
+        self.group_ = build_grpmat(self.p_, self.n_features_in_, minnesota)
+        self._group_id = np.array(list(dict.fromkeys(self.group_.flatten(order="F").tolist())), dtype=np.int32)
+        self._own_id = None
+        self._cross_id = None
+        self._ggl = ggl
+        self._verbose = verbose
+        self._device = device
+        self._record_mask = record_mask
+        self._rng = np.random.default_rng(seed)
+        self.cov_spec_ = LdltConfig() if cov_config is None else cov_config
+        self.spec_ = SsvsConfig() if bayes_config is None else bayes_config
+        self.intercept_spec_ = InterceptConfig() if intercept_config is None else intercept_config
+        self._prior_type = PRIOR_TYPE.get(self.spec_.prior)
+        self.is_fitted_ = False
+        self.coef_ = None
+        self.intercept_ = None
+        self.param_names_ = None
+        self.param_: Optional[Dict[str, np.ndarray]] = None
+        self.sparse_coef_ = None
+        self.init_ = None
+        self._fit_obj = None
+
+    # -- shared pieces ----------------------------------------------------------------------
+    def _validate(self):
+        if not isinstance(self.cov_spec_, LdltConfig):
+            raise TypeError("`cov_config` should be `LdltConfig` or `SvConfig`.")
+        if not isinstance(self.intercept_spec_, InterceptConfig):
+            raise TypeError("`intercept_config` should be `InterceptConfig` when 'fit_intercept' is True.")
+        if not isinstance(self.spec_, _BayesConfig):
+            raise TypeError("`bayes_spec` should be the derived class of `_BayesConfig`.")
+        self.cov_spec_.update(self.n_features_in_)
+        self.intercept_spec_.update(self.n_features_in_)
+        if isinstance(self.spec_, SsvsConfig):
+            self.spec_.update(self._group_id, self._own_id, self._cross_id)
+        elif isinstance(self.spec_, MinnesotaConfig):
+            self.spec_.update(self.y_, self.p_, self.n_features_in_)
+
+    @property
+    def _is_sv(self) -> bool:
+        return isinstance(self.cov_spec_, SvConfig)
+
+    def _make_inits(self):
+        n_design = self.design_.shape[1]
+        self.init_ = make_inits(self.spec_.prior, self._is_sv, self.n_features_in_, n_design, self.response_.shape[0],
+                                len(self._group_id), self.chains_, self._rng)
+
+    def _seeds(self, *shape):
+        return self._rng.integers(1, np.iinfo(np.int32).max, size=shape)
+
+    def _pack(self, x, y, seeds, win_row0=None, win_nrow=None, record_mask=None, lvol_from_init=False) -> PackedFit:
+        return PackedFit(self.chains_, self.iter_, self.burn_, self.thin_, x, y, self.cov_spec_.to_dict(),
+                         self.spec_.to_dict(), self.intercept_spec_.to_dict(), self.init_, int(self._prior_type),
+                         self._group_id, self._own_id, self._cross_id, self.group_, self.fit_intercept, seeds,
+                         is_group=self._ggl, win_row0=win_row0, win_nrow=win_nrow,
+                         record_mask=self._record_mask if record_mask is None else record_mask, device=self._device,
+                         lvol_from_init=lvol_from_init)
+
+    def _coef_name(self) -> str:
+        return "alpha"
+
+    def fit(self):
+        """Conduct MCMC on the GPU and compute posterior means."""
+        packed = self._pack(self.design_, self.response_, self._seeds(1, self.chains_))
+        fit = CudaFit(packed)
+        cb = None
+        if self._verbose:
+            cb = lambda done, total: print(f"[{self.chains_} chains] {done} / {total}", flush=True) or False
+        try:
+            fit.run(cb)
+        except _abi.BvharCudaError as e:
+            if e.status != 3:
+                raise
+            warnings.warn(str(e))
+        names = fit.record_names()
+        recs = {nm: fit.record_all(nm) for nm in names}  # [chain, draw, column]
+        fit.close()
+        self.param_ = recs
+        self.param_names_ = [nm.replace("_record", "") for nm in names]
+        k = self.n_features_in_
+        self.coef_ = recs["alpha_record"].mean(axis=(0, 1)).reshape(k, -1).T
+        if "alpha_sparse_record" in recs:
+            self.sparse_coef_ = np.nanmean(recs["alpha_sparse_record"], axis=(0, 1)).reshape(k, -1).T
+        if self.fit_intercept:
+            self.intercept_ = recs["c_record"].mean(axis=(0, 1)).reshape(k)
+            self.coef_ = np.concatenate([self.coef_, self.intercept_[None, :]], axis=0)
+            if self.sparse_coef_ is not None:
+                self.sparse_coef_ = np.concatenate([self.sparse_coef_, np.nanmean(recs["c_sparse_record"], axis=(0, 1))[None, :]], axis=0)
+        self.is_fitted_ = True
+        return self
+
+    def to_frame(self):
+        """Draws as the reference's wide pandas frame (one column per parameter, _misc.py:122-148)."""
+        import pandas as pd
+        frames = []
+        tot = 0
+        for c in range(self.chains_):
+            cols = {}
+            for nm, arr in self.param_.items():
+                base = nm.replace("_record", "")
+                if self._coef_name() == "phi":
+                    base = base.replace("alpha", "phi")
+                for j in range(arr.shape[2]):
+                    cols[f"{base}[{j + 1}]"] = arr[c, :, j]
+            df = pd.DataFrame(cols)
+            df["_chain"] = c
+            df["_iteration"] = np.arange(1, len(df) + 1)
+            df["_draw"] = np.arange(tot + 1, tot + len(df) + 1)
+            tot += len(df)
+            frames.append(df)
+        return pd.concat(frames, axis=0)
+
+    def _chain_records(self, sparse=False) -> List[Dict[str, np.ndarray]]:
+        if not self.is_fitted_:
+            raise RuntimeError("call fit() first")
+        return [{nm: arr[c] for nm, arr in self.param_.items()} for c in range(self.chains_)]
+
+    @staticmethod
+    def _summarise(dens: np.ndarray, dim: int, level: float, med: bool):
+        step = dens.shape[0]
+        draws = dens.reshape(step, -1, dim)  # [step, draw, variable]
+        return {
+            "forecast": np.median(draws, axis=1) if med else np.mean(draws, axis=1),
+            "se": np.std(draws, axis=1, ddof=1),
+            "lower": np.quantile(draws, level / 2, axis=1),
+            "upper": np.quantile(draws, 1 - level / 2, axis=1),
+        }
+
+    def _har(self):
+        return None
+
+    def predict(self, n_ahead: int, level=.05, stable=False, sparse=False, med=False, sv=True):
+        """'n_ahead'-step density forecast from the stored draws (forecaster.h:494-568)."""
+        recs = self._chain_records()
+        dens, _ = forecast_density(recs, [self.y_] * self.chains_, n_ahead, self.lag_, self.fit_intercept, self._is_sv,
+                                   self._seeds(self.chains_), har_trans=self._har(), sv=sv, stable=stable, sparse=sparse,
+                                   device=self._device)
+        k = self.n_features_in_
+        allchains = np.concatenate([d.reshape(n_ahead, -1, k) for d in dens], axis=1).reshape(n_ahead, -1)
+        return self._summarise(allchains, k, level, med)
+
+    def _outforecast(self, n_ahead: int, test, expanding: bool, level, stable, sparse, med, sv):
+        """forecast_roll / forecast_expand: window 0 reuses the fit, windows >= 1 are refitted, every
+        (window, chain) in one GPU batch (forecaster.h:575-807, 851-875, 920-956)."""
+        test = _check_np(test)
+        k = self.n_features_in_
+        n_hor = test.shape[0] - n_ahead + 1
+        if n_hor < 1:
+            raise ValueError("'test' needs at least 'n_ahead' rows")
+        tot = np.asfortranarray(np.vstack([self.y_, test]))
+        x_tot, y_tot = self._design_of(tot)
+        n0 = self.response_.shape[0]
+        if expanding:
+            row0 = [0] * n_hor
+            nrow = [n0 + w for w in range(n_hor)]
+        else:
+            row0 = list(range(n_hor))
+            nrow = [n0] * n_hor
+        seeds = self._seeds(self.chains_, n_hor).T  # _bayes.py: reshape(chains, -1).T
+        seed_fc = self._seeds(self.chains_)
+        units: List[Dict[str, np.ndarray]] = list(self._chain_records())
+        if n_hor > 1:
+            mask = REC_COEF | REC_SPARSE | REC_LVOL_LAST
+            packed = self._pack(x_tot, y_tot, seeds[1:], win_row0=row0[1:], win_nrow=nrow[1:], record_mask=mask,
+                                lvol_from_init=self._is_sv and expanding)
+            fit = CudaFit(packed)
+            try:
+                fit.run(None)
+            except _abi.BvharCudaError as e:
+                if e.status != 3:
+                    raise
+                warnings.warn(str(e))
+            bulk = {nm: fit.record_all(nm) for nm in fit.record_names()}
+            for u in range((n_hor - 1) * self.chains_):
+                units.append({nm: arr[u] for nm, arr in bulk.items()})
+            fit.close()
+        last = []
+        for w in range(n_hor):
+            end = self.lag_ + row0[w] + nrow[w]  # rows of the window's response end here in `tot`
+            for c in range(self.chains_):
+                last.append(tot[:end])
+        valid = test[n_ahead] if test.shape[0] > n_ahead else None  # y_test.row(step), forecaster.h:802
+        dens, lpl = forecast_density(units, last, n_ahead, self.lag_, self.fit_intercept, self._is_sv,
+                                     np.tile(seed_fc, n_hor), har_trans=self._har(), sv=sv, valid_vec=valid, stable=stable,
+                                     sparse=sparse, device=self._device)
+        out = {"forecast": [], "se": [], "lower": [], "upper": []}
+        for w in range(n_hor):
+            d = np.concatenate([dens[w * self.chains_ + c][-1:, :].reshape(1, -1, k) for c in range(self.chains_)], axis=1)
+            s = self._summarise(d.reshape(1, -1), k, level, med)  # only the last step is kept (forecaster.h:803)
+            for key in out:
+                out[key].append(s[key])
+        res = {key: np.concatenate(v, axis=0) for key, v in out.items()}
+        if lpl is not None:
+            l = lpl.reshape(n_hor, self.chains_, n_ahead).mean(axis=2)  # returnLpl(): mean over steps
+            res["lpl"] = np.median(l, axis=1) if med else np.mean(l, axis=1)
+        return res
+
+    def roll_forecast(self, n_ahead: int, test, level=.05, stable=False, sparse=False, med=False, sv=True):
+        return self._outforecast(n_ahead, test, False, level, stable, sparse, med, sv)
+
+    def expand_forecast(self, n_ahead: int, test, level=.05, stable=False, sparse=False, med=False, sv=True):
+        return self._outforecast(n_ahead, test, True, level, stable, sparse, med, sv)
+
+
+class VarBayes(_AutoregBayes):
+    """Bayesian VAR(lag) — arguments as python/src/bvhar/model/_bayes.py:229-246."""
+
+    def __init__(self, data, lag=1, n_chain=1, n_iter=1000, n_burn=None, n_thin=1, bayes_config=None, cov_config=None,
+                 intercept_config=None, fit_intercept=True, minnesota=True, ggl=True, verbose=False, n_thread=1, seed=None,
+                 device: int = 0, record_mask: int = REC_ALL):
+        super().__init__(data, lag, lag, n_chain, n_iter, n_burn, n_thin, bayes_config, cov_config, intercept_config,
+                         fit_intercept, "short" if minnesota else "no", ggl, verbose, seed, device, record_mask)
+        self.design_ = build_design(self.y_, lag, fit_intercept)
+        self.response_ = build_response(self.y_, lag, lag + 1)
+        if minnesota:  # _bayes.py:309-310
+            self._own_id = np.arange(2, 2 * self.p_, 2, dtype=np.int32)
+            self._cross_id = np.arange(1, 2 * self.p_, 2, dtype=np.int32)
+            if self._own_id.size == 0:
+                self._own_id = np.array([2], dtype=np.int32)
+        else:
+            self._own_id = np.array([2], dtype=np.int32)
+            self._cross_id = np.array([2], dtype=np.int32)
+        self._validate()
+        self.thread_ = n_thread
+        self._make_inits()
+
+    def _design_of(self, y):
+        return build_design(y, self.lag_, self.fit_intercept), build_response(y, self.lag_, self.lag_ + 1)
+
+
+class VharBayes(_AutoregBayes):
+    """Bayesian VHAR(week, month) — arguments as python/src/bvhar/model/_bayes.py:716-735."""
+
+    def __init__(self, data, week=5, month=22, n_chain=1, n_iter=1000, n_burn=None, n_thin=1, bayes_config=None,
+                 cov_config=None, intercept_config=None, fit_intercept=True, minnesota="longrun", ggl=True, verbose=False,
+                 n_thread=1, seed=None, device: int = 0, record_mask: int = REC_ALL):
+        super().__init__(data, month, 3, n_chain, n_iter, n_burn, n_thin, bayes_config, cov_config, intercept_config,
+                         fit_intercept, minnesota, ggl, verbose, seed, device, record_mask)
+        self.week_ = week
+        self.month_ = month
+        self.design_ = build_vhar_design(self.y_, week, month, fit_intercept)
+        self.response_ = build_response(self.y_, month, month + 1)
+        if minnesota == "longrun":  # _bayes.py:742-750
+            self._own_id = np.array([2, 4, 6], dtype=np.int32)
+            self._cross_id = np.array([1, 3, 5], dtype=np.int32)
+        elif minnesota == "short":
+            self._own_id = np.array([2], dtype=np.int32)
+            self._cross_id = np.array([1, 3, 4], dtype=np.int32)
+        else:
+            self._own_id = np.array([1], dtype=np.int32)
+            self._cross_id = np.array([2], dtype=np.int32)
+        self._validate()
+        self.thread_ = n_thread
+        self._make_inits()
+
+    def _coef_name(self) -> str:
+        return "phi"
+
+    def _har(self):
+        return build_vhar(self.n_features_in_, self.week_, self.month_, self.fit_intercept)
+
+    def _design_of(self, y):
+        return build_vhar_design(y, self.week_, self.month_, self.fit_intercept), build_response(y, self.month_, self.month_ + 1)

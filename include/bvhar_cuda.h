@@ -196,6 +196,11 @@ int bvhar_cuda_fit_step(bvhar_fit* fit, int n_sweeps, int record);
 int bvhar_cuda_fit_sync(bvhar_fit* fit);
 /* Device time (ms, CUDA events on the engine's stream) of the last fit_step / fit_run call. */
 int bvhar_cuda_fit_last_ms(bvhar_fit* fit, double* ms);
+/* Per-kernel timing: while on, sweeps are launched eagerly with a CUDA-event pair around every kernel
+ * (the sv_state entry covers its three kernels); bvhar_cuda_fit_profile writes one line per kernel,
+ * "name launches total_ms". */
+int bvhar_cuda_fit_set_profiling(bvhar_fit* fit, int on);
+int bvhar_cuda_fit_profile(bvhar_fit* fit, char* buf, int64_t buflen);
 /* Number of kernels launched by this engine since creation. */
 int bvhar_cuda_fit_launch_count(bvhar_fit* fit, int64_t* launches);
 
@@ -206,6 +211,9 @@ int bvhar_cuda_fit_launch_count(bvhar_fit* fit, int64_t* launches);
 int bvhar_cuda_fit_record_dims(bvhar_fit* fit, const char* name, int64_t* rows, int64_t* cols);
 int bvhar_cuda_fit_record(bvhar_fit* fit, int window, int chain, const char* name, double* out,
                           int64_t rows, int64_t cols);
+/* All units of one record in a single call: out[unit][kept draw][column], C order, unit = window *
+ * n_chains + chain. */
+int bvhar_cuda_fit_record_all(bvhar_fit* fit, const char* name, double* out, int64_t units, int64_t rows, int64_t cols);
 /* Names of the records this fit exports, '\n'-separated, in the reference's list order. */
 int bvhar_cuda_fit_record_names(bvhar_fit* fit, char* buf, int64_t buflen);
 

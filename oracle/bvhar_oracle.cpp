@@ -97,6 +97,7 @@ struct Chain {
   double coef_gamma_shape = 0, coef_gamma_rate = 0, contem_gamma_shape = 0, contem_gamma_rate = 0;
   Records rec;
   uint32_t sweep_count = 0;
+  int inner_threads = 1;
 
   // ---------------------------------------------------------------- construction
   // McmcTriangular ctor tri.h:40-71, McmcReg tri.h:363-367, McmcSv tri.h:388-396.
@@ -611,8 +612,11 @@ struct Chain {
   void update_state_sv() {
     Mat U = ortho_latent();
     for (auto& x : U.v) x = std::log(x * x + .0001);
-    Vec u(n), z(n), ys(n);
+    // Series are independent given the orthogonalised residuals; with the addressed (Philox) stream
+    // they may run concurrently when fewer units than threads are being swept (inner_threads > 1).
+#pragma omp parallel for num_threads(inner_threads) schedule(dynamic, 1) if (inner_threads > 1 && rng.philox)
     for (int i = 0; i < k; ++i) {
+      Vec u(n), z(n), ys(n);
       if (rng.philox) {
         // element (series i, time t) = i * 2*ceil(n/2) + t: the two lanes of a Philox pair are
         // consecutive time points of the same series (DESIGN.md "Random streams")
@@ -1227,7 +1231,10 @@ int oracle_fit_step(void* h, int n_sweeps, int record) {
   Fit* F = (Fit*)h;
   const int U = (int)F->chains.size();
   const int nt = F->nthreads > 0 ? F->nthreads : omp_get_max_threads();
-#pragma omp parallel for num_threads(nt) schedule(dynamic, 1)   // tri.h:1222 / fc.h:626: chains and windows
+  const int outer = U < nt ? U : nt, inner = U < nt ? nt / U : 1;
+  omp_set_max_active_levels(2);
+  for (auto& c : F->chains) c->inner_threads = inner;
+#pragma omp parallel for num_threads(outer) schedule(dynamic, 1)   // tri.h:1222 / fc.h:626: chains and windows
   for (int u = 0; u < U; ++u)
     for (int s = 0; s < n_sweeps; ++s) F->chains[u]->sweep(record != 0);
   return 0;

@@ -40,6 +40,7 @@ inline void gemm_tn(const Mat& A, const Mat& B, Mat& C) {
       for (int i = 0; i < m; ++i) {
         const double* a = A.col(i);
         double s = 0;
+#pragma omp simd reduction(+ : s)
         for (int t = k0; t < k1; ++t) s += a[t] * b[t];
         C(i, j) += s;
       }
