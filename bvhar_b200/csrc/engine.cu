@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -90,7 +91,8 @@ struct bvhar_fit {
   DevBuf<long long> d_off, g1_b, g1_c, g2_b, g2_c, g3_a, g3_b, g3_y;
   DevBuf<uint32_t> seeds, iter;
   DevBuf<double> H, Z, Dinv, YLD, S, Cm, Acoef, alpha, cvec, prec, contem, L, chol_prec, sparse_coef, sparse_contem;
-  DevBuf<double> lvol_init, lvol_sig, diag, znorm, hN[4], hG[3], hq[4], hs, vscratch, gscratch;
+  DevBuf<double> lvol_init, lvol_sig, diag, znorm, hN[4], hG[3], hq[4], hs, vscratch, gscratch, Pfac;
+  bool coef_v2 = false;
   std::map<std::string, std::unique_ptr<DevBuf<double>>> rec;
   std::vector<RecordSpec> rec_order;
   GemmArgs g1{}, g2{}, g3{};
@@ -151,11 +153,21 @@ struct bvhar_fit {
       LAUNCH("gram_S_dmma", launch_dgemm_tn(g1, st));
       LAUNCH("gram_C_dmma", launch_dgemm_tn(g2, st));
     }
-    LAUNCH("coef_draw", launch_coef(D, P, vscratch.p, smem_limit, st));
+    if (coef_v2) {
+      if (D.sv) LAUNCH("coef_pbuild", launch_coef_v2(0, D, P, Pfac.p, smem_limit, st));
+      LAUNCH("coef_chol", launch_coef_v2(1, D, P, Pfac.p, smem_limit, st));
+      LAUNCH("coef_seq", launch_coef_v2(2, D, P, Pfac.p, smem_limit, st));
+    } else {
+      LAUNCH("coef_draw", launch_coef(D, P, vscratch.p, smem_limit, st));
+    }
     if (D.prior != 1) LAUNCH("prior_contem", launch_prior(D, P, PC, 1, st));
     LAUNCH("latent_dmma", launch_dgemm_tn(g3, st));
     if (D.k > 1) LAUNCH("impact_draw", launch_impact(D, P, gscratch.p, st));
-    if (D.sv) { LAUNCH("sv_state", launch_sv_state(D, P, st)); nl += 2; }
+    if (D.sv) {
+      LAUNCH("sv_mix", launch_sv_state(0, D, P, st));
+      LAUNCH("sv_solve", launch_sv_state(1, D, P, st));
+      LAUNCH("sv_finish", launch_sv_state(2, D, P, st));
+    }
     else LAUNCH("ldlt_state", launch_ldlt_state(D, P, st));
     if (record) {
       LAUNCH("record", launch_record(D, P, R, st));
@@ -517,7 +529,9 @@ int build(const bvhar_fit_desc* d, bvhar_fit** out) {
   // ---- scratch + setup kernels ----
   bool need_v = false;
   int ch_plan = 0;
-  if (!coef_plan(D, F->smem_limit, &ch_plan, &need_v))
+  F->coef_v2 = coef_v2_fits(D, F->smem_limit) && getenv("BVHAR_COEF_V1") == nullptr;
+  if (F->coef_v2) CU(F->Pfac.alloc((size_t)U * k * D.ldS));
+  else if (!coef_plan(D, F->smem_limit, &ch_plan, &need_v))
     return fail(BVHAR_ERR_UNSUPPORTED, "dim_design too large for the shared-memory Cholesky of this build (packed d(d+1)/2 doubles must fit 227 KB)");
   if (need_v) CU(F->vscratch.alloc((size_t)U * 2 * k * dd));
   CU(F->gscratch.alloc((size_t)U * impact_gsize(D)));
@@ -963,14 +977,20 @@ int bvhar_cuda_fit_run_stage(bvhar_fit* fit, int stage, int iter) {
     case 3: if (D.sv) CU(launch_sv_prep(D, fit->P, fit->st)); break;
     case 4:
       if (D.sv) { CU(launch_dgemm_tn(fit->g1, fit->st)); CU(launch_dgemm_tn(fit->g2, fit->st)); }
-      CU(launch_coef(D, fit->P, fit->vscratch.p, fit->smem_limit, fit->st));
+      if (fit->coef_v2) {
+        CU(launch_coef_v2(0, D, fit->P, fit->Pfac.p, fit->smem_limit, fit->st));
+        CU(launch_coef_v2(1, D, fit->P, fit->Pfac.p, fit->smem_limit, fit->st));
+        CU(launch_coef_v2(2, D, fit->P, fit->Pfac.p, fit->smem_limit, fit->st));
+      } else {
+        CU(launch_coef(D, fit->P, fit->vscratch.p, fit->smem_limit, fit->st));
+      }
       break;
     case 5: CU(launch_prior(D, fit->P, fit->PC, 1, fit->st)); break;
     case 6: CU(launch_dgemm_tn(fit->g3, fit->st)); break;
     case 7: if (D.k > 1) CU(launch_impact(D, fit->P, fit->gscratch.p, fit->st)); break;
     case 8: break;  // chol_lower is rebuilt inside the contemporaneous draw
     case 9:
-      if (D.sv) CU(launch_sv_state(D, fit->P, fit->st));
+      if (D.sv) { CU(launch_sv_state(0, D, fit->P, fit->st)); CU(launch_sv_state(1, D, fit->P, fit->st)); CU(launch_sv_state(2, D, fit->P, fit->st)); }
       else CU(launch_ldlt_state(D, fit->P, fit->st));
       break;
     default: return fail(BVHAR_ERR_BAD_ARG, "stage must be 1..9");

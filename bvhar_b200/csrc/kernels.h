@@ -11,9 +11,11 @@ bool coef_plan(const Dims& D, size_t smem_limit, int* CH_out, bool* vglobal_out)
 cudaError_t launch_coef(const Dims& D, const DevPtrs& P, double* vscratch, size_t smem_limit, cudaStream_t st);
 cudaError_t launch_draw_coef_batched(long long batch, int d, const double* Pp, const double* b, const double* z, double* out,
                                      cudaStream_t st);
+bool coef_v2_fits(const Dims& D, size_t smem_limit);
+cudaError_t launch_coef_v2(int part, const Dims& D, const DevPtrs& P, double* Pfac, size_t smem_limit, cudaStream_t st);
 int impact_gsize(const Dims& D);
 cudaError_t launch_impact(const Dims& D, const DevPtrs& P, double* gscratch, cudaStream_t st);
-cudaError_t launch_sv_state(const Dims& D, const DevPtrs& P, cudaStream_t st);
+cudaError_t launch_sv_state(int part, const Dims& D, const DevPtrs& P, cudaStream_t st);  // 0 mix, 1 solve, 2 finish
 cudaError_t launch_ldlt_state(const Dims& D, const DevPtrs& P, cudaStream_t st);
 cudaError_t launch_record(const Dims& D, const DevPtrs& P, const RecPtrs& R, cudaStream_t st);
 cudaError_t launch_bump(const DevPtrs& P, int bump_iter, int bump_rec, cudaStream_t st);

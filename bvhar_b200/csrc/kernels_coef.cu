@@ -1,0 +1,272 @@
+// kernels_coef.cu — stage 4 (updateCoef, triangular.h:281-316 + draw_coef draw.h:372-383 + draw_mn_savs
+// draw.h:417-430) split by data dependence into three kernels:
+//
+//   coef_pbuild   (SV)  P_j = sum_{i>=j} L_ij^2 S_i for all j of a unit in ONE pass over S (each S_i read once)
+//   coef_chol           chol(diag(prec_j) + P_j) for every (unit, equation): no dependence on this sweep's
+//                       draws, so all U*k factorisations run concurrently, one warp per matrix
+//   coef_seq            the part that IS sequential in j (equation j conditions on the draws of equations < j):
+//                       with g_i = S_i v_i, v_i = A L_i' kept up to date,
+//                          r_j     = prec_j o (mean_j - a_j) + sum_{i>=j} L_ij (C_i - g_i)
+//                          delta_j = P_j^-1 r_j + chol(P_j)^-T z,   a_j += delta_j,   g_i += L_ij S_i delta_j  (i > j)
+//                       which is the reference's draw (a_j = P_j^-1 b_j + chol^-T z with equation j zeroed,
+//                       tri.h:283) written as an increment, so no product with the old a_j is ever needed.
+//
+// Packed symmetric products S_i x are done by one warp straight from global/L2 memory, row by row with
+// coalesced loads: lanes own columns (private accumulators for the upper part) and one warp reduction
+// per row gives the lower part.  LDLT models have S_i = X'X / d_i: one product per equation.
+#include "engine.cuh"
+#include "kernels.h"
+#include "rng.cuh"
+#include "warp_linalg.cuh"
+
+namespace bvhar {
+
+namespace {
+
+// ---- A1: P_j = sum_{i>=j} L_ij^2 S_i, all j, one pass over the unit's S ----------------------
+template <int KMAX>
+__global__ void __launch_bounds__(256) coef_pbuild_kernel(const Dims D, const DevPtrs P, double* __restrict__ Pfac) {
+  extern __shared__ __align__(16) double sm[];
+  const int u = blockIdx.x, k = D.k;
+  double* Lsq = sm;  // [i][j], i >= j
+  for (int e = threadIdx.x; e < k * k; e += blockDim.x) {
+    const double l = P.L[(size_t)u * k * k + e];
+    Lsq[e] = l * l;
+  }
+  __syncthreads();
+  const double* Su = P.S + (size_t)u * k * D.ldS;
+  double* Pu = Pfac + (size_t)u * k * D.ldS;
+  for (int p = threadIdx.x; p < D.Pp; p += blockDim.x) {
+    double acc[KMAX];
+#pragma unroll
+    for (int j = 0; j < KMAX; ++j) acc[j] = 0.0;
+    for (int i = 0; i < k; ++i) {
+      const double s = Su[(size_t)i * D.ldS + p];
+      const double* lr = Lsq + i * k;
+#pragma unroll
+      for (int j = 0; j < KMAX; ++j)
+        if (j <= i) acc[j] = fma(lr[j], s, acc[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < KMAX; ++j)
+      if (j < k) Pu[(size_t)j * D.ldS + p] = acc[j];
+  }
+}
+// generic fallback for k > 64: one thread per (j, p), streaming i
+__global__ void __launch_bounds__(256) coef_pbuild_generic_kernel(const Dims D, const DevPtrs P, double* __restrict__ Pfac) {
+  const int u = blockIdx.x, k = D.k;
+  const double* Su = P.S + (size_t)u * k * D.ldS;
+  const double* Lu = P.L + (size_t)u * k * k;
+  double* Pu = Pfac + (size_t)u * k * D.ldS;
+  for (int j = 0; j < k; ++j)
+    for (int p = threadIdx.x; p < D.Pp; p += blockDim.x) {
+      double acc = 0.0;
+      for (int i = j; i < k; ++i) {
+        const double l = Lu[i * k + j];
+        acc = fma(l * l, Su[(size_t)i * D.ldS + p], acc);
+      }
+      Pu[(size_t)j * D.ldS + p] = acc;
+    }
+}
+
+// ---- A2: chol(diag(prec_j) + P_j), one warp per (unit, equation) ------------------------------
+template <bool SV, int NC>
+__global__ void __launch_bounds__(128) coef_chol_kernel(const Dims D, const DevPtrs P, double* __restrict__ Pfac) {
+  extern __shared__ __align__(16) double sm[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const long long job = (long long)blockIdx.x * nw + warp;
+  if (job >= (long long)D.U * D.k) return;
+  const int u = (int)(job / D.k), j = (int)(job % D.k), w = u / D.C;
+  const int k = D.k, d = D.d, Pp = D.Pp;
+  double* Pk = sm + (size_t)warp * ((Pp + 1) & ~1);
+  double* Pg = Pfac + ((size_t)u * k + j) * D.ldS;
+  __shared__ int bad[8];
+  if (lane == 0) bad[warp] = 0;
+  if (SV) {
+    for (int p = lane; p < Pp; p += 32) Pk[p] = Pg[p];
+  } else {  // P_j = (sum_{i>=j} L_ij^2 / d_i) X'X
+    double ws = 0.0;
+    for (int i = j; i < k; ++i) {
+      const double l = P.L[((size_t)u * k + i) * k + j];
+      ws += l * l / P.diag[(size_t)u * k + i];
+    }
+    const double* X2 = P.XtX + (size_t)w * D.ldS;
+    for (int p = lane; p < Pp; p += 32) Pk[p] = ws * X2[p];
+  }
+  __syncwarp();
+  const double* pr = P.prec + (size_t)u * k * d + (size_t)j * d;
+  for (int a = lane; a < d; a += 32) Pk[a * (a + 1) / 2 + a] += pr[a];
+  __syncwarp();
+  chol_blocked_warp<NC>(Pk, d, &bad[warp]);
+  for (int p = lane; p < Pp; p += 32) Pg[p] = Pk[p];
+  __syncwarp();
+  if (lane == 0 && bad[warp]) atomicOr(&P.flags[u], 1);
+}
+
+// ---- B: the sequential-in-j part, one CTA per unit ---------------------------------------------
+template <bool SV, int NC>
+__global__ void __launch_bounds__(256) coef_seq_kernel(const Dims D, const DevPtrs P, const double* __restrict__ Pfac) {
+  extern __shared__ __align__(16) double sm[];
+  const int u = blockIdx.x, w = u / D.C, c = u % D.C;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+  const int k = D.k, d = D.d, Pp = D.Pp, ldM = D.ldM;
+  double* Lc = sm;                          // factor of the current equation
+  double* g = Lc + ((Pp + 1) & ~1);         // [k][d]
+  double* Lsm = g + (size_t)k * d;          // [k][k]
+  double* rv = Lsm + k * k;                 // [d]
+  double* zv = rv + d;
+  double* dl = zv + d;                      // delta
+  double* tv = dl + d;                      // LDLT: X'X delta
+  double* wscr = tv + d;                    // [nw][d] per-warp vectors
+  const Philox rng(P.seeds[u], (uint32_t)u, *P.iter);
+  double* Ac = P.Acoef + (size_t)w * d * ldM + (size_t)c * k;
+  const double* prec_u = P.prec + (size_t)u * k * d;
+  const double* xn = P.xnorm + (size_t)w * d;
+  const double* X2 = SV ? nullptr : P.XtX + (size_t)w * D.ldS;
+
+  for (int e = tid; e < k * k; e += blockDim.x) Lsm[e] = P.L[(size_t)u * k * k + e];
+  __syncthreads();
+  // g_i = S_i v_i, v_i = A L_i'
+  for (int i = warp; i < k; i += nw) {
+    double* v = wscr + (size_t)warp * d;
+    for (int a = lane; a < d; a += 32) {
+      double s = 0.0;
+      for (int m = 0; m <= i; ++m) s = fma(Lsm[i * k + m], Ac[(size_t)a * ldM + m], s);
+      v[a] = s;
+    }
+    __syncwarp();
+    double out[NC];
+    symv_packed_warp<NC>(SV ? P.S + ((size_t)u * k + i) * D.ldS : X2, v, d, out);
+    const double sc = SV ? 1.0 : 1.0 / P.diag[(size_t)u * k + i];
+#pragma unroll
+    for (int s = 0; s < NC; ++s) {
+      const int b = lane + 32 * s;
+      if (b < d) g[(size_t)i * d + b] = out[s] * sc;
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+
+  for (int j = 0; j < k; ++j) {
+    const double* Lg = Pfac + ((size_t)u * k + j) * D.ldS;
+    for (int p = tid; p < Pp; p += blockDim.x) Lc[p] = Lg[p];
+    for (int a = tid; a < d; a += blockDim.x) {
+      const double aold = Ac[(size_t)a * ldM + j];
+      double acc = prec_u[j * d + a] * (P.prior_mean[j * d + a] - aold);
+      if (SV) {
+        for (int i = j; i < k; ++i) acc = fma(Lsm[i * k + j], P.Cm[((size_t)u * k + i) * D.ldX + a] - g[(size_t)i * d + a], acc);
+      } else {
+        const double* xty = P.XtY + ((size_t)w * d + a) * k;
+        for (int i = j; i < k; ++i) {
+          double s = 0.0;
+          for (int m = 0; m <= i; ++m) s = fma(xty[m], Lsm[i * k + m], s);
+          acc = fma(Lsm[i * k + j], s / P.diag[(size_t)u * k + i] - g[(size_t)i * d + a], acc);
+        }
+      }
+      rv[a] = acc;
+      zv[a] = rng.normal_elem(ST_COEF_Z, (uint32_t)(j * d + a));
+    }
+    __syncthreads();
+    if (warp == 0) precision_solve_lanes<NC>(Lc, d, rv, zv, dl);
+    __syncthreads();
+    for (int a = tid; a < d; a += blockDim.x) {
+      const double val = Ac[(size_t)a * ldM + j] + dl[a];
+      Ac[(size_t)a * ldM + j] = val;
+      double pen = 0.0;
+      if (a < D.nrow) {
+        P.alpha[(size_t)u * D.N + j * D.nrow + a] = val;
+        pen = P.own_flag[j * D.nrow + a] ? 0.0 : 1.0;
+      } else {
+        P.cvec[(size_t)u * k + j] = val;
+      }
+      const double fit = fabs(val) * xn[a];  // draw_mn_savs, draw.h:417-430
+      P.sparse_coef[(size_t)u * d * k + j * d + a] = val * fmax(fit - pen / (val * val), 0.0) / fit;
+    }
+    if (j + 1 < k) {
+      if (SV) {
+        for (int i = j + 1 + warp; i < k; i += nw) {
+          double out[NC];
+          symv_packed_warp<NC>(P.S + ((size_t)u * k + i) * D.ldS, dl, d, out);
+          const double lij = Lsm[i * k + j];
+#pragma unroll
+          for (int s = 0; s < NC; ++s) {
+            const int b = lane + 32 * s;
+            if (b < d) g[(size_t)i * d + b] = fma(lij, out[s], g[(size_t)i * d + b]);
+          }
+        }
+      } else {
+        if (warp == 0) {
+          double out[NC];
+          symv_packed_warp<NC>(X2, dl, d, out);
+#pragma unroll
+          for (int s = 0; s < NC; ++s) {
+            const int b = lane + 32 * s;
+            if (b < d) tv[b] = out[s];
+          }
+        }
+        __syncthreads();
+        for (int e = tid; e < (k - j - 1) * d; e += blockDim.x) {
+          const int i = j + 1 + e / d, a = e % d;
+          g[(size_t)i * d + a] = fma(Lsm[i * k + j] / P.diag[(size_t)u * k + i], tv[a], g[(size_t)i * d + a]);
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+template <bool SV, int NC>
+cudaError_t launch_part(int part, const Dims& D, const DevPtrs& P, double* Pfac, size_t smem_limit, cudaStream_t st) {
+  const int k = D.k, d = D.d;
+  const size_t ppad = (D.Pp + 1) & ~1;
+  if (part == 0) {
+    if (!SV) return cudaSuccess;
+    const size_t sm1 = (size_t)k * k * sizeof(double);
+    if (k <= 32) {
+      cudaFuncSetAttribute(coef_pbuild_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1);
+      coef_pbuild_kernel<32><<<D.U, 256, sm1, st>>>(D, P, Pfac);
+    } else if (k <= 64) {
+      cudaFuncSetAttribute(coef_pbuild_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1);
+      coef_pbuild_kernel<64><<<D.U, 256, sm1, st>>>(D, P, Pfac);
+    } else {
+      coef_pbuild_generic_kernel<<<D.U, 256, 0, st>>>(D, P, Pfac);
+    }
+  } else if (part == 1) {
+    int nw = 4;
+    while (nw > 1 && nw * ppad * sizeof(double) > 96 * 1024) nw >>= 1;
+    const size_t sm2 = nw * ppad * sizeof(double);
+    if (sm2 > smem_limit) return cudaErrorInvalidConfiguration;
+    const long long jobs = (long long)D.U * k;
+    cudaFuncSetAttribute(coef_chol_kernel<SV, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2);
+    coef_chol_kernel<SV, NC><<<(unsigned)((jobs + nw - 1) / nw), nw * 32, sm2, st>>>(D, P, Pfac);
+  } else {
+    const size_t sm3 = (ppad + (size_t)k * d + (size_t)k * k + 12 * (size_t)d) * sizeof(double);
+    if (sm3 > smem_limit) return cudaErrorInvalidConfiguration;
+    cudaFuncSetAttribute(coef_seq_kernel<SV, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm3);
+    coef_seq_kernel<SV, NC><<<D.U, 256, sm3, st>>>(D, P, Pfac);
+  }
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+bool coef_v2_fits(const Dims& D, size_t smem_limit) {
+  if (D.d > 256) return false;
+  const size_t ppad = (D.Pp + 1) & ~1;
+  const size_t sm3 = (ppad + (size_t)D.k * D.d + (size_t)D.k * D.k + 12 * (size_t)D.d) * sizeof(double);
+  return sm3 <= smem_limit && ppad * sizeof(double) <= smem_limit;
+}
+
+// part 0: P build (SV only), 1: batched Cholesky, 2: sequential draws
+cudaError_t launch_coef_v2(int part, const Dims& D, const DevPtrs& P, double* Pfac, size_t smem_limit, cudaStream_t st) {
+  const int nc = (D.d + 31) / 32;
+#define BV_DISPATCH(NCV)                                                                                  \
+  return D.sv ? launch_part<true, NCV>(part, D, P, Pfac, smem_limit, st) : launch_part<false, NCV>(part, D, P, Pfac, smem_limit, st)
+  if (nc <= 1) BV_DISPATCH(1);
+  if (nc <= 2) BV_DISPATCH(2);
+  if (nc <= 4) BV_DISPATCH(4);
+  BV_DISPATCH(8);
+#undef BV_DISPATCH
+}
+
+}  // namespace bvhar

@@ -41,21 +41,38 @@ __device__ double block_sum(double v, double* scratch) {
 
 // ------------------------------------------------------------------ stage 3: updateSv (SV)
 // Dinv = exp(-h) = 1 / sqrt_sv^2 and YLD = (Y L')_{t,i} * Dinv, both in [t][m] contraction layout.
+// One thread per series m keeps its row of L in registers and walks a chunk of time points; the
+// response rows of the chunk are staged in shared memory.
+constexpr int SVP_TT = 16;  // time points per block
+template <int KMAX>
 __global__ void __launch_bounds__(256) sv_prep_kernel(const Dims D, const DevPtrs P) {
-  const int w = blockIdx.y;
+  extern __shared__ __align__(16) double sm[];
+  const int w = blockIdx.z;
   const int n = P.win_n[w], row0 = P.win_row0[w];
-  const long long off = P.win_off[w];
-  const long long total = (long long)n * D.M;
-  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
-    const int t = (int)(e / D.M), m = (int)(e % D.M);
-    const int c = m / D.k, i = m % D.k;
-    const int u = w * D.C + c;
-    const long long at = off + (long long)t * D.ldM + m;
+  const int t0 = blockIdx.y * SVP_TT;
+  if (t0 >= n) return;
+  const int k = D.k;
+  const int tn = min(SVP_TT, n - t0);
+  for (int e = threadIdx.x; e < tn * k; e += blockDim.x) sm[e] = P.Y[(size_t)(row0 + t0) * k + e];
+  __syncthreads();
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= D.M) return;
+  const int c = m / k, i = m - c * k;
+  const int u = w * D.C + c;
+  double lr[KMAX];
+  const double* Lr = P.L + ((size_t)u * k + i) * k;
+#pragma unroll
+  for (int m2 = 0; m2 < KMAX; ++m2) lr[m2] = (m2 <= i) ? Lr[m2] : 0.0;
+  const long long base = P.win_off[w] + (long long)t0 * D.ldM + m;
+#pragma unroll 4
+  for (int tt = 0; tt < tn; ++tt) {
+    const long long at = base + (long long)tt * D.ldM;
     const double dinv = exp(-P.H[at]);
-    const double* Lr = P.L + ((size_t)u * D.k + i) * D.k;
-    const double* y = P.Y + (size_t)(row0 + t) * D.k;
+    const double* y = sm + tt * k;
     double yl = 0.0;
-    for (int m2 = 0; m2 <= i; ++m2) yl += Lr[m2] * y[m2];
+#pragma unroll
+    for (int m2 = 0; m2 < KMAX; ++m2)
+      if (m2 < k) yl = fma(lr[m2], y[m2], yl);
     P.Dinv[at] = dinv;
     P.YLD[at] = yl * dinv;
   }
@@ -442,56 +459,92 @@ __constant__ double c_ksc_m[7] = {-10.12999, -3.97281, -8.56686, 2.77786, 0.6194
 __constant__ double c_ksc_v[7] = {5.79596, 2.61369, 5.17950, 0.16735, 0.64009, 0.34023, 1.26261};      // draw.h:450
 
 // Mixture indicators (draw.h:458-468) for every (t, series): y* = log((Z L')^2 + 1e-4) (tri.h:401-402),
-// s_t by inverse CDF on the normalised 7-component weights; leaves the tridiagonal system's
-// diagonal term 1/v_s in Dinv and right-hand-side term (y* - m_s)/v_s in YLD.
+// s_t by inverse CDF on the 7-component weights p_c N(y* - h; m_c - 1.2704, v_c); leaves the tridiagonal
+// system's diagonal term 1/v_s in Dinv and right-hand-side term (y* - m_s)/v_s in YLD.
+// Same thread mapping as sv_prep (row of L in registers); the unit's residual rows are staged in smem.
+__constant__ double c_ksc_mm[7] = {-10.12999 - 1.2704, -3.97281 - 1.2704, -8.56686 - 1.2704, 2.77786 - 1.2704,
+                                   0.61942 - 1.2704, 1.79518 - 1.2704, -1.08819 - 1.2704};
+template <int KMAX>
 __global__ void __launch_bounds__(256) sv_mix_kernel(const Dims D, const DevPtrs P) {
-  const int w = blockIdx.y;
+  extern __shared__ __align__(16) double sm[];  // [SVP_TT][blockDim.x span of Z columns]
+  __shared__ double s_h2v[7], s_lw[7], s_iv[7];
+  const int w = blockIdx.z;
   const int n = P.win_n[w];
-  const long long off = P.win_off[w];
-  const long long total = (long long)n * D.M;
-  const uint32_t it = *P.iter;
+  const int t0 = blockIdx.y * SVP_TT;
+  if (t0 >= n) return;
+  const int k = D.k;
+  if (threadIdx.x < 7) {
+    const double v = c_ksc_v[threadIdx.x];
+    s_h2v[threadIdx.x] = 0.5 / v;
+    s_iv[threadIdx.x] = 1.0 / v;
+    s_lw[threadIdx.x] = c_ksc_p[threadIdx.x] / (sqrt(v) * sqrt(2 * 3.14159265358979323846));
+  }
+  const int tn = min(SVP_TT, n - t0);
+  const int mbase = blockIdx.x * blockDim.x;
+  const int c0 = mbase / k;                                  // first unit touched by this block
+  const int zlo = c0 * k;                                    // first Z column staged
+  const int mhi = min(D.M, mbase + (int)blockDim.x);
+  const int zhi = min(D.M, ((mhi - 1) / k + 1) * k);         // one past the last Z column staged
+  const int zw = zhi - zlo;
+  const long long wbase = P.win_off[w] + (long long)t0 * D.ldM;
+  for (int e = threadIdx.x; e < tn * zw; e += blockDim.x) {
+    const int tt = e / zw, col = e - tt * zw;
+    sm[e] = P.Z[wbase + (long long)tt * D.ldM + zlo + col];
+  }
+  __syncthreads();
+  const int m = mbase + threadIdx.x;
+  if (m >= D.M) return;
+  const int c = m / k, i = m - c * k;
+  const int u = w * D.C + c;
+  double lr[KMAX];
+  const double* Lr = P.L + ((size_t)u * k + i) * k;
+#pragma unroll
+  for (int m2 = 0; m2 < KMAX; ++m2) lr[m2] = (m2 <= i) ? Lr[m2] : 0.0;
+  const Philox rng(P.seeds[u], (uint32_t)u, *P.iter);
   const uint32_t nh = (uint32_t)((n + 1) / 2);
-  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
-    const int t = (int)(e / D.M), m = (int)(e % D.M);
-    const int c = m / D.k, i = m % D.k;
-    const int u = w * D.C + c;
-    const long long rowat = off + (long long)t * D.ldM;
-    const double* Lr = P.L + ((size_t)u * D.k + i) * D.k;
-    const double* z = P.Z + rowat + (long long)c * D.k;
+  const int zoff = c * k - zlo;
+  double ua = 0.0, ub = 0.0;
+  for (int tt = 0; tt < tn; ++tt) {
+    const int t = t0 + tt;
+    const long long at = wbase + (long long)tt * D.ldM + m;
+    const double* z = sm + tt * zw + zoff;
     double uu = 0.0;
-    for (int m2 = 0; m2 <= i; ++m2) uu += Lr[m2] * z[m2];
+#pragma unroll
+    for (int m2 = 0; m2 < KMAX; ++m2)
+      if (m2 < k) uu = fma(lr[m2], z[m2], uu);
     const double ystar = log(uu * uu + .0001);
-    const double h = P.H[rowat + m];
-    const Philox rng(P.seeds[u], (uint32_t)u, it);
-    double ua, ub;
-    rng.uniform_pair(ST_SV_MIX_U, (uint32_t)i * nh + ((uint32_t)t >> 1), 0, ua, ub);
+    const double h = P.H[at];
+    if (!(t & 1) || tt == 0) rng.uniform_pair(ST_SV_MIX_U, (uint32_t)i * nh + ((uint32_t)t >> 1), 0, ua, ub);
     const double uni = (t & 1) ? ub : ua;
+    const double r = ystar - h;
     double pdf[7], tot = 0.0;
 #pragma unroll
     for (int cc = 0; cc < 7; ++cc) {
-      const double mm = c_ksc_m[cc] - 1.2704, sd = sqrt(c_ksc_v[cc]);
-      const double ee = (ystar - h - mm) / sd;
-      pdf[cc] = exp(-ee * ee / 2) * c_ksc_p[cc] / (sd * sqrt(2 * 3.14159265358979323846));
+      const double e = r - c_ksc_mm[cc];
+      pdf[cc] = s_lw[cc] * exp(-e * e * s_h2v[cc]);
       tot += pdf[cc];
     }
+    const double target = uni * tot;  // u < cum / tot  <=>  u * tot < cum
     double cum = 0.0;
     int cnt = 0;
 #pragma unroll
     for (int cc = 0; cc < 7; ++cc) {
-      cum += pdf[cc] / tot;
-      if (uni < cum) ++cnt;
+      cum += pdf[cc];
+      if (target < cum) ++cnt;
     }
-    int s = 7 - cnt;
+    int s = 7 - cnt;  // draw.h:468
     if (s > 6) s = 6;
-    const double iv = 1.0 / c_ksc_v[s];
-    P.Dinv[rowat + m] = iv;
-    P.YLD[rowat + m] = (ystar - (c_ksc_m[s] - 1.2704)) * iv;
+    const double iv = s_iv[s];
+    P.Dinv[at] = iv;
+    P.YLD[at] = (ystar - c_ksc_mm[s]) * iv;
   }
 }
 
 // h_i ~ N(K^-1 b, K^-1) with the tridiagonal K = H'H / sig + diag(1/v_s) (draw.h:469-487): one thread
-// per series runs the bidiagonal Cholesky forward, then the combined mean + noise back substitution.
-// All accesses are [t][m]: coalesced across the series of a window.
+// per series runs the bidiagonal Cholesky forward (storing 1 / l_t), then the combined mean + noise
+// back substitution.  Loads are issued SVS_B time points ahead of the dependent chain (they would
+// otherwise serialise behind the stores to the same arrays); accesses are [t][m], coalesced.
+constexpr int SVS_B = 8;
 __global__ void __launch_bounds__(128) sv_solve_kernel(const Dims D, const DevPtrs P) {
   const int w = blockIdx.y;
   const int m = blockIdx.x * blockDim.x + threadIdx.x;
@@ -504,42 +557,59 @@ __global__ void __launch_bounds__(128) sv_solve_kernel(const Dims D, const DevPt
   const double h0 = P.lvol_init[(size_t)u * D.k + i];
   const Philox rng(P.seeds[u], (uint32_t)u, *P.iter);
   const uint32_t nh = (uint32_t)((n + 1) / 2);
-  double lprev = 1.0, yprev = 0.0;
-  for (int t = 0; t < n; ++t) {
-    const long long at = off + (long long)t * D.ldM;
-    const double dg = (t < n - 1 ? 2.0 : 1.0) * isig + P.Dinv[at];
-    const double b = (t == 0 ? h0 * isig : 0.0) + P.YLD[at];
-    double l, y;
-    if (t == 0) {
-      l = sqrt(dg);
-      y = b / l;
-    } else {
-      const double e = -isig / lprev;
-      l = sqrt(dg - e * e);
-      y = (b - e * yprev) / l;
+  double wprev = 0.0, yprev = 0.0;  // w = 1 / l
+  for (int t0 = 0; t0 < n; t0 += SVS_B) {
+    double dg[SVS_B], bb[SVS_B];
+#pragma unroll
+    for (int r = 0; r < SVS_B; ++r) {
+      const int t = t0 + r;
+      const long long at = off + (long long)t * D.ldM;
+      dg[r] = t < n ? P.Dinv[at] : 1.0;
+      bb[r] = t < n ? P.YLD[at] : 0.0;
     }
-    P.Dinv[at] = l;
-    P.YLD[at] = y;
-    lprev = l;
-    yprev = y;
+#pragma unroll
+    for (int r = 0; r < SVS_B; ++r) {
+      const int t = t0 + r;
+      if (t < n) {
+        const double e = -isig * wprev;  // e_t = -isig / l_{t-1}; wprev = 0 at t = 0
+        const double q = fma(-e, e, (t < n - 1 ? 2.0 : 1.0) * isig + dg[r]);
+        const double wv = 1.0 / sqrt(q);
+        const double b = (t == 0 ? h0 * isig : 0.0) + bb[r];
+        const double y = (b - e * yprev) * wv;
+        const long long at = off + (long long)t * D.ldM;
+        P.Dinv[at] = wv;
+        P.YLD[at] = y;
+        wprev = wv;
+        yprev = y;
+      }
+    }
   }
-  double next = 0.0, zkeep = 0.0;
-  for (int t = n - 1; t >= 0; --t) {
-    const long long at = off + (long long)t * D.ldM;
-    const double l = P.Dinv[at];
-    double z;
-    if ((t & 1) || t == n - 1) {  // pair (t even, t odd): fetch both lanes once
-      double z0, z1;
-      rng.normal_pair(ST_SV_H_Z, (uint32_t)i * nh + ((uint32_t)t >> 1), 0, z0, z1);
-      z = (t & 1) ? z1 : z0;
-      zkeep = z0;
-    } else {
-      z = zkeep;
+  double next = 0.0;
+  const int nb = (n + SVS_B - 1) / SVS_B;
+  for (int blk = nb - 1; blk >= 0; --blk) {
+    const int t0 = blk * SVS_B;  // SVS_B is even, so Philox pairs (t even, t odd) never straddle blocks
+    double wv[SVS_B], yv[SVS_B], zv[SVS_B];
+#pragma unroll
+    for (int r = 0; r < SVS_B; ++r) {
+      const int t = t0 + r;
+      const long long at = off + (long long)t * D.ldM;
+      wv[r] = t < n ? P.Dinv[at] : 0.0;
+      yv[r] = t < n ? P.YLD[at] : 0.0;
     }
-    double v = P.YLD[at] + z;
-    if (t < n - 1) v -= (-isig / l) * next;  // e_{t+1} = -isig / l_t
-    next = v / l;
-    P.H[at] = next;
+#pragma unroll
+    for (int r = 0; r < SVS_B; r += 2) {
+      if (t0 + r < n) rng.normal_pair(ST_SV_H_Z, (uint32_t)i * nh + ((uint32_t)(t0 + r) >> 1), 0, zv[r], zv[r + 1]);
+    }
+#pragma unroll
+    for (int r = SVS_B - 1; r >= 0; --r) {
+      const int t = t0 + r;
+      if (t < n) {
+        double v = yv[r] + zv[r];
+        if (t < n - 1) v = fma(isig * wv[r], next, v);  // - e_{t+1} next, e_{t+1} = -isig / l_t
+        next = v * wv[r];
+        P.H[off + (long long)t * D.ldM] = next;
+      }
+    }
   }
 }
 
@@ -716,21 +786,30 @@ cudaError_t launch_impact(const Dims& D, const DevPtrs& P, double* gscratch, cud
   return cudaGetLastError();
 }
 cudaError_t launch_sv_prep(const Dims& D, const DevPtrs& P, cudaStream_t st) {
-  const long long total = (long long)D.nmax * D.M;
-  int bx = (int)((total + 255) / 256);
-  if (bx > 148 * 16) bx = 148 * 16;
-  sv_prep_kernel<<<dim3(bx, D.W), 256, 0, st>>>(D, P);
+  const dim3 grid((D.M + 255) / 256, (D.nmax + SVP_TT - 1) / SVP_TT, D.W);
+  const size_t smem = (size_t)SVP_TT * D.k * sizeof(double);
+  if (D.k <= 32) sv_prep_kernel<32><<<grid, 256, smem, st>>>(D, P);
+  else if (D.k <= 64) sv_prep_kernel<64><<<grid, 256, smem, st>>>(D, P);
+  else sv_prep_kernel<128><<<grid, 256, smem, st>>>(D, P);
   return cudaGetLastError();
 }
-cudaError_t launch_sv_state(const Dims& D, const DevPtrs& P, cudaStream_t st) {
-  const long long total = (long long)D.nmax * D.M;
-  int bx = (int)((total + 255) / 256);
-  if (bx > 148 * 16) bx = 148 * 16;
-  sv_mix_kernel<<<dim3(bx, D.W), 256, 0, st>>>(D, P);
-  sv_solve_kernel<<<dim3((D.M + 127) / 128, D.W), 128, 0, st>>>(D, P);
-  const size_t smem = ((size_t)D.k * (D.k + 1) / 2 + 4 * D.k) * sizeof(double);
-  cudaFuncSetAttribute(sv_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  sv_finish_kernel<<<D.U, 128, smem, st>>>(D, P);
+cudaError_t launch_sv_state(int part, const Dims& D, const DevPtrs& P, cudaStream_t st) {
+  if (part == 0) {
+    const dim3 grid((D.M + 255) / 256, (D.nmax + SVP_TT - 1) / SVP_TT, D.W);
+    const size_t smem = (size_t)SVP_TT * (256 + 2 * D.k) * sizeof(double);
+    if (D.k <= 32) sv_mix_kernel<32><<<grid, 256, smem, st>>>(D, P);
+    else if (D.k <= 64) sv_mix_kernel<64><<<grid, 256, smem, st>>>(D, P);
+    else {
+      cudaFuncSetAttribute(sv_mix_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      sv_mix_kernel<128><<<grid, 256, smem, st>>>(D, P);
+    }
+  } else if (part == 1) {
+    sv_solve_kernel<<<dim3((D.M + 127) / 128, D.W), 128, 0, st>>>(D, P);
+  } else {
+    const size_t smem = ((size_t)D.k * (D.k + 1) / 2 + 4 * D.k) * sizeof(double);
+    cudaFuncSetAttribute(sv_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    sv_finish_kernel<<<D.U, 128, smem, st>>>(D, P);
+  }
   return cudaGetLastError();
 }
 cudaError_t launch_ldlt_state(const Dims& D, const DevPtrs& P, cudaStream_t st) {
