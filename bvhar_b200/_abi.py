@@ -70,7 +70,7 @@ class FitDesc(C.Structure):
         ("dim", C.c_int32), ("dim_design", C.c_int32), ("include_mean", C.c_int32),
         ("cov_type", C.c_int32), ("prior_type", C.c_int32), ("is_group", C.c_int32),
         ("num_iter", C.c_int32), ("num_burn", C.c_int32), ("thin", C.c_int32),
-        ("record_mask", C.c_uint32), ("lvol_from_init", C.c_int32), ("reserved0", C.c_int32),
+        ("record_mask", C.c_uint32), ("lvol_from_init", C.c_int32), ("unit_id_base", C.c_int32),
         ("n_rows_total", C.c_int64),
         ("x", c_dp), ("y", c_dp), ("win_row0", c_ip), ("win_nrow", c_ip),
         ("grp_mat", c_ip), ("grp_id", c_ip), ("n_grp", C.c_int32), ("n_own", C.c_int32),
@@ -129,7 +129,7 @@ class PackedFit:
         param_cov: Dict[str, Any], param_prior: Dict[str, Any], param_intercept: Dict[str, Any],
         param_init: Sequence[Dict[str, Any]], prior_type: int, grp_id, own_id, cross_id, grp_mat,
         include_mean: bool, seed_chain, is_group: bool = True, win_row0=None, win_nrow=None,
-        record_mask: int = REC_ALL, device: int = 0, lvol_from_init: bool = False,
+        record_mask: int = REC_ALL, device: int = 0, lvol_from_init: bool = False, unit_id_base: int = 0,
     ):
         self._keep: List[Any] = []
         k = self._keep.append
@@ -165,7 +165,7 @@ class PackedFit:
         D.include_mean = int(bool(include_mean)); D.cov_type = COV_SV if sv else COV_LDLT
         D.prior_type = int(prior_type); D.is_group = int(bool(is_group))
         D.num_iter = int(num_iter); D.num_burn = int(num_burn); D.thin = int(thin)
-        D.record_mask = int(record_mask); D.lvol_from_init = int(bool(lvol_from_init))
+        D.record_mask = int(record_mask); D.lvol_from_init = int(bool(lvol_from_init)); D.unit_id_base = int(unit_id_base)
         D.n_rows_total = n_tot
         D.x = _dp(X); D.y = _dp(Y); D.win_row0 = _ip(w0); D.win_nrow = _ip(wn)
         D.grp_mat = _ip(gm); D.grp_id = _ip(gid); D.n_grp = len(gid)

@@ -112,3 +112,40 @@ def minnesota_moments(priors: dict, dim: int, nrow: int, hierarchical: bool = Fa
     mean = np.linalg.solve(chol.T, np.linalg.solve(chol, rhs))
     alpha_prec = np.kron(1.0 / sigma, np.diag(prec))  # diag(kron(diag(1/sigma), prec)), triangular.h:439
     return np.asfortranarray(mean), alpha_prec
+
+
+def build_dummies(p: int, sigma, lam: float, daily, weekly, monthly, eps: float, include_mean: bool = True):
+    """``build_ydummy`` / ``build_xdummy`` (design.h:60-98) including the constant-term row / column."""
+    sigma = np.asarray(sigma, dtype=np.float64).reshape(-1)
+    dim = sigma.size
+    yd = np.zeros((dim * p + dim + 1, dim))
+    yd[:dim * p + dim] = _build_ydummy(p, sigma, lam, np.asarray(daily, dtype=np.float64), np.asarray(weekly, dtype=np.float64),
+                                      np.asarray(monthly, dtype=np.float64))
+    xd = np.zeros((dim * p + dim + 1, dim * p + 1))
+    xd[:dim * p + dim, :dim * p] = _build_xdummy(np.arange(1, p + 1, dtype=np.float64), lam, sigma, eps)
+    xd[dim * p + dim, dim * p] = eps
+    if include_mean:
+        return xd, yd
+    return xd[:dim * p + dim, :dim * p], yd[:dim * p + dim]
+
+
+def mniw_posterior(x, y, p: int, sigma, lam: float, delta, eps: float = 1e-4, weekly=None, monthly=None,
+                   include_mean: bool = True):
+    """Closed-form Minnesota (matrix-normal inverse-Wishart) posterior on dummy-augmented data:
+    ``Minnesota::estimateCoef`` / ``estimateCov`` (bayes/mniw/minnesota.h:153-186).
+
+    prec = X*'X*, coef = prec^-1 X*'Y*, IW scale = (Y* - X* coef)'(Y* - X* coef),
+    IW shape = n_dummy - dim_design + 2 + n, with X* = [X; Xd], Y* = [Y; Yd].
+    Host-side and one-off: a deterministic parity target, not a kernel."""
+    x = np.asarray(x, dtype=np.float64); y = np.asarray(y, dtype=np.float64)
+    dim = y.shape[1]
+    zeros = np.zeros(dim)
+    xd, yd = build_dummies(p, sigma, lam, delta, zeros if weekly is None else weekly, zeros if monthly is None else monthly,
+                           eps, include_mean)
+    xs = np.vstack([x, xd]); ys = np.vstack([y, yd])
+    prec = xs.T @ xs
+    chol = np.linalg.cholesky(prec)
+    coef = np.linalg.solve(chol.T, np.linalg.solve(chol, xs.T @ ys))
+    res = ys - xs @ coef
+    return {"coef": coef, "prec": prec, "scale": res.T @ res, "shape": xd.shape[0] - x.shape[1] + 2 + x.shape[0],
+            "x_dummy": xd, "y_dummy": yd}

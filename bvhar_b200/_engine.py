@@ -191,13 +191,13 @@ def _stable_rows(coef: np.ndarray, dim: int, nrow: int, har: Optional[np.ndarray
     return keep
 
 
-def forecast_density(units: Sequence[Dict[str, np.ndarray]], last_obs: Sequence[np.ndarray], step: int, var_lag: int,
-                     include_mean: bool, sv_model: bool, seeds, har_trans: Optional[np.ndarray] = None, sv: bool = True,
-                     valid_vec: Optional[np.ndarray] = None, stable: bool = False, sparse: bool = False,
-                     coef_name: str = "alpha", device: int = 0):
-    """Density forecasts of independent units on the GPU (``McmcForecaster::forecastDensity``,
-    forecaster.h:55-85).  Returns (list of step x (S*k) matrices, step-wise ALPL per unit or None)."""
-    L = load_library()
+def pack_forecast(units: Sequence[Dict[str, np.ndarray]], last_obs: Sequence[np.ndarray], step: int, var_lag: int,
+                  include_mean: bool, sv_model: bool, seeds, har_trans: Optional[np.ndarray] = None, sv: bool = True,
+                  valid_vec: Optional[np.ndarray] = None, stable: bool = False, sparse: bool = False,
+                  coef_name: str = "alpha", device: int = 0):
+    """Build the ``bvhar_forecast_desc`` of a batch of forecasters from their record dicts
+    (``initialize_record`` config.h:1316-1363 + the forecaster ctors forecaster.h:27-52, 229-240).
+    Returns (descriptor, keep-alive list)."""
     dim = last_obs[0].shape[1]
     sfx = "_sparse_record" if sparse else "_record"
     coefs, contems, diags, sighs = [], [], [], []
@@ -242,6 +242,19 @@ def forecast_density(units: Sequence[Dict[str, np.ndarray]], last_obs: Sequence[
         vv = np.ascontiguousarray(valid_vec, dtype=np.float64); keep.append(vv); D.valid_vec = vv.ctypes.data_as(c_dp)
     sd = np.ascontiguousarray(np.asarray(seeds, dtype=np.int64) & 0xFFFFFFFF, dtype=np.uint32); keep.append(sd)
     D.seed = sd.ctypes.data_as(c_up)
+    return D, keep
+
+
+def forecast_density(units: Sequence[Dict[str, np.ndarray]], last_obs: Sequence[np.ndarray], step: int, var_lag: int,
+                     include_mean: bool, sv_model: bool, seeds, har_trans: Optional[np.ndarray] = None, sv: bool = True,
+                     valid_vec: Optional[np.ndarray] = None, stable: bool = False, sparse: bool = False,
+                     coef_name: str = "alpha", device: int = 0):
+    """Density forecasts of independent units on the GPU (``McmcForecaster::forecastDensity``,
+    forecaster.h:55-85).  Returns (list of step x (S*k) matrices, step-wise ALPL per unit or None)."""
+    L = load_library()
+    D, keep = pack_forecast(units, last_obs, step, var_lag, include_mean, sv_model, seeds, har_trans, sv, valid_vec, stable,
+                            sparse, coef_name, device)
+    U, S, dim = D.n_units, D.n_draws, D.dim
     out = np.empty(U * step * S * dim)
     lpl = np.zeros(U * step) if valid_vec is not None else None
     check(L.bvhar_cuda_forecast_density(C.byref(D), out.ctypes.data_as(c_dp), lpl.ctypes.data_as(c_dp) if lpl is not None else c_dp()))

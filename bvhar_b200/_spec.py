@@ -253,7 +253,7 @@ class GdpConfig(_BayesConfig):
 PRIOR_TYPE = {"Minnesota": 1, "SSVS": 2, "Horseshoe": 3, "HMN": 4, "NG": 5, "DL": 6, "GDP": 7}
 
 
-def make_inits(prior: str, sv: bool, dim: int, n_design: int, n_obs: int, n_grp: int, n_chain: int, rng):
+def make_inits(prior: str, sv: bool, dim: int, n_design: int, n_obs: int, n_grp: int, n_chain: int, rng, include_mean=None):
     """Random initial values per chain, drawn as the reference front ends draw them
     (python/src/bvhar/model/_bayes.py:58-170; R/var-bayes.R:164-172, 271-413, 440-463):
     U(-1,1) coefficients, exp(U(-1,0)) contemporaneous terms, exp(U(-1,1)) scales.
@@ -262,7 +262,7 @@ def make_inits(prior: str, sv: bool, dim: int, n_design: int, n_obs: int, n_grp:
     (constant included), ``n_obs`` = rows of the response.
     """
     n_eta = dim * (dim - 1) // 2
-    has_const = n_design % dim != 0
+    has_const = (n_design % dim != 0) if include_mean is None else bool(include_mean)
     n_alpha = dim * (n_design - (1 if has_const else 0))
     inits = []
     for _ in range(n_chain):

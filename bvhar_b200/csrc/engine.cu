@@ -265,6 +265,7 @@ int build(const bvhar_fit_desc* d, bvhar_fit** out) {
   D.N = D.k * D.d - (D.mean ? D.k : 0);
   D.nrow = D.N / D.k;
   D.G = d->n_grp;
+  D.ubase = d->unit_id_base;
   D.Pp = D.d * (D.d + 1) / 2;
   D.ldS = round_even(D.Pp);
   D.ldX = round_even(D.d);
@@ -535,7 +536,7 @@ int build(const bvhar_fit_desc* d, bvhar_fit** out) {
     return fail(BVHAR_ERR_UNSUPPORTED, "dim_design too large for the shared-memory Cholesky of this build (packed d(d+1)/2 doubles must fit 227 KB)");
   if (need_v) CU(F->vscratch.alloc((size_t)U * 2 * k * dd));
   CU(F->gscratch.alloc((size_t)U * impact_gsize(D)));
-  if ((size_t)(2 * 16 * k + 8 * (k * (k + 1) / 2 + 3 * k)) * sizeof(double) > F->smem_limit)
+  if (!impact_supported(D, F->smem_limit))
     return fail(BVHAR_ERR_UNSUPPORTED, "dim too large for the shared-memory contemporaneous draw of this build");
   if (D.sv) CU(launch_build_xx(D, P, F->XX.p, F->st));
   else {
@@ -706,6 +707,7 @@ int view_io(bvhar_fit* F, const View& v, int w, int c, double* host, int64_t len
   switch (v.kind) {
     case View::UNIT_VEC:
       if (len != v.len) return fail(BVHAR_ERR_BAD_ARG, "state length mismatch");
+      if (v.len == 0) return 0;
       if (to_host) CU(cudaMemcpy(host, v.base + (size_t)u * v.len, sizeof(double) * v.len, dir));
       else CU(cudaMemcpy(v.base + (size_t)u * v.len, host, sizeof(double) * v.len, dir));
       return 0;

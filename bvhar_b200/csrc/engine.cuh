@@ -24,6 +24,7 @@ struct Dims {
   int T;                // rows of the full design
   int mean, sv, ggl, prior;
   int nmax;             // largest window
+  int ubase;            // global index of unit 0 (Philox key word 1 = ubase + u)
 };
 
 struct PriorConst {  // scalars of bvhar_prior_params

@@ -69,40 +69,6 @@ __global__ void __launch_bounds__(256) coef_pbuild_generic_kernel(const Dims D, 
     }
 }
 
-// ---- A2: chol(diag(prec_j) + P_j), one warp per (unit, equation) ------------------------------
-template <bool SV, int NC>
-__global__ void __launch_bounds__(128) coef_chol_kernel(const Dims D, const DevPtrs P, double* __restrict__ Pfac) {
-  extern __shared__ __align__(16) double sm[];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  const long long job = (long long)blockIdx.x * nw + warp;
-  if (job >= (long long)D.U * D.k) return;
-  const int u = (int)(job / D.k), j = (int)(job % D.k), w = u / D.C;
-  const int k = D.k, d = D.d, Pp = D.Pp;
-  double* Pk = sm + (size_t)warp * ((Pp + 1) & ~1);
-  double* Pg = Pfac + ((size_t)u * k + j) * D.ldS;
-  __shared__ int bad[8];
-  if (lane == 0) bad[warp] = 0;
-  if (SV) {
-    for (int p = lane; p < Pp; p += 32) Pk[p] = Pg[p];
-  } else {  // P_j = (sum_{i>=j} L_ij^2 / d_i) X'X
-    double ws = 0.0;
-    for (int i = j; i < k; ++i) {
-      const double l = P.L[((size_t)u * k + i) * k + j];
-      ws += l * l / P.diag[(size_t)u * k + i];
-    }
-    const double* X2 = P.XtX + (size_t)w * D.ldS;
-    for (int p = lane; p < Pp; p += 32) Pk[p] = ws * X2[p];
-  }
-  __syncwarp();
-  const double* pr = P.prec + (size_t)u * k * d + (size_t)j * d;
-  for (int a = lane; a < d; a += 32) Pk[a * (a + 1) / 2 + a] += pr[a];
-  __syncwarp();
-  chol_blocked_warp<NC>(Pk, d, &bad[warp]);
-  for (int p = lane; p < Pp; p += 32) Pg[p] = Pk[p];
-  __syncwarp();
-  if (lane == 0 && bad[warp]) atomicOr(&P.flags[u], 1);
-}
-
 // ---- B: the sequential-in-j part, one CTA per unit ---------------------------------------------
 template <bool SV, int NC>
 __global__ void __launch_bounds__(256) coef_seq_kernel(const Dims D, const DevPtrs P, const double* __restrict__ Pfac) {
@@ -118,7 +84,7 @@ __global__ void __launch_bounds__(256) coef_seq_kernel(const Dims D, const DevPt
   double* dl = zv + d;                      // delta
   double* tv = dl + d;                      // LDLT: X'X delta
   double* wscr = tv + d;                    // [nw][d] per-warp vectors
-  const Philox rng(P.seeds[u], (uint32_t)u, *P.iter);
+  const Philox rng(P.seeds[u], (uint32_t)(D.ubase + u), *P.iter);
   double* Ac = P.Acoef + (size_t)w * d * ldM + (size_t)c * k;
   const double* prec_u = P.prec + (size_t)u * k * d;
   const double* xn = P.xnorm + (size_t)w * d;
@@ -232,13 +198,7 @@ cudaError_t launch_part(int part, const Dims& D, const DevPtrs& P, double* Pfac,
       coef_pbuild_generic_kernel<<<D.U, 256, 0, st>>>(D, P, Pfac);
     }
   } else if (part == 1) {
-    int nw = 4;
-    while (nw > 1 && nw * ppad * sizeof(double) > 96 * 1024) nw >>= 1;
-    const size_t sm2 = nw * ppad * sizeof(double);
-    if (sm2 > smem_limit) return cudaErrorInvalidConfiguration;
-    const long long jobs = (long long)D.U * k;
-    cudaFuncSetAttribute(coef_chol_kernel<SV, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2);
-    coef_chol_kernel<SV, NC><<<(unsigned)((jobs + nw - 1) / nw), nw * 32, sm2, st>>>(D, P, Pfac);
+    return launch_coef_chol(NC, D, P, Pfac, smem_limit, st);
   } else {
     const size_t sm3 = (ppad + (size_t)k * d + (size_t)k * k + 12 * (size_t)d) * sizeof(double);
     if (sm3 > smem_limit) return cudaErrorInvalidConfiguration;

@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(256) prior_kernel(const Dims D, const DevPtrs 
   __shared__ int pick;
   const int u = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
   const int N = D.N, q = D.q, G = D.G;
-  const Philox rng(P.seeds[u], (uint32_t)u, *P.iter);
+  const Philox rng(P.seeds[u], (uint32_t)(D.ubase + u), *P.iter);
   const Blk B{red, gridbuf, &pick};
   double* hs = P.hs + (size_t)u * HS_SLOTS;
   const uint32_t P0 = ST_PRIOR_COEF, P1 = ST_PRIOR_CONTEM;

@@ -15,29 +15,9 @@
 #include "engine.cuh"
 #include "kernels.h"
 #include "rng.cuh"
+#include "block_linalg.cuh"
 
 namespace bvhar {
-
-__device__ __forceinline__ double warp_sum(double v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
-// Sum over the block; every thread gets the result.  `scratch` holds >= 33 doubles.
-__device__ double block_sum(double v, double* scratch) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
-  v = warp_sum(v);
-  __syncthreads();
-  if (lane == 0) scratch[warp] = v;
-  __syncthreads();
-  if (warp == 0) {
-    double t = lane < nw ? scratch[lane] : 0.0;
-    t = warp_sum(t);
-    if (lane == 0) scratch[32] = t;
-  }
-  __syncthreads();
-  return scratch[32];
-}
 
 // ------------------------------------------------------------------ stage 3: updateSv (SV)
 // Dinv = exp(-h) = 1 / sqrt_sv^2 and YLD = (Y L')_{t,i} * Dinv, both in [t][m] contraction layout.
@@ -78,75 +58,6 @@ __global__ void __launch_bounds__(256) sv_prep_kernel(const Dims D, const DevPtr
   }
 }
 
-// ------------------------------------------------------------------ packed Cholesky / solves
-// Right-looking Cholesky of a packed-lower (row-major packed) matrix in shared memory, whole block.
-__device__ void chol_packed_block(double* Pk, int d, int* bad) {
-  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
-  for (int c = 0; c < d; ++c) {
-    const int cc = tri_idx(c, c);
-    __syncthreads();
-    const double p = Pk[cc];
-    __syncthreads();
-    const double piv = sqrt(p), inv = 1.0 / piv;
-    if (tid == 0) {
-      Pk[cc] = piv;
-      if (!(p > 0.0)) *bad = 1;
-    }
-    for (int a = c + 1 + tid; a < d; a += nt) Pk[tri_idx(a, c)] *= inv;
-    __syncthreads();
-    for (int a = c + 1 + warp; a < d; a += nw) {
-      const double lac = Pk[tri_idx(a, c)];
-      const int ra = a * (a + 1) / 2;
-      for (int b = c + 1 + lane; b <= a; b += 32) Pk[ra + b] -= lac * Pk[tri_idx(b, c)];
-    }
-  }
-  __syncthreads();
-}
-// Same for one warp (small matrices), packed-lower in shared or global memory.
-__device__ void chol_packed_warp(double* Pk, int d, int* bad) {
-  const int lane = threadIdx.x & 31;
-  for (int c = 0; c < d; ++c) {
-    const int cc = tri_idx(c, c);
-    __syncwarp();
-    const double p = Pk[cc];
-    __syncwarp();
-    const double piv = sqrt(p), inv = 1.0 / piv;
-    if (lane == 0) {
-      Pk[cc] = piv;
-      if (!(p > 0.0)) *bad = 1;
-    }
-    for (int a = c + 1 + lane; a < d; a += 32) Pk[tri_idx(a, c)] *= inv;
-    __syncwarp();
-    for (int a = c + 1; a < d; ++a) {
-      const double lac = Pk[tri_idx(a, c)];
-      const int ra = a * (a + 1) / 2;
-      for (int b = c + 1 + lane; b <= a; b += 32) Pk[ra + b] -= lac * Pk[tri_idx(b, c)];
-    }
-  }
-  __syncwarp();
-}
-// One warp: x <- L^-T (L^-1 r + z), i.e. mean + chol(P)^-T z of draw.h:382-383.  x, r, z length d.
-__device__ void precision_solve_warp(const double* Lp, int d, const double* r, const double* z, double* x) {
-  const int lane = threadIdx.x & 31;
-  for (int a = 0; a < d; ++a) {  // forward, row-oriented
-    const int ra = a * (a + 1) / 2;
-    double s = 0.0;
-    for (int b = lane; b < a; b += 32) s += Lp[ra + b] * x[b];
-    s = warp_sum(s);
-    if (lane == 0) x[a] = (r[a] - s) / Lp[ra + a];
-    __syncwarp();
-  }
-  for (int a = lane; a < d; a += 32) x[a] += z[a];
-  __syncwarp();
-  for (int c = d - 1; c >= 0; --c) {  // backward with L^T, column c of L
-    double s = 0.0;
-    for (int a = c + 1 + lane; a < d; a += 32) s += Lp[tri_idx(a, c)] * x[a];
-    s = warp_sum(s);
-    if (lane == 0) x[c] = (x[c] - s) / Lp[tri_idx(c, c)];
-    __syncwarp();
-  }
-}
-
 // ------------------------------------------------------------------ stage 4: updateCoef
 // One CTA per unit; equations j = 0..k-1 in order (the draw of equation j conditions on this
 // sweep's draws of equations < j, tri.h:283, 297):
@@ -176,7 +87,7 @@ __global__ void __launch_bounds__(256) coef_kernel(const Dims D, const DevPtrs P
   double* Asm = V + k * d;
   __shared__ int bad;
   if (tid == 0) bad = 0;
-  const Philox rng(P.seeds[u], (uint32_t)u, *P.iter);
+  const Philox rng(P.seeds[u], (uint32_t)(D.ubase + u), *P.iter);
 
   for (int e = tid; e < k * k; e += blockDim.x) Lsm[e] = P.L[(size_t)u * k * k + e];
   double* Ac = P.Acoef + (size_t)w * d * ldM + (size_t)c * k;
@@ -304,132 +215,6 @@ __global__ void __launch_bounds__(256) coef_kernel(const Dims D, const DevPtrs P
   if (tid == 0 && bad) atomicOr(&P.flags[u], 1);
 }
 
-// ------------------------------------------------------------------ stage 7 (+8): updateImpact
-__device__ __forceinline__ int impact_row_off(int j) {  // sum_{j'<j} (j'(j'+1)/2 + j')
-  return ((j - 1) * j * (2 * j - 1) / 6 + 3 * (j - 1) * j / 2) / 2;
-}
-// Row j of L: regress Z_j / s_j on Z_{<j} / s_j with prior N(0, diag(1/prec)) (tri.h:322-336).
-// Phase 1 accumulates, for every pair b <= a, sum_t dinv_tj z_ta z_tb for all j >= a (SV) or the
-// plain Z'Z (LDLT) into gscratch; phase 2 factorises and draws each row with one warp.
-template <bool SV, int KJ>
-__global__ void __launch_bounds__(256) impact_kernel(const Dims D, const DevPtrs P, double* gscratch, const int gsize) {
-  extern __shared__ __align__(16) double sm[];
-  const int u = blockIdx.x, w = u / D.C, c = u % D.C;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
-  const int k = D.k, ldM = D.ldM, q = D.q;
-  const int n = P.win_n[w];
-  const long long off = P.win_off[w] + (long long)c * k;
-  constexpr int TT = 16;
-  double* zt = sm;            // [TT][k]
-  double* dt = zt + TT * k;   // [TT][k]
-  double* wbuf = dt + TT * k; // per-warp packed matrices
-  double* G = gscratch + (size_t)u * gsize;
-  __shared__ int bad;
-  if (tid == 0) bad = 0;
-  const int npairs = k * (k + 1) / 2;
-  for (int pbase = 0; pbase < npairs; pbase += blockDim.x) {
-    const int pid = pbase + tid;
-    int a = 0, b = 0;
-    const bool active = pid < npairs;
-    if (active) {
-      a = (int)((sqrt(8.0 * pid + 1.0) - 1.0) * 0.5);
-      while (tri_idx(a + 1, 0) <= pid) ++a;
-      while (tri_idx(a, 0) > pid) --a;
-      b = pid - tri_idx(a, 0);
-    }
-    for (int jbase = 0; jbase < (SV ? k : 1); jbase += KJ) {
-      double acc[KJ];
-#pragma unroll
-      for (int jj = 0; jj < KJ; ++jj) acc[jj] = 0.0;
-      double nrm = 0.0;
-      for (int t0 = 0; t0 < n; t0 += TT) {
-        __syncthreads();
-        for (int e = tid; e < TT * k; e += blockDim.x) {
-          const int tt = e / k, m = e % k;
-          const bool ok = t0 + tt < n;
-          const long long at = off + (long long)(t0 + tt) * ldM + m;
-          zt[e] = ok ? P.Z[at] : 0.0;
-          if (SV) dt[e] = ok ? P.Dinv[at] : 0.0;
-        }
-        __syncthreads();
-        if (active) {
-#pragma unroll 4
-          for (int tt = 0; tt < TT; ++tt) {
-            const double pz = zt[tt * k + a] * zt[tt * k + b];
-            if (SV) {
-#pragma unroll
-              for (int jj = 0; jj < KJ; ++jj) {
-                const int j = jbase + jj;
-                if (j < k) acc[jj] = fma(dt[tt * k + j], pz, acc[jj]);
-              }
-            } else {
-              acc[0] += pz;
-            }
-            nrm += pz;
-          }
-        }
-      }
-      if (active) {
-        if (SV) {
-#pragma unroll
-          for (int jj = 0; jj < KJ; ++jj) {
-            const int j = jbase + jj;
-            if (j >= k) continue;
-            if (j > a) G[impact_row_off(j) + tri_idx(a, b)] = acc[jj];            // Gram of row j
-            else if (j == a && b < a) G[impact_row_off(j) + j * (j + 1) / 2 + b] = acc[jj];  // rhs of row a
-          }
-        } else {
-          G[tri_idx(a, b)] = acc[0];
-        }
-        if (a == b && jbase == 0) P.znorm[(size_t)u * k + a] = nrm;
-      }
-    }
-  }
-  __threadfence_block();
-  __syncthreads();
-  // phase 2: one warp per row
-  const Philox rng(P.seeds[u], (uint32_t)u, *P.iter);
-  const int wstride = k * (k + 1) / 2 + 3 * k;
-  double* Pw = wbuf + (size_t)warp * wstride;
-  double* r = Pw + k * (k + 1) / 2;
-  double* z = r + k;
-  double* x = z + k;
-  double* Lu = P.L + (size_t)u * k * k;
-  if (tid < k) {  // row 0 of L (build_inv_lower, draw.h:124-132)
-    Lu[tid] = tid == 0 ? 1.0 : 0.0;
-  }
-  for (int j = 1 + warp; j < k; j += nw) {
-    const int id = j * (j - 1) / 2;
-    const double inv_dj = SV ? 1.0 : 1.0 / P.diag[(size_t)u * k + j];
-    const double* Gj = SV ? G + impact_row_off(j) : G;
-    for (int p = lane; p < j * (j + 1) / 2; p += 32) Pw[p] = Gj[p] * inv_dj;
-    __syncwarp();
-    for (int b = lane; b < j; b += 32) {
-      const double pr = P.chol_prec[(size_t)u * q + id + b];
-      Pw[tri_idx(b, b)] += pr;
-      const double g = SV ? Gj[j * (j + 1) / 2 + b] : G[tri_idx(j, b)] * inv_dj;
-      r[b] = g;  // prior_chol_mean = 0 (tri.h:52)
-      z[b] = rng.normal_elem(ST_IMPACT_Z, (uint32_t)(id + b));
-    }
-    __syncwarp();
-    chol_packed_warp(Pw, j, &bad);
-    precision_solve_warp(Pw, j, r, z, x);
-    __syncwarp();
-    for (int b = lane; b < k; b += 32) {
-      double val = b == j ? 1.0 : 0.0;
-      if (b < j) {
-        val = x[b];
-        P.contem[(size_t)u * q + id + b] = val;
-        const double fit = fabs(val) * P.znorm[(size_t)u * k + b];  // draw_savs, draw.h:398-415
-        P.sparse_contem[(size_t)u * q + id + b] = val * fmax(fit - 1.0 / (val * val), 0.0) / fit;
-      }
-      Lu[j * k + b] = val;
-    }
-    __syncwarp();
-  }
-  if (tid == 0 && bad) atomicOr(&P.flags[u], 2);
-}
-
 // ------------------------------------------------------------------ stage 9 (LDLT): updateState
 // d_i = 1 / Gamma(shape_i + floor(n/2), 1 / (scl_i + ||(Z L')_i||^2 / 2))   (draw.h:1244-1259)
 __global__ void __launch_bounds__(128) ldlt_state_kernel(const Dims D, const DevPtrs P) {
@@ -437,7 +222,7 @@ __global__ void __launch_bounds__(128) ldlt_state_kernel(const Dims D, const Dev
   const int u = blockIdx.x, w = u / D.C, c = u % D.C;
   const int k = D.k, n = P.win_n[w];
   const long long off = P.win_off[w] + (long long)c * k;
-  const Philox rng(P.seeds[u], (uint32_t)u, *P.iter);
+  const Philox rng(P.seeds[u], (uint32_t)(D.ubase + u), *P.iter);
   const double* Lu = P.L + (size_t)u * k * k;
   for (int i = 0; i < k; ++i) {
     double ss = 0.0;
@@ -500,7 +285,7 @@ __global__ void __launch_bounds__(256) sv_mix_kernel(const Dims D, const DevPtrs
   const double* Lr = P.L + ((size_t)u * k + i) * k;
 #pragma unroll
   for (int m2 = 0; m2 < KMAX; ++m2) lr[m2] = (m2 <= i) ? Lr[m2] : 0.0;
-  const Philox rng(P.seeds[u], (uint32_t)u, *P.iter);
+  const Philox rng(P.seeds[u], (uint32_t)(D.ubase + u), *P.iter);
   const uint32_t nh = (uint32_t)((n + 1) / 2);
   const int zoff = c * k - zlo;
   double ua = 0.0, ub = 0.0;
@@ -555,7 +340,7 @@ __global__ void __launch_bounds__(128) sv_solve_kernel(const Dims D, const DevPt
   const int u = w * D.C + c;
   const double isig = 1.0 / P.lvol_sig[(size_t)u * D.k + i];
   const double h0 = P.lvol_init[(size_t)u * D.k + i];
-  const Philox rng(P.seeds[u], (uint32_t)u, *P.iter);
+  const Philox rng(P.seeds[u], (uint32_t)(D.ubase + u), *P.iter);
   const uint32_t nh = (uint32_t)((n + 1) / 2);
   double wprev = 0.0, yprev = 0.0;  // w = 1 / l
   for (int t0 = 0; t0 < n; t0 += SVS_B) {
@@ -622,7 +407,7 @@ __global__ void __launch_bounds__(128) sv_finish_kernel(const Dims D, const DevP
   const int u = blockIdx.x, w = u / D.C, c = u % D.C;
   const int k = D.k, n = P.win_n[w];
   const long long off = P.win_off[w] + (long long)c * k;
-  const Philox rng(P.seeds[u], (uint32_t)u, *P.iter);
+  const Philox rng(P.seeds[u], (uint32_t)(D.ubase + u), *P.iter);
   double* Kp = sm;                      // packed k(k+1)/2
   double* r = Kp + k * (k + 1) / 2;
   double* z = r + k;
@@ -764,25 +549,6 @@ cudaError_t launch_draw_coef_batched(long long batch, int d, const double* Pp, c
   if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
   cudaFuncSetAttribute(draw_coef_batched_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   draw_coef_batched_kernel<<<(unsigned)batch, 256, smem, st>>>(d, Pp, b, z, out);
-  return cudaGetLastError();
-}
-int impact_gsize(const Dims& D) {
-  const int k = D.k;
-  if (!D.sv) return k * (k + 1) / 2;
-  return ((k - 1) * k * (2 * k - 1) / 6 + 3 * (k - 1) * k / 2) / 2 + 8;
-}
-cudaError_t launch_impact(const Dims& D, const DevPtrs& P, double* gscratch, cudaStream_t st) {
-  const int k = D.k;
-  const int nw = 8;
-  const size_t smem = (2 * 16 * (size_t)k + (size_t)nw * (k * (k + 1) / 2 + 3 * k)) * sizeof(double);
-  const int gs = impact_gsize(D);
-  if (D.sv) {
-    cudaFuncSetAttribute(impact_kernel<true, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    impact_kernel<true, 32><<<D.U, 256, smem, st>>>(D, P, gscratch, gs);
-  } else {
-    cudaFuncSetAttribute(impact_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    impact_kernel<false, 1><<<D.U, 256, smem, st>>>(D, P, gscratch, gs);
-  }
   return cudaGetLastError();
 }
 cudaError_t launch_sv_prep(const Dims& D, const DevPtrs& P, cudaStream_t st) {

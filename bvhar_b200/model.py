@@ -94,7 +94,7 @@ class _AutoregBayes:
     def _make_inits(self):
         n_design = self.design_.shape[1]
         self.init_ = make_inits(self.spec_.prior, self._is_sv, self.n_features_in_, n_design, self.response_.shape[0],
-                                len(self._group_id), self.chains_, self._rng)
+                                len(self._group_id), self.chains_, self._rng, include_mean=self.fit_intercept)
 
     def _seeds(self, *shape):
         return self._rng.integers(1, np.iinfo(np.int32).max, size=shape)
@@ -273,6 +273,8 @@ class VarBayes(_AutoregBayes):
             self._cross_id = np.array([2], dtype=np.int32)
         self._validate()
         self.thread_ = n_thread
+        if self.thread_ > n_chain:  # _bayes.py:300-301 (threads have no meaning on the GPU; the message is kept)
+            warnings.warn(f"'n_thread = {self.thread_} > 'n_chain' = {n_chain}' will not use every thread. Specify as 'n_thread <= 'n_chain'.")
         self._make_inits()
 
     def _design_of(self, y):
@@ -302,6 +304,8 @@ class VharBayes(_AutoregBayes):
             self._cross_id = np.array([2], dtype=np.int32)
         self._validate()
         self.thread_ = n_thread
+        if self.thread_ > n_chain:  # _bayes.py:754-755
+            warnings.warn(f"'n_thread = {self.thread_} > 'n_chain' = {n_chain}' will not use every thread. Specify as 'n_thread <= 'n_chain'.")
         self._make_inits()
 
     def _coef_name(self) -> str:

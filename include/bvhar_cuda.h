@@ -146,7 +146,9 @@ typedef struct {
   int32_t thin;
   uint32_t record_mask;
   int32_t lvol_from_init; /* SvInits(init, num_design): replicate lvol_init over time (config.h:416-420) */
-  int32_t reserved0;
+  int32_t unit_id_base; /* global index of this engine's first unit: unit u draws from the Philox stream keyed
+                           (seed_chain[u], unit_id_base + u), so a batch split over several engines / GPUs
+                           reproduces the draws of the unsplit batch bit for bit */
   int64_t n_rows_total; /* leading dimension of x and y */
   const double* x;      /* n_rows_total x dim_design */
   const double* y;      /* n_rows_total x dim */

@@ -105,6 +105,10 @@ class OracleFit:
 
     def get_state(self, name, window=0, chain=0):
         n = self.L.oracle_fit_state_len(self.h, name.encode())
+        if name in ("latent_innov", "lvol_draw", "sqrt_sv"):  # n x k of THIS window (ragged window tables)
+            n = int(self.packed.win_nrow[window]) * self.packed.dim
+        if n == 0:  # e.g. the contemporaneous block of a univariate model
+            return np.empty(0)
         out = np.empty(n)
         rc = self.L.oracle_fit_get_state(self.h, window, chain, name.encode(), dp(out), n)
         if rc:

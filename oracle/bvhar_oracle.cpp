@@ -1127,7 +1127,7 @@ static Fit* build_fit(const bvhar_fit_desc* D, int faithful, int rng_mode) {
     for (int c = 0; c < S.C; ++c) {
       const int u = w * S.C + c;
       F->chains[u].reset(new Chain);
-      F->chains[u]->init(&F->S, &F->wins[w], D->init[c], D->seed_chain[u], (uint32_t)u);
+      F->chains[u]->init(&F->S, &F->wins[w], D->init[c], D->seed_chain[u], (uint32_t)(D->unit_id_base + u));
     }
   return F.release();
 }

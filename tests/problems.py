@@ -59,7 +59,7 @@ def make_problem(prior="DL", sv=True, dim=3, T=40, lag=2, vhar=False, week=2, mo
     elif prior in ("Minnesota", "HMN"):
         cfg.update(y, p, dim)
     n_obs = resp.shape[0] if windows is None else windows[0][1]
-    inits = sp.make_inits(prior, sv, dim, x.shape[1], n_obs, len(grp_id), chains, rng)
+    inits = sp.make_inits(prior, sv, dim, x.shape[1], n_obs, len(grp_id), chains, rng, include_mean=include_mean)
     n_win = 1 if windows is None else len(windows)
     seeds = rng.integers(1, 2**31 - 1, size=(n_win, chains))
     kw = dict(num_chains=chains, num_iter=iters, num_burn=burn, thin=thin, x=x, y=resp, param_cov=cov.to_dict(),

@@ -1,0 +1,95 @@
+"""The drop-in boundary: include/bvhar_cuda.h <-> libbvhar_b200.so <-> the ctypes mirror.  No GPU needed
+(no compute call is made); on a box without a device the engine must refuse loudly, never fall back."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from bvhar_b200 import _abi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "bvhar_cuda.h")
+
+
+def _declared_symbols():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(bvhar_cuda_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_declares_the_expected_entry_points():
+    syms = _declared_symbols()
+    for must in ("bvhar_cuda_fit_create", "bvhar_cuda_fit_run", "bvhar_cuda_fit_record", "bvhar_cuda_fit_destroy",
+                 "bvhar_cuda_forecast_density", "bvhar_cuda_last_error"):
+        assert must in syms
+
+
+def test_library_exports_every_declared_symbol():
+    lib = C.CDLL(_abi.lib_path())
+    missing = [s for s in _declared_symbols() if not hasattr(lib, s)]
+    assert not missing, f"declared in include/bvhar_cuda.h but not exported: {missing}"
+
+
+def test_abi_version_and_struct_layout():
+    L = _abi.load_library()  # raises if the version or any sizeof() differs
+    assert L.bvhar_cuda_abi_version() == _abi.ABI_VERSION
+    m = re.search(r"#define\s+BVHAR_CUDA_ABI_VERSION\s+(\d+)", open(HEADER).read())
+    assert int(m.group(1)) == _abi.ABI_VERSION
+
+
+def test_enums_match_header():
+    src = open(HEADER).read()
+    for name, val in (("BVHAR_PRIOR_MINNESOTA", 1), ("BVHAR_PRIOR_SSVS", 2), ("BVHAR_PRIOR_HORSESHOE", 3),
+                      ("BVHAR_PRIOR_HIERMINN", 4), ("BVHAR_PRIOR_NG", 5), ("BVHAR_PRIOR_DL", 6), ("BVHAR_PRIOR_GDP", 7),
+                      ("BVHAR_COV_LDLT", 0), ("BVHAR_COV_SV", 1)):
+        assert re.search(rf"{name}\s*=\s*{val}\b", src), name
+
+
+def test_no_cpu_fallback_without_a_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present; the refusal path is exercised on CPU-only boxes")
+    import problems as pr
+    pk, _ = pr.pack(prior="Minnesota", sv=False)
+    L = _abi.load_library()
+    h = C.c_void_p()
+    rc = L.bvhar_cuda_fit_create(C.byref(pk.desc), C.byref(h))
+    assert rc == 2, "fit_create must fail with BVHAR_ERR_CUDA when no device is usable"
+    assert b"no CPU fallback" in L.bvhar_cuda_last_error()
+    out = np.zeros(4)
+    a = np.ones((2, 2))
+    rc = L.bvhar_cuda_dgemm_tn(0, 2, 2, 2, a.ctypes.data_as(_abi.c_dp), 2, a.ctypes.data_as(_abi.c_dp), 2,
+                               out.ctypes.data_as(_abi.c_dp), 2)
+    assert rc == 2
+
+
+def test_product_package_never_imports_the_oracle():
+    """oracle/ is test infrastructure: nothing in the product may import, include, link or dlopen it."""
+    pkg = os.path.join(ROOT, "bvhar_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if not f.endswith((".py", ".cu", ".cuh", ".h", ".cpp", "Makefile")):
+                continue
+            for line in open(os.path.join(dirpath, f), errors="ignore"):
+                s = line.strip()
+                if s.startswith(("import ", "from ", "#include")) or "CDLL" in s or "dlopen" in s or "-l" in s.split():
+                    assert "oracle" not in s.lower(), f"{f}: {s}"
+
+
+def test_descriptor_validation_is_host_side():
+    import problems as pr
+    kw, _ = pr.make_problem(prior="SSVS", sv=True)
+    bad = dict(kw)
+    bad["seed_chain"] = np.arange(5)
+    with pytest.raises(ValueError):
+        _abi.PackedFit(**bad)
+    bad = dict(kw)
+    bad["grp_mat"] = np.ones((3, 3), dtype=np.int32)
+    with pytest.raises(ValueError):
+        _abi.PackedFit(**bad)
+    bad = dict(kw)
+    bad["param_init"] = kw["param_init"][:1]
+    with pytest.raises(ValueError):
+        _abi.PackedFit(**bad)

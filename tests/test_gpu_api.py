@@ -1,0 +1,113 @@
+"""The reference-facing Python classes on the GPU, written like the reference's own smoke tests
+(python/tests/test_bayes.py:8-133, 135-259; tests/testthat/test-var-bayes.R, test-summary-forecast.R):
+every prior x {LDLT, SV} on etf_vix[:50, :2], a few iterations, shapes / names / error messages."""
+import warnings
+
+import numpy as np
+import pytest
+
+from bvhar_b200 import datasets
+from bvhar_b200._spec import (DlConfig, GdpConfig, HorseshoeConfig, InterceptConfig, LambdaConfig, LdltConfig, MinnesotaConfig,
+                              NgConfig, SsvsConfig, SvConfig)
+from bvhar_b200.model import VarBayes, VharBayes
+
+pytestmark = pytest.mark.gpu
+
+PRIOR_CFGS = [SsvsConfig, HorseshoeConfig, lambda: MinnesotaConfig(lam=LambdaConfig()), MinnesotaConfig, NgConfig, DlConfig, GdpConfig]
+PRIOR_NAMES = {"SSVS": {"gamma"}, "Horseshoe": {"lambda", "eta", "tau", "kappa"}, "NG": {"lambda", "eta", "tau"}, "DL": {"lambda", "tau"}}
+
+
+def _data(num_data=50, dim=2, n_ahead=5):
+    vix = datasets.load_vix()
+    return vix[:num_data, :dim], vix[num_data:num_data + n_ahead, :dim]
+
+
+def _check_forecast(out, rows, dim):
+    for key in ("forecast", "se", "lower", "upper"):
+        assert out[key].shape == (rows, dim)
+        assert np.all(np.isfinite(out[key]))
+    assert np.all(out["lower"] <= out["upper"])
+
+
+@pytest.mark.parametrize("cfg", PRIOR_CFGS)
+@pytest.mark.parametrize("cov", [LdltConfig, SvConfig])
+def test_var_bayes(cfg, cov):
+    dim, lag, n_ahead = 2, 3, 5
+    data, test_y = _data(n_ahead=n_ahead)
+    fit = VarBayes(data, lag, 2, 5, 2, 1, cfg(), cov(), InterceptConfig(), True, True, True, False, 1, seed=1)
+    fit.fit()
+    assert fit.n_features_in_ == dim
+    assert fit.coef_.shape == (dim * lag + 1, dim)
+    assert fit.intercept_.shape == (dim,)
+    assert fit.param_["alpha_record"].shape == (2, 3, dim * dim * lag)  # chains x kept draws x N (test-var-bayes.R:251-254)
+    for nm in PRIOR_NAMES.get(fit.spec_.prior, ()):  # test-var-bayes.R:31-32, 49, 82, 99
+        assert nm in fit.param_names_
+    assert ("h" in fit.param_names_) == (cov is SvConfig) and ("d" in fit.param_names_) == (cov is LdltConfig)
+    _check_forecast(fit.predict(n_ahead, stable=False, sparse=True), n_ahead, dim)
+    _check_forecast(fit.roll_forecast(1, test_y, stable=False, sparse=True), n_ahead, dim)
+    _check_forecast(fit.expand_forecast(1, test_y, stable=False, sparse=False), n_ahead, dim)
+    frame = fit.to_frame()
+    assert len(frame) == 2 * 3 and "alpha[1]" in frame.columns
+
+
+@pytest.mark.parametrize("cfg", PRIOR_CFGS)
+@pytest.mark.parametrize("cov", [LdltConfig, SvConfig])
+def test_vhar_bayes(cfg, cov):
+    dim, n_ahead = 2, 5
+    data, test_y = _data(n_ahead=n_ahead)
+    c = cfg()
+    if isinstance(c, MinnesotaConfig):
+        c = MinnesotaConfig(lam=c.lam if hasattr(c, "lam") and isinstance(c.lam, LambdaConfig) else .1, is_long=True)
+    fit = VharBayes(data, 5, 22, 2, 5, 2, 1, c, cov(), InterceptConfig(), True, "longrun", True, False, 1, seed=1)
+    fit.fit()
+    assert fit.coef_.shape == (dim * 3 + 1, dim)
+    assert fit.intercept_.shape == (dim,)
+    _check_forecast(fit.predict(n_ahead, stable=False, sparse=True), n_ahead, dim)
+    _check_forecast(fit.roll_forecast(1, test_y, stable=False, sparse=True), n_ahead, dim)
+    _check_forecast(fit.expand_forecast(1, test_y, stable=False, sparse=True), n_ahead, dim)
+    assert any(col.startswith("phi[") for col in fit.to_frame().columns)  # R/vhar-bayes.R:526 renames alpha -> phi
+
+
+def test_errors_and_warnings():
+    data, _ = _data()
+    with pytest.warns(UserWarning, match="will not use every thread"):
+        VarBayes(data, 3, 2, 5, 2, 1, SsvsConfig(), LdltConfig(), InterceptConfig(), True, True, False, True, 3)
+    with pytest.raises(ValueError, match="'data' rows must be larger than 'lag' = 3"):
+        VarBayes(data[:2], 3, 2, 5, 2, 1, SsvsConfig(), LdltConfig(), InterceptConfig(), True, True, False, True, 1)
+    with pytest.raises(TypeError):
+        VarBayes(data, 3, 2, 5, 2, 1, SsvsConfig(), "ldlt", InterceptConfig())
+    with pytest.raises(ValueError):
+        VarBayes(data.reshape(-1), 3)
+
+
+def test_lpl_and_multistep_roll():
+    data, test_y = _data(n_ahead=6)
+    fit = VarBayes(data, 2, 2, 6, 2, 1, HorseshoeConfig(), SvConfig(), seed=3).fit()
+    out = fit.roll_forecast(2, test_y)  # 6 - 2 + 1 = 5 windows, last step kept (forecaster.h:803)
+    _check_forecast(out, 5, 2)
+    assert out["lpl"].shape == (5,) and np.all(np.isfinite(out["lpl"]))
+
+
+def test_fit_is_reproducible_for_a_seed():
+    data, _ = _data()
+    a = VharBayes(data, 5, 22, 3, 6, 2, 1, DlConfig(), SvConfig(), seed=9).fit()
+    b = VharBayes(data, 5, 22, 3, 6, 2, 1, DlConfig(), SvConfig(), seed=9).fit()
+    c = VharBayes(data, 5, 22, 3, 6, 2, 1, DlConfig(), SvConfig(), seed=10).fit()
+    assert np.array_equal(a.param_["alpha_record"], b.param_["alpha_record"])
+    assert not np.array_equal(a.param_["alpha_record"], c.param_["alpha_record"])
+
+
+def test_progress_callback_and_interrupt():
+    import problems as pr
+    from bvhar_b200._abi import BvharCudaError
+    from bvhar_b200._engine import CudaFit
+    pk, _ = pr.pack(prior="DL", sv=True, iters=40, burn=20)
+    seen = []
+    g = CudaFit(pk)
+    g.run(lambda done, total: seen.append((done, total)) or False)
+    assert seen[-1] == (40, 40) and len(seen) == 20  # every 5 % (triangular.h:1248-1251)
+    g2 = CudaFit(pk)
+    with pytest.raises(BvharCudaError) as ei:
+        g2.run(lambda done, total: done >= 24)
+    assert ei.value.status == 4  # interrupted: partial records stay readable (triangular.h:1261-1270)
+    assert g2.record("alpha_record").shape[0] == 4

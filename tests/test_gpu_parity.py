@@ -1,0 +1,226 @@
+"""Parity of the CUDA engine with the CPU oracle, through the C-ABI (`pytest -m gpu`, needs a B200).
+
+Level 1 (north_star): deterministic stages fed the same random numbers must agree to 1e-10 relative.
+Both sides draw from the same addressed Philox stream, so after the building blocks every stage of the
+sweep, and whole multi-sweep trajectories, are compared state-for-state and record-for-record.
+Tolerances: 1e-10 for single stages, 1e-7 for multi-sweep trajectories (rounding differences between
+the device's FMA / reduction order and the host's are amplified by the sampler's own dynamics)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+from numpy.testing import assert_allclose
+
+import oracle_binding as ob
+import problems as pr
+from bvhar_b200 import _abi
+from bvhar_b200._engine import CudaFit, forecast_density
+
+pytestmark = pytest.mark.gpu
+
+STAGE_TOL = 1e-10
+TRAJ_TOL = 1e-7
+
+STATES = {1: ["prior_alpha_prec"], 3: ["sqrt_sv"], 4: ["coef_mat", "sparse_coef"], 5: ["prior_chol_prec"],
+          6: ["latent_innov"], 7: ["contem_coef", "sparse_contem"], 8: ["chol_lower"], 9: []}  # the engine fuses 8 into 7
+HYPER = {
+    "SSVS": ["coef_dummy", "coef_slab", "coef_weight", "spike_scl", "contem_dummy", "contem_slab", "contem_weight", "contem_spike_scl"],
+    "Horseshoe": ["local_lev", "latent_local", "shrink_fac", "group_lev", "latent_group", "global_lev", "contem_local_lev",
+                  "latent_contem_local", "contem_global_lev"],
+    "HMN": ["own_lambda", "contem_lambda"],
+    "NG": ["local_lev", "group_lev", "local_shape", "global_lev", "contem_fac", "contem_global_lev", "contem_shape"],
+    "DL": ["local_lev", "latent_local", "group_lev", "global_lev", "dir_concen", "contem_local_lev", "latent_contem_local",
+           "contem_global_lev", "contem_dir_concen"],
+    "GDP": ["local_lev", "group_rate", "coef_gamma_shape", "coef_gamma_rate", "contem_fac", "contem_rate", "contem_gamma_shape",
+            "contem_gamma_rate"],
+    "Minnesota": [],
+}
+
+
+def relerr(a, b):
+    a = np.asarray(a, dtype=np.float64); b = np.asarray(b, dtype=np.float64)
+    assert a.shape == b.shape
+    if a.size == 0:
+        return 0.0
+    nan_a, nan_b = np.isnan(a), np.isnan(b)
+    assert np.array_equal(nan_a, nan_b), "NaN pattern differs (SAVS 0/0 entries must match, draw.h:417-430)"
+    inf_a, inf_b = np.isinf(a), np.isinf(b)
+    assert np.array_equal(inf_a, inf_b) and np.array_equal(a[inf_a], b[inf_b]), "infinities differ"
+    ok = ~nan_a & ~inf_a
+    if not ok.any():
+        return 0.0
+    scale = np.maximum(np.abs(a[ok]), np.abs(b[ok]))
+    floor = 1e-3 * scale.max() + 1e-300  # entries far below the array's own scale are judged against that scale
+    return float(np.max(np.abs(a[ok] - b[ok]) / np.maximum(scale, floor)))
+
+
+# ---------------------------------------------------------------- building blocks
+@pytest.mark.parametrize("M,N,K", [(37, 29, 50), (130, 257, 33), (256, 128, 64), (20, 1891, 1000), (1, 1, 1), (129, 3, 7)])
+def test_dgemm_tn_dmma(M, N, K):
+    """The DMMA contraction (SV-weighted Gram / latent residual) against a float64 host contraction."""
+    rng = np.random.default_rng(M * 1000 + N)
+    A = rng.normal(size=(K, M)); B = rng.normal(size=(K, N)); Cg = np.zeros((M, N))
+    L = _abi.load_library()
+    _abi.check(L.bvhar_cuda_dgemm_tn(0, M, N, K, A.ctypes.data_as(_abi.c_dp), M, B.ctypes.data_as(_abi.c_dp), N,
+                                     Cg.ctypes.data_as(_abi.c_dp), N))
+    Co = np.zeros((M, N))
+    ob.lib().oracle_dgemm_tn(M, N, K, ob.dp(A), ob.dp(B), ob.dp(Co))
+    assert_allclose(Cg, Co, rtol=1e-11, atol=1e-11 * np.sqrt(K))
+
+
+@pytest.mark.parametrize("d,batch", [(1, 3), (7, 5), (28, 9), (46, 4), (61, 64), (97, 3), (150, 2)])
+def test_draw_coef_batched(d, batch):
+    """chol + two triangular solves + Gaussian draw (draw.h:372-383) for a batch of systems, 1e-10."""
+    rng = np.random.default_rng(d)
+    np_ = d * (d + 1) // 2
+    Pp = np.empty((batch, np_)); b = rng.normal(size=(batch, d)); z = rng.normal(size=(batch, d))
+    for s in range(batch):
+        X = rng.normal(size=(d + 20, d))
+        P = X.T @ X + np.diag(rng.uniform(0.1, 2, d))
+        Pp[s] = np.concatenate([P[a, : a + 1] for a in range(d)])
+    out = np.empty((batch, d))
+    L = _abi.load_library()
+    _abi.check(L.bvhar_cuda_draw_coef_batched(0, batch, d, Pp.ctypes.data_as(_abi.c_dp), b.ctypes.data_as(_abi.c_dp),
+                                              z.ctypes.data_as(_abi.c_dp), out.ctypes.data_as(_abi.c_dp)))
+    ref = np.empty(d)
+    for s in range(batch):
+        ob.lib().oracle_draw_coef_packed(d, ob.dp(Pp[s]), ob.dp(b[s]), ob.dp(z[s]), ob.dp(ref))
+        assert relerr(ref, out[s]) < STAGE_TOL
+
+
+# ---------------------------------------------------------------- stage by stage
+def _stage_check(prior, sv, **kw):
+    pk, _ = pr.pack(prior=prior, sv=sv, **kw)
+    o = ob.OracleFit(pk, faithful=False); g = CudaFit(pk)
+    worst = 0.0
+    for it in (1, 2):
+        for st in range(1, 10):
+            o.run_stage(st, it); g.run_stage(st, it)
+            names = list(STATES.get(st, []))
+            if st in (1, 5):
+                names += HYPER[prior]
+            if st == 9:
+                names += ["lvol_draw", "lvol_sig", "lvol_init"] if sv else ["diag_vec"]
+            if st == 3 and not sv:
+                names = []
+            for nm in names:
+                for w in range(pk.n_windows):
+                    for c in range(pk.n_chains):
+                        e = relerr(o.get_state(nm, w, c), g.get_state(nm, w, c))
+                        assert e < STAGE_TOL, f"{prior} sv={sv} sweep {it} stage {st} {nm}[w{w} c{c}]: rel err {e:.3e}"
+                        worst = max(worst, e)
+    o.close(); g.close()
+    return worst
+
+
+@pytest.mark.parametrize("prior", pr.PRIORS)
+@pytest.mark.parametrize("sv", [True, False])
+def test_every_stage_every_prior(prior, sv):
+    _stage_check(prior, sv)
+
+
+@pytest.mark.parametrize("kw", [
+    dict(vhar=True, week=2, month=4, T=44), dict(include_mean=False), dict(ggl=False), dict(minnesota=False),
+    dict(dim=1, T=30), dict(dim=5, lag=3, T=60, chains=3), dict(dim=2, lag=1, T=25),
+    dict(dim=3, T=70, lag=7),      # d = 22
+    dict(dim=4, T=120, lag=9),     # d = 37 > 32: two register blocks in the warp Cholesky
+    dict(dim=7, T=150, lag=10, chains=1),  # d = 71 > 64: three blocks
+], ids=lambda k: ",".join(f"{a}={b}" for a, b in k.items()))
+@pytest.mark.parametrize("prior,sv", [("Horseshoe", True), ("SSVS", False), ("DL", True)])
+def test_stage_parity_model_variants(prior, sv, kw):
+    _stage_check(prior, sv, **kw)
+
+
+def test_stage_parity_windows():
+    """Rolling (equal) and expanding (ragged) window tables in one batch (forecaster.h:851-859, 920-928)."""
+    _stage_check("NG", True, dim=2, T=48, chains=2, windows=[(0, 30), (1, 30), (5, 30), (16, 30)])
+    pk_kw = dict(dim=2, T=48, chains=2, windows=[(0, 30), (0, 31), (0, 37), (0, 46)])
+    kw, _ = pr.make_problem(prior="GDP", sv=True, **pk_kw)
+    kw["lvol_from_init"] = True
+    pk = _abi.PackedFit(**kw)
+    o = ob.OracleFit(pk); g = CudaFit(pk)
+    o.step(3, False); g.step(3, False)
+    for w in range(4):
+        for c in range(2):
+            for nm in ("coef_mat", "lvol_draw", "contem_coef", "local_lev"):
+                assert relerr(o.get_state(nm, w, c), g.get_state(nm, w, c)) < TRAJ_TOL, (nm, w, c)
+    _stage_check("Minnesota", False, dim=3, T=48, chains=2, windows=[(0, 30), (0, 33), (2, 41)])
+
+
+# ---------------------------------------------------------------- whole trajectories
+@pytest.mark.parametrize("prior", pr.PRIORS)
+@pytest.mark.parametrize("sv", [True, False])
+def test_trajectory_records(prior, sv):
+    """5 recorded sweeps after 2 warm-up sweeps through fit_run (CUDA-graph replay): every record of
+    every chain equals the oracle's, including thinning (draw.h:1297-1310)."""
+    pk, _ = pr.pack(prior=prior, sv=sv, dim=3, T=40, chains=3, iters=12, burn=2, thin=2)
+    o = ob.OracleFit(pk); g = CudaFit(pk)
+    o.run(); g.run()
+    assert g.record_names() == o.record_names()
+    for nm in g.record_names():
+        for c in range(3):
+            a, b = o.record(nm, 0, c), g.record(nm, 0, c)
+            assert a.shape == b.shape and a.shape[0] == 5
+            assert relerr(a, b) < TRAJ_TOL, f"{prior} sv={sv} {nm} chain {c}"
+    bulk = g.record_all("alpha_record")
+    assert bulk.shape == (3, 5, pk.n_alpha)
+    assert_allclose(bulk[1], g.record("alpha_record", 0, 1), rtol=0, atol=0)
+    o.close(); g.close()
+
+
+def test_unit_id_base_shifts_the_stream():
+    kw, _ = pr.make_problem(prior="DL", sv=True, chains=4, iters=3, burn=0)
+    full = CudaFit(_abi.PackedFit(**kw)); full.run()
+    from bvhar_b200._partition import shard_fit_kwargs, shard_units
+    for r in range(2):
+        sh = shard_units(1, 4, 2, r)
+        part = CudaFit(_abi.PackedFit(**shard_fit_kwargs(kw, sh))); part.run()
+        for i, c in enumerate(sh.chains):
+            assert np.array_equal(part.record("alpha_record", 0, i), full.record("alpha_record", 0, c))
+            assert np.array_equal(part.record("h_record", 0, i), full.record("h_record", 0, c))
+
+
+# ---------------------------------------------------------------- golden fixtures (no oracle at run time)
+def _golden_names():
+    import golden
+    return sorted(golden.CASES)
+
+
+@pytest.mark.parametrize("name", _golden_names())
+def test_golden_trajectories(name):
+    """Committed fixtures (tests/golden/*.npz): the engine is checked without executing the oracle."""
+    import golden
+    case = golden.load(name)
+    g = CudaFit(golden.pack(case)); g.run()
+    for nm, exp in case["records"].items():
+        got = np.stack([g.record(nm, w, c) for w in range(case["windows"]) for c in range(case["chains"])])
+        assert relerr(exp, got) < TRAJ_TOL, f"{name}: {nm}"
+
+
+# ---------------------------------------------------------------- forecast
+@pytest.mark.parametrize("sv_model,vhar,lpl", [(True, False, True), (False, False, False), (True, True, True), (False, True, True)])
+def test_forecast_density(sv_model, vhar, lpl):
+    """McmcForecaster::forecastDensity (forecaster.h:55-85, 162-190, 248-262) from stored draws."""
+    pk, meta = pr.pack(prior="Horseshoe", sv=sv_model, dim=3, T=60, vhar=vhar, week=2, month=4, chains=2, iters=9, burn=1)
+    g = CudaFit(pk); g.run()
+    units = [g.records(0, c) for c in range(2)]
+    from bvhar_b200._design import build_vhar
+    har = build_vhar(3, 2, 4, True) if vhar else None
+    lag = 4 if vhar else 2
+    valid = meta["y"][-1] * 0.9 if lpl else None
+    step = 4
+    dens, l = forecast_density(units, [meta["y"]] * 2, step, lag, True, sv_model, [11, 12], har_trans=har, valid_vec=valid)
+    # the oracle on the same descriptor
+    from bvhar_b200._engine import pack_forecast
+    D, keep = pack_forecast(units, [meta["y"]] * 2, step, lag, True, sv_model, [11, 12], har_trans=har, valid_vec=valid)
+    S = D.n_draws
+    out = np.empty(2 * step * S * 3); lp = np.zeros(2 * step)
+    ob.lib().oracle_forecast_density(C.byref(D), 0, ob.dp(out), ob.dp(lp) if lpl else None)
+    dens2, _ = forecast_density(units, [meta["y"]] * 2, step, lag, True, sv_model, [11, 12], har_trans=har, valid_vec=valid)
+    for u in range(2):
+        ref = out[u * step * S * 3:(u + 1) * step * S * 3].reshape(step, S * 3, order="F")
+        assert dens[u].shape == (step, S * 3)
+        assert relerr(ref, dens[u]) < 1e-9
+        assert relerr(dens[u], dens2[u]) == 0.0
+    if lpl:
+        assert relerr(lp.reshape(2, step), l) < 1e-9

@@ -1,0 +1,76 @@
+"""Level-2 parity (north_star): full MCMC runs of the CUDA engine and of the oracle driven by an
+INDEPENDENT random stream (std::mt19937 sequential draws, as the reference's one-generator-per-chain design,
+triangular.h:207) must agree in posterior means, standard deviations and forecast MSE within 3 Monte-Carlo
+standard errors.  MCSE is estimated from the spread of chain means (many short independent chains).
+A handful of the many compared coordinates may exceed 3 sigma by chance: the test bounds the worst |z| by
+4.5 and the fraction beyond 3 by 2 %."""
+import numpy as np
+import pytest
+
+import oracle_binding as ob
+import problems as pr
+from bvhar_b200._engine import CudaFit, forecast_density
+
+pytestmark = pytest.mark.gpu
+
+CHAINS = 48
+ITERS, BURN = 700, 300
+
+
+def _chain_stats(fit, name, chains, is_oracle):
+    recs = np.stack([fit.record(name, 0, c) for c in range(chains)])  # [chain, draw, col]
+    return recs.mean(axis=1), recs.std(axis=1, ddof=1)
+
+
+def _compare(a_means, b_means, label):
+    """z-score of the difference of across-chain averages; MCSE from the across-chain spread."""
+    ma, mb = a_means.mean(axis=0), b_means.mean(axis=0)
+    se = np.sqrt(a_means.var(axis=0, ddof=1) / a_means.shape[0] + b_means.var(axis=0, ddof=1) / b_means.shape[0])
+    ok = se > 0
+    z = np.abs(ma - mb)[ok] / se[ok]
+    assert z.size > 0
+    frac3 = float(np.mean(z > 3.0))
+    assert z.max() < 4.5 and frac3 <= 0.02, f"{label}: max |z| = {z.max():.2f}, {100 * frac3:.1f}% beyond 3 MCSE"
+    return z
+
+
+@pytest.mark.parametrize("prior,sv", [("Horseshoe", True), ("SSVS", False), ("DL", True), ("NG", False), ("GDP", True),
+                                      ("Minnesota", False), ("HMN", True)])
+def test_posterior_moments_within_3_mcse(prior, sv):
+    kw = dict(prior=prior, sv=sv, dim=3, T=80, lag=1, chains=CHAINS, iters=ITERS, burn=BURN, seed=101)
+    pk, meta = pr.pack(**kw)
+    g = CudaFit(pk); g.run()
+    o = ob.OracleFit(pk, faithful=False, rng="mt19937"); o.run()
+    names = ["alpha_record", "a_record", "c_record"] + (["sigh_record", "h0_record"] if sv else ["d_record"])
+    for nm in names:
+        gm, gs = _chain_stats(g, nm, CHAINS, False)
+        om, os_ = _chain_stats(o, nm, CHAINS, True)
+        _compare(gm, om, f"{prior} sv={sv} mean of {nm}")
+        _compare(gs, os_, f"{prior} sv={sv} sd of {nm}")
+    if sv:  # a slice of the log-volatility path
+        gh = np.stack([g.record("h_record", 0, c) for c in range(CHAINS)])[:, :, ::37]
+        oh = np.stack([o.record("h_record", 0, c) for c in range(CHAINS)])[:, :, ::37]
+        _compare(gh.mean(axis=1), oh.mean(axis=1), f"{prior} mean of h")
+    o.close(); g.close()
+
+
+def test_forecast_mse_within_3_mcse():
+    """One-step density forecasts from both posteriors: per-chain squared error of the predictive mean."""
+    kw = dict(prior="Horseshoe", sv=True, dim=3, T=81, lag=1, chains=CHAINS, iters=ITERS, burn=BURN, seed=202)
+    kwp, meta = pr.make_problem(**kw)
+    y = meta["y"]
+    from bvhar_b200._abi import PackedFit
+    train = y[:-1]
+    kwp2, meta2 = pr.make_problem(**{**kw, "y": train})
+    pk = PackedFit(**kwp2)
+    g = CudaFit(pk); g.run()
+    o = ob.OracleFit(pk, rng="mt19937"); o.run()
+    truth = y[-1]
+    res = []
+    for fit in (g, o):
+        units = [fit.records(0, c) if fit is g else {nm: fit.record(nm, 0, c) for nm in fit.record_names()} for c in range(CHAINS)]
+        dens, _ = forecast_density(units, [train] * CHAINS, 1, 1, True, True, np.arange(1, CHAINS + 1))
+        S = dens[0].shape[1] // 3
+        pm = np.stack([d.reshape(1, S, 3)[0].mean(axis=0) for d in dens])  # per-chain predictive mean
+        res.append(((pm - truth) ** 2))
+    _compare(res[0], res[1], "forecast squared error")
