@@ -15,6 +15,7 @@
 // coalesced loads: lanes own columns (private accumulators for the upper part) and one warp reduction
 // per row gives the lower part.  LDLT models have S_i = X'X / d_i: one product per equation.
 #include "engine.cuh"
+#include "gemm_tn.cuh"
 #include "kernels.h"
 #include "rng.cuh"
 #include "warp_linalg.cuh"
@@ -70,73 +71,105 @@ __global__ void __launch_bounds__(256) coef_pbuild_generic_kernel(const Dims D, 
 }
 
 // ---- B: the sequential-in-j part, one CTA per unit ---------------------------------------------
+// Shared memory holds everything the dependent chain touches: h_i = C_i - S_i v_i (k x d), the unit's
+// coefficient matrix, all k*d standard normals of the sweep (drawn up front: they depend on nothing), and the
+// Cholesky factor of the current equation, double-buffered so that the factor of equation j + 1 streams in
+// (cp.async) while equation j is solved.  Per equation only the solve (one warp) and the k-j-1 products
+// S_i delta (all warps, S_i from L2) remain on the critical path.
+constexpr int SEQ_THREADS = 256;
+template <bool SV>
+__host__ __device__ inline size_t coef_seq_smem_doubles(int k, int d, int ppad) {
+  return 2 * (size_t)ppad + 3 * (size_t)k * d + (size_t)k * k + 4 * (size_t)d + (size_t)(SEQ_THREADS / 32) * d + (size_t)k + 8;
+}
+
 template <bool SV, int NC>
-__global__ void __launch_bounds__(256) coef_seq_kernel(const Dims D, const DevPtrs P, const double* __restrict__ Pfac) {
+__global__ void __launch_bounds__(SEQ_THREADS) coef_seq_kernel(const Dims D, const DevPtrs P, const double* __restrict__ Pfac) {
   extern __shared__ __align__(16) double sm[];
   const int u = blockIdx.x, w = u / D.C, c = u % D.C;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
-  const int k = D.k, d = D.d, Pp = D.Pp, ldM = D.ldM;
-  double* Lc = sm;                          // factor of the current equation
-  double* g = Lc + ((Pp + 1) & ~1);         // [k][d]
-  double* Lsm = g + (size_t)k * d;          // [k][k]
+  const int k = D.k, d = D.d, ldM = D.ldM;
+  const int ppad = D.ldS;                   // even pitch of a packed factor (16-byte chunks)
+  double* Lc = sm;                          // [2][ppad] factor of the current / next equation
+  double* h = Lc + 2 * (size_t)ppad;        // [k][d]  C_i - S_i v_i
+  double* Asm = h + (size_t)k * d;          // [k][d]  coefficient matrix, equation-major
+  double* zall = Asm + (size_t)k * d;       // [k][d]  this sweep's normals
+  double* Lsm = zall + (size_t)k * d;       // [k][k]
   double* rv = Lsm + k * k;                 // [d]
-  double* zv = rv + d;
-  double* dl = zv + d;                      // delta
+  double* dl = rv + d;                      // delta
   double* tv = dl + d;                      // LDLT: X'X delta
-  double* wscr = tv + d;                    // [nw][d] per-warp vectors
+  double* wscr = tv + 2 * d;                // [nw][d] per-warp vectors
+  double* idg = wscr + (size_t)nw * d;      // [k] 1 / diag (LDLT)
   const Philox rng(P.seeds[u], (uint32_t)(D.ubase + u), *P.iter);
   double* Ac = P.Acoef + (size_t)w * d * ldM + (size_t)c * k;
   const double* prec_u = P.prec + (size_t)u * k * d;
   const double* xn = P.xnorm + (size_t)w * d;
   const double* X2 = SV ? nullptr : P.XtX + (size_t)w * D.ldS;
 
+  auto prefetch_factor = [&](int j) {
+    const double* Lg = Pfac + ((size_t)u * k + j) * D.ldS;
+    double* dst = Lc + (size_t)(j & 1) * ppad;
+    for (int p = 2 * tid; p < ppad; p += 2 * SEQ_THREADS) cp_async16(dst + p, Lg + p, 16);
+    cp_async_commit();
+  };
+  prefetch_factor(0);
+
   for (int e = tid; e < k * k; e += blockDim.x) Lsm[e] = P.L[(size_t)u * k * k + e];
+  for (int e = tid; e < d * k; e += blockDim.x) {
+    const int a = e / k, m = e - a * k;
+    Asm[m * d + a] = Ac[(size_t)a * ldM + m];
+  }
+  for (int e = tid; e < (k * d + 1) / 2; e += blockDim.x) {  // ST_COEF_Z element j*d + a, pairs (2e, 2e+1)
+    double z0, z1;
+    rng.normal_pair(ST_COEF_Z, (uint32_t)e, 0, z0, z1);
+    zall[2 * e] = z0;
+    if (2 * e + 1 < k * d) zall[2 * e + 1] = z1;
+  }
+  if (!SV) for (int i = tid; i < k; i += blockDim.x) idg[i] = 1.0 / P.diag[(size_t)u * k + i];
   __syncthreads();
-  // g_i = S_i v_i, v_i = A L_i'
+  // h_i = C_i - S_i v_i, v_i = A L_i'
   for (int i = warp; i < k; i += nw) {
     double* v = wscr + (size_t)warp * d;
     for (int a = lane; a < d; a += 32) {
-      double s = 0.0;
-      for (int m = 0; m <= i; ++m) s = fma(Lsm[i * k + m], Ac[(size_t)a * ldM + m], s);
-      v[a] = s;
+      double sacc = 0.0;
+      for (int m = 0; m <= i; ++m) sacc = fma(Lsm[i * k + m], Asm[m * d + a], sacc);
+      v[a] = sacc;
     }
     __syncwarp();
     double out[NC];
     symv_packed_warp<NC>(SV ? P.S + ((size_t)u * k + i) * D.ldS : X2, v, d, out);
-    const double sc = SV ? 1.0 : 1.0 / P.diag[(size_t)u * k + i];
 #pragma unroll
-    for (int s = 0; s < NC; ++s) {
-      const int b = lane + 32 * s;
-      if (b < d) g[(size_t)i * d + b] = out[s] * sc;
+    for (int sidx = 0; sidx < NC; ++sidx) {
+      const int b = lane + 32 * sidx;
+      if (b < d) {
+        if (SV) {
+          h[(size_t)i * d + b] = P.Cm[((size_t)u * k + i) * D.ldX + b] - out[sidx];
+        } else {
+          const double* xty = P.XtY + ((size_t)w * d + b) * k;
+          double sacc = 0.0;
+          for (int m = 0; m <= i; ++m) sacc = fma(xty[m], Lsm[i * k + m], sacc);
+          h[(size_t)i * d + b] = (sacc - out[sidx]) * idg[i];
+        }
+      }
     }
     __syncwarp();
   }
-  __syncthreads();
 
   for (int j = 0; j < k; ++j) {
-    const double* Lg = Pfac + ((size_t)u * k + j) * D.ldS;
-    for (int p = tid; p < Pp; p += blockDim.x) Lc[p] = Lg[p];
+    cp_async_wait<0>();
+    __syncthreads();  // factor j landed; h, Asm of the previous equation are final
+    if (j + 1 < k) prefetch_factor(j + 1);
+    const double* Lj = Lc + (size_t)(j & 1) * ppad;
     for (int a = tid; a < d; a += blockDim.x) {
-      const double aold = Ac[(size_t)a * ldM + j];
-      double acc = prec_u[j * d + a] * (P.prior_mean[j * d + a] - aold);
-      if (SV) {
-        for (int i = j; i < k; ++i) acc = fma(Lsm[i * k + j], P.Cm[((size_t)u * k + i) * D.ldX + a] - g[(size_t)i * d + a], acc);
-      } else {
-        const double* xty = P.XtY + ((size_t)w * d + a) * k;
-        for (int i = j; i < k; ++i) {
-          double s = 0.0;
-          for (int m = 0; m <= i; ++m) s = fma(xty[m], Lsm[i * k + m], s);
-          acc = fma(Lsm[i * k + j], s / P.diag[(size_t)u * k + i] - g[(size_t)i * d + a], acc);
-        }
-      }
+      double acc = prec_u[j * d + a] * (P.prior_mean[j * d + a] - Asm[j * d + a]);
+      for (int i = j; i < k; ++i) acc = fma(Lsm[i * k + j], h[(size_t)i * d + a], acc);
       rv[a] = acc;
-      zv[a] = rng.normal_elem(ST_COEF_Z, (uint32_t)(j * d + a));
     }
     __syncthreads();
-    if (warp == 0) precision_solve_lanes<NC>(Lc, d, rv, zv, dl);
+    if (warp == 0) precision_solve_blocked<NC>(Lj, d, rv, zall + (size_t)j * d, dl);
     __syncthreads();
     for (int a = tid; a < d; a += blockDim.x) {
-      const double val = Ac[(size_t)a * ldM + j] + dl[a];
+      const double val = Asm[j * d + a] + dl[a];
+      Asm[j * d + a] = val;
       Ac[(size_t)a * ldM + j] = val;
       double pen = 0.0;
       if (a < D.nrow) {
@@ -155,9 +188,9 @@ __global__ void __launch_bounds__(256) coef_seq_kernel(const Dims D, const DevPt
           symv_packed_warp<NC>(P.S + ((size_t)u * k + i) * D.ldS, dl, d, out);
           const double lij = Lsm[i * k + j];
 #pragma unroll
-          for (int s = 0; s < NC; ++s) {
-            const int b = lane + 32 * s;
-            if (b < d) g[(size_t)i * d + b] = fma(lij, out[s], g[(size_t)i * d + b]);
+          for (int sidx = 0; sidx < NC; ++sidx) {
+            const int b = lane + 32 * sidx;
+            if (b < d) h[(size_t)i * d + b] = fma(-lij, out[sidx], h[(size_t)i * d + b]);
           }
         }
       } else {
@@ -165,19 +198,18 @@ __global__ void __launch_bounds__(256) coef_seq_kernel(const Dims D, const DevPt
           double out[NC];
           symv_packed_warp<NC>(X2, dl, d, out);
 #pragma unroll
-          for (int s = 0; s < NC; ++s) {
-            const int b = lane + 32 * s;
-            if (b < d) tv[b] = out[s];
+          for (int sidx = 0; sidx < NC; ++sidx) {
+            const int b = lane + 32 * sidx;
+            if (b < d) tv[b] = out[sidx];
           }
         }
         __syncthreads();
         for (int e = tid; e < (k - j - 1) * d; e += blockDim.x) {
           const int i = j + 1 + e / d, a = e % d;
-          g[(size_t)i * d + a] = fma(Lsm[i * k + j] / P.diag[(size_t)u * k + i], tv[a], g[(size_t)i * d + a]);
+          h[(size_t)i * d + a] = fma(-Lsm[i * k + j] * idg[i], tv[a], h[(size_t)i * d + a]);
         }
       }
     }
-    __syncthreads();
   }
 }
 
@@ -200,10 +232,10 @@ cudaError_t launch_part(int part, const Dims& D, const DevPtrs& P, double* Pfac,
   } else if (part == 1) {
     return launch_coef_chol(NC, D, P, Pfac, smem_limit, st);
   } else {
-    const size_t sm3 = (ppad + (size_t)k * d + (size_t)k * k + 12 * (size_t)d) * sizeof(double);
+    const size_t sm3 = coef_seq_smem_doubles<SV>(k, d, D.ldS) * sizeof(double);
     if (sm3 > smem_limit) return cudaErrorInvalidConfiguration;
     cudaFuncSetAttribute(coef_seq_kernel<SV, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm3);
-    coef_seq_kernel<SV, NC><<<D.U, 256, sm3, st>>>(D, P, Pfac);
+    coef_seq_kernel<SV, NC><<<D.U, SEQ_THREADS, sm3, st>>>(D, P, Pfac);
   }
   return cudaGetLastError();
 }
@@ -213,7 +245,7 @@ cudaError_t launch_part(int part, const Dims& D, const DevPtrs& P, double* Pfac,
 bool coef_v2_fits(const Dims& D, size_t smem_limit) {
   if (D.d > 256) return false;
   const size_t ppad = (D.Pp + 1) & ~1;
-  const size_t sm3 = (ppad + (size_t)D.k * D.d + (size_t)D.k * D.k + 12 * (size_t)D.d) * sizeof(double);
+  const size_t sm3 = coef_seq_smem_doubles<true>(D.k, D.d, D.ldS) * sizeof(double);
   return sm3 <= smem_limit && ppad * sizeof(double) <= smem_limit;
 }
 

@@ -111,8 +111,13 @@ __device__ __forceinline__ void chol_blocked_warp(double* Pk, int d, int* bad) {
 
 // out (lane-distributed: element b = lane + 32 c in out[c]) = S x, S packed lower (row-major packed) in
 // global memory, x in shared memory.  NC = ceil(d / 32).
+// Rows are taken in blocks of 32.  Within a block, lane b accumulates the row partials S_ab x_b in registers
+// (part[r], static indices) and its own column contribution S_ab x_a, with the loads of 8 rows in flight at
+// a time; ONE butterfly reduce-scatter per block (31 shuffles for 32 rows instead of 5 per row) then leaves
+// the total of row 32 rb + l on lane l.
 template <int NC>
 __device__ __forceinline__ void symv_packed_warp(const double* __restrict__ S, const double* x, int d, double (&out)[NC]) {
+  const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   double xb[NC];
 #pragma unroll
@@ -121,36 +126,50 @@ __device__ __forceinline__ void symv_packed_warp(const double* __restrict__ S, c
     xb[c] = b < d ? x[b] : 0.0;
     out[c] = 0.0;
   }
-  constexpr int UR = 4;
-  for (int a0 = 0; a0 < d; a0 += UR) {
-    double s[UR][NC];
 #pragma unroll
-    for (int r = 0; r < UR; ++r) {
-      const int a = a0 + r;
-      const int ra = a * (a + 1) / 2;
+  for (int rb = 0; rb < NC; ++rb) {
+    if (32 * rb >= d) break;
+    double part[32];
+    constexpr int RB = 8;
 #pragma unroll
-      for (int c = 0; c < NC; ++c) {
-        const int b = lane + 32 * c;
-        s[r][c] = (a < d && b <= a) ? S[ra + b] : 0.0;
+    for (int r0 = 0; r0 < 32; r0 += RB) {
+      double s[RB][NC];
+#pragma unroll
+      for (int r = 0; r < RB; ++r) {
+        const int a = 32 * rb + r0 + r;
+        const int ra = a * (a + 1) / 2;
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+          const int b = lane + 32 * c;
+          s[r][c] = (c <= rb && a < d && b <= a) ? S[ra + b] : 0.0;
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < RB; ++r) {
+        const int a = 32 * rb + r0 + r;
+        const double xa = a < d ? x[a] : 0.0;
+        double p = 0.0;
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+          if (c > rb) continue;
+          const int b = lane + 32 * c;
+          p = fma(s[r][c], xb[c], p);
+          out[c] = fma(s[r][c], b < a ? xa : 0.0, out[c]);
+        }
+        part[r0 + r] = p;
       }
     }
 #pragma unroll
-    for (int r = 0; r < UR; ++r) {
-      const int a = a0 + r;
-      if (a >= d) break;
-      const double xa = x[a];
-      double part = 0.0;
+    for (int off = 16; off >= 1; off >>= 1) {
+      const bool up = (lane & off) != 0;
 #pragma unroll
-      for (int c = 0; c < NC; ++c) {
-        const int b = lane + 32 * c;
-        part = fma(s[r][c], xb[c], part);
-        if (b < a) out[c] = fma(s[r][c], xa, out[c]);
+      for (int i = 0; i < off; ++i) {
+        const double send = up ? part[i] : part[i + off];
+        const double keep = up ? part[i + off] : part[i];
+        part[i] = keep + __shfl_xor_sync(FULL, send, off);
       }
-      part = wsum(part);
-#pragma unroll
-      for (int c = 0; c < NC; ++c)
-        if ((a >> 5) == c && (a & 31) == lane) out[c] += part;
     }
+    out[rb] += part[0];
   }
 }
 
@@ -257,6 +276,88 @@ __device__ __forceinline__ void precision_solve_lanes(const double* Lp, int d, c
   }
 }
 
+
+// delta = L^-T (L^-1 r + z) by one warp with the 32 x 32 diagonal blocks of L held in REGISTERS (lane = row
+// for the forward solve, lane = column for the backward solve), rows pre-scaled by 1 / L_aa so that the
+// dependent chain of each of the 2 d substitution steps is one shuffle + one FMA; the off-diagonal block
+// updates are independent dot products.  `out` (shared memory, d doubles) doubles as the broadcast buffer.
+template <int NC>
+__device__ __forceinline__ void precision_solve_blocked(const double* Lp, int d, const double* r, const double* z, double* out) {
+  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  double y[NC], inv[NC];
+#pragma unroll
+  for (int s = 0; s < NC; ++s) {
+    const int a = lane + 32 * s;
+    inv[s] = a < d ? 1.0 / Lp[a * (a + 1) / 2 + a] : 0.0;
+    y[s] = a < d ? r[a] * inv[s] : 0.0;  // scaled unknowns: y_a / L_aa
+  }
+  // ---- forward: L y = r
+#pragma unroll
+  for (int jb = 0; jb < NC; ++jb) {
+    if (32 * jb >= d) break;
+    const int a = 32 * jb + lane;
+    const int ra = a * (a + 1) / 2 + 32 * jb;
+    double dg[32];
+#pragma unroll
+    for (int c = 0; c < 32; ++c) dg[c] = (a < d && c < lane) ? Lp[ra + c] * inv[jb] : 0.0;
+#pragma unroll
+    for (int c = 0; c < 32; ++c) {
+      const double yc = __shfl_sync(FULL, y[jb], c);
+      y[jb] = fma(-dg[c], yc, y[jb]);  // dg[c] = 0 for lanes <= c: solved entries stay put
+    }
+    if (a < d) out[a] = y[jb];
+    __syncwarp();
+#pragma unroll
+    for (int ib = jb + 1; ib < NC; ++ib) {
+      const int a2 = 32 * ib + lane;
+      if (a2 < d) {
+        const double* row = Lp + a2 * (a2 + 1) / 2 + 32 * jb;
+        double acc = 0.0;
+#pragma unroll 8
+        for (int c = 0; c < 32; ++c) acc = fma(row[c], out[32 * jb + c], acc);
+        y[ib] = fma(-acc, inv[ib], y[ib]);
+      }
+    }
+    __syncwarp();
+  }
+  // ---- backward: L' x = y + z.  y holds (L^-1 r)_a exactly; pre-scale the right-hand side by 1 / L_cc
+#pragma unroll
+  for (int s = 0; s < NC; ++s) {
+    const int a = lane + 32 * s;
+    y[s] = a < d ? (y[s] + z[a]) * inv[s] : 0.0;
+  }
+#pragma unroll
+  for (int jb = NC - 1; jb >= 0; --jb) {
+    if (32 * jb >= d) continue;
+    const int b = 32 * jb + lane;
+    double dgT[32];
+#pragma unroll
+    for (int c = 0; c < 32; ++c) {
+      const int a = 32 * jb + c;
+      dgT[c] = (a < d && c > lane) ? Lp[a * (a + 1) / 2 + b] * inv[jb] : 0.0;
+    }
+#pragma unroll
+    for (int c = 31; c >= 0; --c) {
+      const double xc = __shfl_sync(FULL, y[jb], c);
+      y[jb] = fma(-dgT[c], xc, y[jb]);
+    }
+    if (b < d) out[b] = y[jb];
+    __syncwarp();
+#pragma unroll
+    for (int ib = 0; ib < jb; ++ib) {
+      const int b2 = 32 * ib + lane;  // always < d here
+      double acc = 0.0;
+#pragma unroll 8
+      for (int c = 0; c < 32; ++c) {
+        const int a = 32 * jb + c;
+        if (a < d) acc = fma(Lp[a * (a + 1) / 2 + b2], out[a], acc);
+      }
+      y[ib] = fma(-acc, inv[ib], y[ib]);
+    }
+    __syncwarp();
+  }
+}
 
 #undef wsum
 }  // namespace bvhar

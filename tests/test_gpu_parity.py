@@ -107,7 +107,10 @@ def _stage_check(prior, sv, **kw):
                 for w in range(pk.n_windows):
                     for c in range(pk.n_chains):
                         e = relerr(o.get_state(nm, w, c), g.get_state(nm, w, c))
-                        assert e < STAGE_TOL, f"{prior} sv={sv} sweep {it} stage {st} {nm}[w{w} c{c}]: rel err {e:.3e}"
+                        # sweep 1 starts from identical states: strict 1e-10.  The states are not re-synchronised, so by
+                        # sweep 2 each stage also inherits the rounding differences of the stages before it: 1e-9.
+                        tol = STAGE_TOL if it == 1 else 10 * STAGE_TOL
+                        assert e < tol, f"{prior} sv={sv} sweep {it} stage {st} {nm}[w{w} c{c}]: rel err {e:.3e}"
                         worst = max(worst, e)
     o.close(); g.close()
     return worst
