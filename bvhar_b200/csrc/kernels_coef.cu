@@ -25,32 +25,52 @@ namespace bvhar {
 namespace {
 
 // ---- A1: P_j = sum_{i>=j} L_ij^2 S_i, all j, one pass over the unit's S ----------------------
-template <int KMAX>
+// Per unit this is a [k x k] x [k x Pp] product (upper-triangular weights W_ji = L_ij^2): DMMA m8n8k4 with the
+// weights held in registers as A fragments for the whole kernel and the B fragments S_i[p] loaded straight
+// from global memory (each S element is read exactly once, each P element written once: HBM-bound).
+// MT = ceil(k / 8) row tiles (j), KS = ceil(k / 4) k-steps (i).
+template <int MT, int KS>
 __global__ void __launch_bounds__(256) coef_pbuild_kernel(const Dims D, const DevPtrs P, double* __restrict__ Pfac) {
-  extern __shared__ __align__(16) double sm[];
   const int u = blockIdx.x, k = D.k;
-  double* Lsq = sm;  // [i][j], i >= j
-  for (int e = threadIdx.x; e < k * k; e += blockDim.x) {
-    const double l = P.L[(size_t)u * k * k + e];
-    Lsq[e] = l * l;
-  }
-  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int fr = lane >> 2, fc = lane & 3;
+  const double* Lu = P.L + (size_t)u * k * k;
+  double af[MT][KS];  // A[m = j][kk = i] = L_ij^2 for i >= j
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+      const int j = 8 * mt + fr, i = 4 * ks + fc;
+      const double l = (i < k && j <= i) ? Lu[i * k + j] : 0.0;
+      af[mt][ks] = l * l;
+    }
   const double* Su = P.S + (size_t)u * k * D.ldS;
   double* Pu = Pfac + (size_t)u * k * D.ldS;
-  for (int p = threadIdx.x; p < D.Pp; p += blockDim.x) {
-    double acc[KMAX];
+  const int ntiles = (D.Pp + 7) / 8;
+  constexpr int NQ = 4;  // n-tiles per warp iteration (loads of all of them in flight together)
+  for (int nt0 = (blockIdx.y * 8 + warp) * NQ; nt0 < ntiles; nt0 += gridDim.y * 8 * NQ) {
+    double bf[NQ][KS];
 #pragma unroll
-    for (int j = 0; j < KMAX; ++j) acc[j] = 0.0;
-    for (int i = 0; i < k; ++i) {
-      const double s = Su[(size_t)i * D.ldS + p];
-      const double* lr = Lsq + i * k;
+    for (int q = 0; q < NQ; ++q)
 #pragma unroll
-      for (int j = 0; j < KMAX; ++j)
-        if (j <= i) acc[j] = fma(lr[j], s, acc[j]);
+      for (int ks = 0; ks < KS; ++ks) {
+        const int i = 4 * ks + fc, p = 8 * (nt0 + q) + fr;
+        bf[q][ks] = (i < k && p < D.Pp) ? Su[(size_t)i * D.ldS + p] : 0.0;
+      }
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+      const int p = 8 * (nt0 + q) + 2 * fc;
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) {
+        double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) dmma_m8n8k4(c0, c1, af[mt][ks], bf[q][ks]);
+        const int j = 8 * mt + fr;
+        if (j < k && p < D.Pp) {  // ldS is even and p is even: 16-byte aligned pair inside the padded row
+          *reinterpret_cast<double2*>(Pu + (size_t)j * D.ldS + p) = make_double2(c0, c1);
+        }
+      }
     }
-#pragma unroll
-    for (int j = 0; j < KMAX; ++j)
-      if (j < k) Pu[(size_t)j * D.ldS + p] = acc[j];
   }
 }
 // generic fallback for k > 64: one thread per (j, p), streaming i
@@ -219,16 +239,12 @@ cudaError_t launch_part(int part, const Dims& D, const DevPtrs& P, double* Pfac,
   const size_t ppad = (D.Pp + 1) & ~1;
   if (part == 0) {
     if (!SV) return cudaSuccess;
-    const size_t sm1 = (size_t)k * k * sizeof(double);
-    if (k <= 32) {
-      cudaFuncSetAttribute(coef_pbuild_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1);
-      coef_pbuild_kernel<32><<<D.U, 256, sm1, st>>>(D, P, Pfac);
-    } else if (k <= 64) {
-      cudaFuncSetAttribute(coef_pbuild_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1);
-      coef_pbuild_kernel<64><<<D.U, 256, sm1, st>>>(D, P, Pfac);
-    } else {
-      coef_pbuild_generic_kernel<<<D.U, 256, 0, st>>>(D, P, Pfac);
-    }
+    const dim3 grid(D.U, 4);
+    if (k <= 8) coef_pbuild_kernel<1, 2><<<grid, 256, 0, st>>>(D, P, Pfac);
+    else if (k <= 16) coef_pbuild_kernel<2, 4><<<grid, 256, 0, st>>>(D, P, Pfac);
+    else if (k <= 24) coef_pbuild_kernel<3, 6><<<grid, 256, 0, st>>>(D, P, Pfac);
+    else if (k <= 32) coef_pbuild_kernel<4, 8><<<grid, 256, 0, st>>>(D, P, Pfac);
+    else coef_pbuild_generic_kernel<<<D.U, 256, 0, st>>>(D, P, Pfac);
   } else if (part == 1) {
     return launch_coef_chol(NC, D, P, Pfac, smem_limit, st);
   } else {

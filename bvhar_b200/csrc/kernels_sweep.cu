@@ -25,7 +25,7 @@ namespace bvhar {
 // response rows of the chunk are staged in shared memory.
 constexpr int SVP_TT = 16;  // time points per block
 template <int KMAX>
-__global__ void __launch_bounds__(256) sv_prep_kernel(const Dims D, const DevPtrs P) {
+__global__ void __launch_bounds__(256, (KMAX <= 32 ? 2 : 1)) sv_prep_kernel(const Dims D, const DevPtrs P) {
   extern __shared__ __align__(16) double sm[];
   const int w = blockIdx.z;
   const int n = P.win_n[w], row0 = P.win_row0[w];
@@ -250,7 +250,7 @@ __constant__ double c_ksc_v[7] = {5.79596, 2.61369, 5.17950, 0.16735, 0.64009, 0
 __constant__ double c_ksc_mm[7] = {-10.12999 - 1.2704, -3.97281 - 1.2704, -8.56686 - 1.2704, 2.77786 - 1.2704,
                                    0.61942 - 1.2704, 1.79518 - 1.2704, -1.08819 - 1.2704};
 template <int KMAX>
-__global__ void __launch_bounds__(256) sv_mix_kernel(const Dims D, const DevPtrs P) {
+__global__ void __launch_bounds__(256, (KMAX <= 32 ? 2 : 1)) sv_mix_kernel(const Dims D, const DevPtrs P) {
   extern __shared__ __align__(16) double sm[];  // [SVP_TT][blockDim.x span of Z columns]
   __shared__ double s_h2v[7], s_lw[7], s_iv[7];
   const int w = blockIdx.z;
@@ -325,10 +325,14 @@ __global__ void __launch_bounds__(256) sv_mix_kernel(const Dims D, const DevPtrs
   }
 }
 
-// h_i ~ N(K^-1 b, K^-1) with the tridiagonal K = H'H / sig + diag(1/v_s) (draw.h:469-487): one thread
-// per series runs the bidiagonal Cholesky forward (storing 1 / l_t), then the combined mean + noise
-// back substitution.  Loads are issued SVS_B time points ahead of the dependent chain (they would
-// otherwise serialise behind the stores to the same arrays); accesses are [t][m], coalesced.
+// h_i ~ N(K^-1 b, K^-1) with the tridiagonal K = H'H / sig + diag(1/v_s) (draw.h:469-487): one thread per
+// series runs the bidiagonal Cholesky forward, then the combined mean + noise back substitution; accesses are
+// [t][m], coalesced.  The three recurrences are rewritten so that each step of the dependent chain is ONE FMA:
+//   pivots   q_t = diag_t - isig^2 / q_{t-1}  as the ratio N_t / D_t of the linear recurrence
+//            N_t = diag_t N_{t-1} - isig^2 D_{t-1},  D_t = N_{t-1}   (re-normalised every SVS_B steps);
+//            the divisions and w_t = 1 / sqrt(q_t) are then independent per t and pipeline freely;
+//   forward  y_t = alpha_t + beta_t y_{t-1},   alpha_t = b_t w_t,  beta_t = isig w_{t-1} w_t;
+//   backward x_t = gamma_t + delta_t x_{t+1},  gamma_t = (y_t + z_t) w_t,  delta_t = isig w_t^2.
 constexpr int SVS_B = 8;
 __global__ void __launch_bounds__(128) sv_solve_kernel(const Dims D, const DevPtrs P) {
   const int w = blockIdx.y;
@@ -339,59 +343,104 @@ __global__ void __launch_bounds__(128) sv_solve_kernel(const Dims D, const DevPt
   const int c = m / D.k, i = m % D.k;
   const int u = w * D.C + c;
   const double isig = 1.0 / P.lvol_sig[(size_t)u * D.k + i];
+  const double isig2 = isig * isig;
   const double h0 = P.lvol_init[(size_t)u * D.k + i];
   const Philox rng(P.seeds[u], (uint32_t)(D.ubase + u), *P.iter);
   const uint32_t nh = (uint32_t)((n + 1) / 2);
-  double wprev = 0.0, yprev = 0.0;  // w = 1 / l
+  double Nc = 1.0, Dc = 0.0;     // q_{-1} "= infinity": the first pivot has no sub-diagonal term
+  double wprev = 0.0, yprev = 0.0;
+  double dgn[SVS_B], bbn[SVS_B];  // the NEXT block's inputs: loaded before this block's stores are issued
+#pragma unroll
+  for (int r = 0; r < SVS_B; ++r) {
+    const long long at = off + (long long)r * D.ldM;
+    dgn[r] = r < n ? P.Dinv[at] : 1.0;
+    bbn[r] = r < n ? P.YLD[at] : 0.0;
+  }
   for (int t0 = 0; t0 < n; t0 += SVS_B) {
-    double dg[SVS_B], bb[SVS_B];
+    double dg[SVS_B], bb[SVS_B], Nr[SVS_B], Dr[SVS_B];
 #pragma unroll
     for (int r = 0; r < SVS_B; ++r) {
-      const int t = t0 + r;
-      const long long at = off + (long long)t * D.ldM;
-      dg[r] = t < n ? P.Dinv[at] : 1.0;
-      bb[r] = t < n ? P.YLD[at] : 0.0;
+      dg[r] = dgn[r];
+      bb[r] = bbn[r];
     }
+#pragma unroll
+    for (int r = 0; r < SVS_B; ++r) {
+      const int t = t0 + SVS_B + r;
+      const long long at = off + (long long)t * D.ldM;
+      dgn[r] = t < n ? P.Dinv[at] : 1.0;
+      bbn[r] = t < n ? P.YLD[at] : 0.0;
+    }
+#pragma unroll
+    for (int r = 0; r < SVS_B; ++r) {  // chain: one FMA per step
+      const int t = t0 + r;
+      const double diag = (t < n - 1 ? 2.0 : 1.0) * isig + dg[r];
+      const double Nn = fma(diag, Nc, -isig2 * Dc);
+      Dc = Nc;
+      Nc = Nn;
+      Nr[r] = Nn;
+      Dr[r] = Dc;
+    }
+    double wv[SVS_B];
+#pragma unroll
+    for (int r = 0; r < SVS_B; ++r) wv[r] = 1.0 / sqrt(Nr[r] / Dr[r]);  // independent: pipelined
+    Nc = Nr[SVS_B - 1] / Dr[SVS_B - 1];  // re-normalise (q itself) for the next block
+    Dc = 1.0;
 #pragma unroll
     for (int r = 0; r < SVS_B; ++r) {
       const int t = t0 + r;
       if (t < n) {
-        const double e = -isig * wprev;  // e_t = -isig / l_{t-1}; wprev = 0 at t = 0
-        const double q = fma(-e, e, (t < n - 1 ? 2.0 : 1.0) * isig + dg[r]);
-        const double wv = 1.0 / sqrt(q);
         const double b = (t == 0 ? h0 * isig : 0.0) + bb[r];
-        const double y = (b - e * yprev) * wv;
+        const double beta = isig * wprev * wv[r];
+        const double y = fma(beta, yprev, b * wv[r]);
         const long long at = off + (long long)t * D.ldM;
-        P.Dinv[at] = wv;
+        P.Dinv[at] = wv[r];
         P.YLD[at] = y;
-        wprev = wv;
+        wprev = wv[r];
         yprev = y;
       }
     }
   }
   double next = 0.0;
   const int nb = (n + SVS_B - 1) / SVS_B;
+  double wvn[SVS_B], yvn[SVS_B];
+#pragma unroll
+  for (int r = 0; r < SVS_B; ++r) {
+    const int t = (nb - 1) * SVS_B + r;
+    const long long at = off + (long long)t * D.ldM;
+    wvn[r] = t < n ? P.Dinv[at] : 0.0;
+    yvn[r] = t < n ? P.YLD[at] : 0.0;
+  }
   for (int blk = nb - 1; blk >= 0; --blk) {
     const int t0 = blk * SVS_B;  // SVS_B is even, so Philox pairs (t even, t odd) never straddle blocks
-    double wv[SVS_B], yv[SVS_B], zv[SVS_B];
+    double wv[SVS_B], yv[SVS_B], zv[SVS_B] = {};
 #pragma unroll
     for (int r = 0; r < SVS_B; ++r) {
-      const int t = t0 + r;
-      const long long at = off + (long long)t * D.ldM;
-      wv[r] = t < n ? P.Dinv[at] : 0.0;
-      yv[r] = t < n ? P.YLD[at] : 0.0;
+      wv[r] = wvn[r];
+      yv[r] = yvn[r];
+    }
+    if (blk > 0) {
+#pragma unroll
+      for (int r = 0; r < SVS_B; ++r) {  // blocks below the last are full
+        const long long at = off + (long long)(t0 - SVS_B + r) * D.ldM;
+        wvn[r] = P.Dinv[at];
+        yvn[r] = P.YLD[at];
+      }
     }
 #pragma unroll
     for (int r = 0; r < SVS_B; r += 2) {
       if (t0 + r < n) rng.normal_pair(ST_SV_H_Z, (uint32_t)i * nh + ((uint32_t)(t0 + r) >> 1), 0, zv[r], zv[r + 1]);
     }
+    double gam[SVS_B], del[SVS_B];
+#pragma unroll
+    for (int r = 0; r < SVS_B; ++r) {
+      gam[r] = (yv[r] + zv[r]) * wv[r];
+      del[r] = (t0 + r < n - 1) ? isig * wv[r] * wv[r] : 0.0;
+    }
 #pragma unroll
     for (int r = SVS_B - 1; r >= 0; --r) {
       const int t = t0 + r;
       if (t < n) {
-        double v = yv[r] + zv[r];
-        if (t < n - 1) v = fma(isig * wv[r], next, v);  // - e_{t+1} next, e_{t+1} = -isig / l_t
-        next = v * wv[r];
+        next = fma(del[r], next, gam[r]);
         P.H[off + (long long)t * D.ldM] = next;
       }
     }
@@ -554,7 +603,10 @@ cudaError_t launch_draw_coef_batched(long long batch, int d, const double* Pp, c
 cudaError_t launch_sv_prep(const Dims& D, const DevPtrs& P, cudaStream_t st) {
   const dim3 grid((D.M + 255) / 256, (D.nmax + SVP_TT - 1) / SVP_TT, D.W);
   const size_t smem = (size_t)SVP_TT * D.k * sizeof(double);
-  if (D.k <= 32) sv_prep_kernel<32><<<grid, 256, smem, st>>>(D, P);
+  if (D.k <= 8) sv_prep_kernel<8><<<grid, 256, smem, st>>>(D, P);
+  else if (D.k <= 16) sv_prep_kernel<16><<<grid, 256, smem, st>>>(D, P);
+  else if (D.k <= 24) sv_prep_kernel<24><<<grid, 256, smem, st>>>(D, P);
+  else if (D.k <= 32) sv_prep_kernel<32><<<grid, 256, smem, st>>>(D, P);
   else if (D.k <= 64) sv_prep_kernel<64><<<grid, 256, smem, st>>>(D, P);
   else sv_prep_kernel<128><<<grid, 256, smem, st>>>(D, P);
   return cudaGetLastError();
@@ -563,9 +615,14 @@ cudaError_t launch_sv_state(int part, const Dims& D, const DevPtrs& P, cudaStrea
   if (part == 0) {
     const dim3 grid((D.M + 255) / 256, (D.nmax + SVP_TT - 1) / SVP_TT, D.W);
     const size_t smem = (size_t)SVP_TT * (256 + 2 * D.k) * sizeof(double);
-    if (D.k <= 32) sv_mix_kernel<32><<<grid, 256, smem, st>>>(D, P);
-    else if (D.k <= 64) sv_mix_kernel<64><<<grid, 256, smem, st>>>(D, P);
-    else {
+    if (D.k <= 8) sv_mix_kernel<8><<<grid, 256, smem, st>>>(D, P);
+    else if (D.k <= 16) sv_mix_kernel<16><<<grid, 256, smem, st>>>(D, P);
+    else if (D.k <= 24) sv_mix_kernel<24><<<grid, 256, smem, st>>>(D, P);
+    else if (D.k <= 32) sv_mix_kernel<32><<<grid, 256, smem, st>>>(D, P);
+    else if (D.k <= 64) {
+      cudaFuncSetAttribute(sv_mix_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      sv_mix_kernel<64><<<grid, 256, smem, st>>>(D, P);
+    } else {
       cudaFuncSetAttribute(sv_mix_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       sv_mix_kernel<128><<<grid, 256, smem, st>>>(D, P);
     }
