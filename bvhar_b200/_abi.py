@@ -314,6 +314,8 @@ def load_library():
     L.bvhar_cuda_abi_version.restype = C.c_int
     L.bvhar_cuda_device_count.argtypes = [C.POINTER(C.c_int)]
     L.bvhar_cuda_struct_sizes.argtypes = [C.POINTER(C.c_int64)] * 4
+    L.bvhar_cuda_host_alloc.argtypes = [C.c_int64, C.POINTER(vp)]
+    L.bvhar_cuda_host_free.argtypes = [vp]
     L.bvhar_cuda_fit_create.argtypes = [C.POINTER(FitDesc), C.POINTER(vp)]
     L.bvhar_cuda_fit_run.argtypes = [vp, PROGRESS_FN, vp]
     L.bvhar_cuda_fit_step.argtypes = [vp, C.c_int, C.c_int]

@@ -113,12 +113,18 @@ class CudaFit:
         check(self.L.bvhar_cuda_fit_record(self._h, window, chain, name.encode(), out.ctypes.data_as(c_dp), r.value, c.value))
         return out
 
-    def record_all(self, name: str) -> np.ndarray:
-        """ndarray[unit, draw, column] of one record for every unit (one bulk device-to-host copy)."""
+    def record_all(self, name: str, pinned: bool = True) -> np.ndarray:
+        """ndarray[unit, draw, column] of one record for every unit (one bulk device-to-host copy, into pooled
+        page-locked memory for large records)."""
         r, c = C.c_int64(), C.c_int64()
         check(self.L.bvhar_cuda_fit_record_dims(self._h, name.encode(), C.byref(r), C.byref(c)))
         U = self.packed.n_windows * self.packed.n_chains
-        out = np.empty((U, r.value, c.value))
+        shape = (U, r.value, c.value)
+        if pinned and U * r.value * c.value * 8 >= (8 << 20):
+            from . import _hostpool
+            out = _hostpool.empty(shape)
+        else:
+            out = np.empty(shape)
         check(self.L.bvhar_cuda_fit_record_all(self._h, name.encode(), out.ctypes.data_as(c_dp), U, r.value, c.value))
         return out
 

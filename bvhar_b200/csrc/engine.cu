@@ -6,6 +6,7 @@
 // captured once into a CUDA graph and replayed.  There is no CPU path: every entry point fails with
 // BVHAR_ERR_CUDA when no device is usable.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -14,6 +15,7 @@
 #include <memory>
 #include <set>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/bvhar_cuda.h"
@@ -37,6 +39,19 @@ int fail(int code, const std::string& msg) {
       return fail(BVHAR_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__));                  \
   } while (0)
 
+// Device buffers come from the device's default stream-ordered memory pool with an unlimited release
+// threshold: the GBs of state / record storage freed by one fit are handed straight to the next one instead of
+// going back to the driver (cudaFree + cudaMalloc of that much memory costs ~0.2 s per fit).
+inline void pool_setup(int device) {
+  static bool done[64] = {};
+  if (device < 0 || device >= 64 || done[device]) return;
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+    unsigned long long thr = ~0ULL;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+  }
+  done[device] = true;
+}
 template <typename T>
 struct DevBuf {
   T* p = nullptr;
@@ -44,17 +59,17 @@ struct DevBuf {
   cudaError_t alloc(size_t count) {
     n = count;
     if (count == 0) return cudaSuccess;
-    cudaError_t e = cudaMalloc(&p, count * sizeof(T));
-    if (e == cudaSuccess) e = cudaMemset(p, 0, count * sizeof(T));
+    cudaError_t e = cudaMallocAsync(&p, count * sizeof(T), 0);
+    if (e == cudaSuccess) e = cudaMemsetAsync(p, 0, count * sizeof(T), 0);
     return e;
   }
   cudaError_t upload(const std::vector<T>& h) {
     cudaError_t e = alloc(h.size());
     if (e != cudaSuccess || h.empty()) return e;
-    return cudaMemcpy(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice);
+    return cudaMemcpyAsync(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, 0);  // pageable source: staged before return
   }
   ~DevBuf() {
-    if (p) cudaFree(p);
+    if (p) cudaFreeAsync(p, 0);
   }
 };
 
@@ -127,6 +142,7 @@ struct bvhar_fit {
 
   ~bvhar_fit() {
     cudaSetDevice(device);
+    if (st) cudaStreamSynchronize(st);  // the buffers go back to the pool in stream order of stream 0
     for (auto& g : graph)
       if (g) cudaGraphExecDestroy(g);
     for (auto& pe : prof_pending) { cudaEventDestroy(pe.a); cudaEventDestroy(pe.b); }
@@ -248,10 +264,21 @@ int build(const bvhar_fit_desc* d, bvhar_fit** out) {
   if (!d->x || !d->y || !d->win_row0 || !d->win_nrow || !d->grp_mat || !d->grp_id || !d->init || !d->seed_chain || !d->sig_shape || !d->sig_scale)
     return fail(BVHAR_ERR_BAD_ARG, "missing required pointer in descriptor");
   CU(cudaSetDevice(d->device));
+  pool_setup(d->device);
   cudaDeviceProp prop;
   CU(cudaGetDeviceProperties(&prop, d->device));
   if (prop.major < 10) return fail(BVHAR_ERR_CUDA, "bvhar_b200 is built for sm_100a (B200) only");
 
+  const bool timing = getenv("BVHAR_TIMING") != nullptr;
+  auto now = [] { return std::chrono::steady_clock::now(); };
+  auto t_last = now();
+  auto lap = [&](const char* what) {
+    if (!timing) return;
+    cudaDeviceSynchronize();
+    auto t = now();
+    fprintf(stderr, "[bvhar_cuda_fit_create] %-28s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(t - t_last).count());
+    t_last = t;
+  };
   std::unique_ptr<bvhar_fit> F(new bvhar_fit);
   F->device = d->device;
   F->smem_limit = prop.sharedMemPerBlockOptin;
@@ -379,11 +406,16 @@ int build(const bvhar_fit_desc* d, bvhar_fit** out) {
   CU(F->seeds.upload(hseed));
   CU(F->iter.alloc(1)); CU(F->rec_row.alloc(1)); CU(F->flags.alloc(U));
 
+  lap("shared data + uploads");
   // ---- per-unit state from the chain inits (McmcTriangular ctor tri.h:40-71 and prior ctors) ----
   std::vector<double> hA((size_t)D.W * dd * D.ldM, 0.0), halpha((size_t)U * N), hc((size_t)U * k, 0.0), hprec((size_t)U * k * dd);
   std::vector<double> hcontem((size_t)U * q), hL((size_t)U * k * k, 0.0), hcp((size_t)U * q, 1.0);
   std::vector<double> hH, hli, hls, hdiag;
-  if (D.sv) { hH.assign((size_t)tm_total, 0.0); hli.resize((size_t)U * k); hls.resize((size_t)U * k); }
+  // SV: the n x k `lvol` blocks of the chains are staged series-major ([chain][series][t], a plain memcpy per
+  // chain) and transposed into the time-major layout on the device; replicated inits are k values per unit.
+  std::vector<double> hlv;     // [C][k][n0] when explicit lvol inits are given
+  bool lvol_explicit = false;
+  if (D.sv) { hli.resize((size_t)U * k); hls.resize((size_t)U * k); }
   else hdiag.resize((size_t)U * k);
   std::vector<double> hhN[4], hhG[3], hhq[4], hhs((size_t)U * HS_SLOTS, 0.0);
   for (auto& v : hhN) v.assign((size_t)U * N, 0.0);
@@ -411,12 +443,13 @@ int build(const bvhar_fit_desc* d, bvhar_fit** out) {
         if (!in.lvol_init || !in.lvol_sig) return fail(BVHAR_ERR_BAD_ARG, "lvol_init / lvol_sig missing");
         const bool rep = d->lvol_from_init || !in.lvol;
         if (!rep && F->win_n[w] != F->win_n[0]) return fail(BVHAR_ERR_BAD_ARG, "lvol inits need equal window lengths (use lvol_from_init)");
+        if (c > 0 && rep == lvol_explicit) return fail(BVHAR_ERR_BAD_ARG, "either every chain or no chain carries an explicit 'lvol' init");
+        lvol_explicit = !rep;
         for (int i = 0; i < k; ++i) {
           hli[(size_t)u * k + i] = in.lvol_init[i];
           hls[(size_t)u * k + i] = in.lvol_sig[i];
-          for (int t = 0; t < F->win_n[w]; ++t)
-            hH[(size_t)F->win_off[w] + (size_t)t * D.ldM + (size_t)c * k + i] = rep ? in.lvol_init[i] : in.lvol[(size_t)i * F->win_n[0] + t];
         }
+        // (the lvol blocks themselves are gathered below, in parallel)
       } else {
         if (!in.init_diag) return fail(BVHAR_ERR_BAD_ARG, "init_diag missing");
         for (int i = 0; i < k; ++i) hdiag[(size_t)u * k + i] = in.init_diag[i];
@@ -468,12 +501,37 @@ int build(const bvhar_fit_desc* d, bvhar_fit** out) {
         default: break;
       }
     }
+  lap("host init loops");
+  if (D.sv && lvol_explicit) {  // gather the chains' n x k lvol blocks into one staging buffer, a few host threads
+    const size_t blk = (size_t)k * F->win_n[0];
+    hlv.resize((size_t)D.C * blk);
+    const int nthr = std::max(1, std::min(8, D.C / 32));
+    std::vector<std::thread> pool;
+    for (int th = 0; th < nthr; ++th)
+      pool.emplace_back([&, th] {
+        for (int c = th; c < D.C; c += nthr) std::memcpy(hlv.data() + (size_t)c * blk, d->init[c].lvol, sizeof(double) * blk);
+      });
+    for (auto& t : pool) t.join();
+  }
   CU(F->Acoef.upload(hA)); CU(F->alpha.upload(halpha)); CU(F->cvec.upload(hc)); CU(F->prec.upload(hprec));
   CU(F->contem.upload(hcontem)); CU(F->L.upload(hL)); CU(F->chol_prec.upload(hcp));
   CU(F->sparse_coef.alloc((size_t)U * dd * k)); CU(F->sparse_contem.alloc((size_t)U * q)); CU(F->znorm.alloc((size_t)U * k));
   CU(F->Z.alloc((size_t)tm_total));
   if (D.sv) {
-    CU(F->H.upload(hH)); CU(F->lvol_init.upload(hli)); CU(F->lvol_sig.upload(hls));
+    CU(F->H.alloc((size_t)tm_total)); CU(F->lvol_init.upload(hli)); CU(F->lvol_sig.upload(hls));
+    {
+      DevBuf<double> stage;
+      const int n0 = F->win_n[0];
+      if (lvol_explicit) CU(stage.upload(hlv));
+      for (int w = 0; w < D.W; ++w) {
+        if (lvol_explicit) {  // every window starts from the chains' lvol blocks (forecaster.h:867-872)
+          CU(launch_scatter_lvol(stage.p, F->H.p + F->win_off[w], F->win_n[w], D.M, D.ldM, n0, 0));
+        } else {  // SvInits(init, num_design): lvol_init replicated over time (config.h:416-420) = rows of length 1
+          CU(launch_scatter_lvol(F->lvol_init.p + (size_t)w * D.M, F->H.p + F->win_off[w], F->win_n[w], D.M, D.ldM, 0, 0));
+        }
+      }
+      CU(cudaDeviceSynchronize());
+    }
     CU(F->Dinv.alloc((size_t)tm_total)); CU(F->YLD.alloc((size_t)tm_total));
     CU(F->S.alloc((size_t)U * k * D.ldS)); CU(F->Cm.alloc((size_t)U * k * D.ldX));
     CU(F->XX.alloc((size_t)D.T * D.ldXX));
@@ -485,6 +543,7 @@ int build(const bvhar_fit_desc* d, bvhar_fit** out) {
   for (int i = 0; i < 4; ++i) CU(F->hq[i].upload(hhq[i]));
   CU(F->hs.upload(hhs));
 
+  lap("state uploads + allocs");
   DevPtrs& P = F->P;
   P.X = F->X.p; P.XT = F->XT.p; P.Y = F->Y.p; P.XX = F->XX.p; P.xnorm = F->xnorm.p;
   P.win_row0 = F->d_row0.p; P.win_n = F->d_n.p; P.win_off = F->d_off.p;
@@ -503,6 +562,7 @@ int build(const bvhar_fit_desc* d, bvhar_fit** out) {
 
   CU(cudaStreamCreateWithFlags(&F->st, cudaStreamNonBlocking));
   CU(cudaEventCreate(&F->ev0)); CU(cudaEventCreate(&F->ev1));
+  CU(cudaDeviceSynchronize());  // uploads / memsets were ordered on stream 0; the setup kernels below run on F->st
 
   // ---- contraction descriptors ----
   std::vector<long long> g1b(D.W), g1c(D.W), g2b(D.W), g2c(D.W), g3a(D.W), g3b(D.W), g3y(D.W);
@@ -568,6 +628,7 @@ int build(const bvhar_fit_desc* d, bvhar_fit** out) {
   CU(launch_dgemm_tn(F->g3, F->st));
   CU(cudaStreamSynchronize(F->st));
 
+  lap("setup kernels");
   // ---- record buffers ----
   RecPtrs& R = F->R;
   std::memset(&R, 0, sizeof R);
@@ -606,6 +667,8 @@ int build(const bvhar_fit_desc* d, bvhar_fit** out) {
     }
   }
 #undef ADD
+  CU(cudaDeviceSynchronize());  // allocations / uploads were ordered on stream 0, the sweeps run on F->st
+  lap("record buffers");
   *out = F.release();
   return 0;
 }
@@ -811,6 +874,21 @@ int bvhar_cuda_struct_sizes(int64_t* fit_desc, int64_t* chain_init, int64_t* for
   if (chain_init) *chain_init = sizeof(bvhar_chain_init);
   if (forecast_desc) *forecast_desc = sizeof(bvhar_forecast_desc);
   if (prior_params) *prior_params = sizeof(bvhar_prior_params);
+  return 0;
+}
+
+int bvhar_cuda_host_alloc(int64_t bytes, void** out) {
+  if (!out || bytes < 0) return fail(BVHAR_ERR_BAD_ARG, "bad host_alloc arguments");
+  *out = nullptr;
+  if (bytes == 0) return 0;
+  cudaError_t e = cudaHostAlloc(out, (size_t)bytes, cudaHostAllocPortable);
+  if (e != cudaSuccess) { *out = nullptr; return fail(BVHAR_ERR_CUDA, std::string("cudaHostAlloc: ") + cudaGetErrorString(e)); }
+  return 0;
+}
+int bvhar_cuda_host_free(void* p) {
+  if (!p) return 0;
+  cudaError_t e = cudaFreeHost(p);
+  if (e != cudaSuccess) return fail(BVHAR_ERR_CUDA, std::string("cudaFreeHost: ") + cudaGetErrorString(e));
   return 0;
 }
 

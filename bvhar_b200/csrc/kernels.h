@@ -34,6 +34,7 @@ cudaError_t launch_bump(const DevPtrs& P, int bump_iter, int bump_rec, cudaStrea
 // prior hyper-parameter updaters (kernels_prior.cu): side 0 = updateCoefPrec, 1 = updateImpactPrec
 cudaError_t launch_prior(const Dims& D, const DevPtrs& P, const PriorConst& C, int side, cudaStream_t st);
 // setup helpers (kernels_setup.cu)
+cudaError_t launch_scatter_lvol(const double* src, double* dst, int n, int M, int ldM, int nsrc, cudaStream_t st);
 cudaError_t launch_build_xx(const Dims& D, const DevPtrs& P, double* XX, cudaStream_t st);
 // forecast (kernels_forecast.cu)
 struct ForecastArgs {

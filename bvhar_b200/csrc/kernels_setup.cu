@@ -28,6 +28,29 @@ cudaError_t launch_build_xx(const Dims& D, const DevPtrs& P, double* XX, cudaStr
   return cudaGetLastError();
 }
 
+// Per-chain log-volatility inits arrive as n x k column-major blocks ([chain][series][t], what `lvol` is in
+// param_init, config.h:410-415); the engine keeps them time-major across the window's units.  Tiled transpose.
+__global__ void __launch_bounds__(256) scatter_lvol_kernel(const double* __restrict__ src, double* __restrict__ dst, int n, int M,
+                                                           int ldM, int nsrc) {
+  __shared__ double tile[32][33];
+  const int m0 = blockIdx.x * 32, t0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  for (int r = ty; r < 32; r += 8) {
+    const int m = m0 + r, t = t0 + tx;
+    tile[r][tx] = (m < M && t < n) ? src[nsrc ? (size_t)m * nsrc + t : (size_t)m] : 0.0;  // nsrc == 0: one value per series
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int t = t0 + r, m = m0 + tx;
+    if (t < n && m < M) dst[(size_t)t * ldM + m] = tile[tx][r];
+  }
+}
+// src: [M = C*k][nsrc] (series-major rows of length nsrc >= n), dst: [n][ldM]
+cudaError_t launch_scatter_lvol(const double* src, double* dst, int n, int M, int ldM, int nsrc, cudaStream_t st) {
+  scatter_lvol_kernel<<<dim3((M + 31) / 32, (n + 31) / 32), 256, 0, st>>>(src, dst, n, M, ldM, nsrc);
+  return cudaGetLastError();
+}
+
 // Density forecast of one (unit, draw) per thread: McmcForecaster::forecastOut fc.h:162-190,
 // RegForecaster fc.h:206-222, SvForecaster fc.h:239-262, computeMean fc.h:300-302 / 338-340.
 // Philox key (seed_forecast[unit], unit), iteration = draw index, stages ST_FORECAST_H / _Y,

@@ -188,6 +188,11 @@ int bvhar_cuda_device_count(int* count);
 /* sizeof() of the descriptor structs as compiled, so that FFI mirrors can verify their layout. */
 int bvhar_cuda_struct_sizes(int64_t* fit_desc, int64_t* chain_init, int64_t* forecast_desc, int64_t* prior_params);
 
+/* Page-locked host buffers for record / forecast outputs (cudaHostAlloc): device-to-host copies into them run at
+ * PCIe speed instead of the pageable staging path.  Optional: every entry point accepts ordinary memory too. */
+int bvhar_cuda_host_alloc(int64_t bytes, void** out);
+int bvhar_cuda_host_free(void* p);
+
 int bvhar_cuda_fit_create(const bvhar_fit_desc* desc, bvhar_fit** out);
 /* Run num_burn warm-up sweeps and num_iter - num_burn recorded sweeps for every unit
  * (McmcRun::fit / runGibbs, triangular.h:1217-1284). */

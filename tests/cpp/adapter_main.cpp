@@ -1,0 +1,65 @@
+// Drives include/bvhar_b200/mcmc_run.hpp from a problem file written by tests/test_cpp_adapter.py and writes the
+// records back: the C++ host adapter is checked against the Python one on identical inputs.
+// File format (both ways): repeated { int32 name_len, name bytes, int64 rows, int64 cols, rows*cols doubles }.
+#include <cstdio>
+#include <cstring>
+#include <bvhar_b200/mcmc_run.hpp>
+
+using namespace bvhar_b200;
+
+static std::map<std::string, Matrix> read_all(const char* path) {
+  std::map<std::string, Matrix> out;
+  FILE* f = std::fopen(path, "rb");
+  if (!f) throw std::runtime_error("cannot open problem file");
+  int32_t nl;
+  while (std::fread(&nl, sizeof nl, 1, f) == 1) {
+    std::string name(nl, '\0');
+    int64_t r, c;
+    if (std::fread(&name[0], 1, nl, f) != (size_t)nl || std::fread(&r, sizeof r, 1, f) != 1 || std::fread(&c, sizeof c, 1, f) != 1)
+      throw std::runtime_error("truncated problem file");
+    Matrix m(r, c);
+    if (r * c && std::fread(m.data.data(), sizeof(double), (size_t)(r * c), f) != (size_t)(r * c)) throw std::runtime_error("truncated");
+    out.emplace(name, std::move(m));
+  }
+  std::fclose(f);
+  return out;
+}
+static ParamList sub(const std::map<std::string, Matrix>& all, const std::string& prefix) {
+  ParamList p;
+  for (auto& kv : all)
+    if (kv.first.compare(0, prefix.size(), prefix) == 0) p[kv.first.substr(prefix.size())] = kv.second.data;
+  return p;
+}
+static std::vector<int32_t> ints(const Matrix& m) { return std::vector<int32_t>(m.data.begin(), m.data.end()); }
+
+int main(int argc, char** argv) {
+  if (argc != 3) { std::fprintf(stderr, "usage: adapter_main problem.bin records.bin\n"); return 2; }
+  try {
+    auto all = read_all(argv[1]);
+    const Matrix& meta = all.at("meta");  // chains, iter, burn, thin, prior_type, include_mean, sv, ggl
+    const int chains = (int)meta.data[0], iters = (int)meta.data[1], burn = (int)meta.data[2], thin = (int)meta.data[3];
+    const int prior = (int)meta.data[4];
+    const bool mean = meta.data[5] != 0, sv = meta.data[6] != 0, ggl = meta.data[7] != 0;
+    std::vector<ParamList> init;
+    for (int c = 0; c < chains; ++c) init.push_back(sub(all, "init" + std::to_string(c) + "."));
+    std::vector<uint32_t> seeds(all.at("seed_chain").data.begin(), all.at("seed_chain").data.end());
+    std::vector<Records> rec;
+#define RUN(T) rec = T(chains, iters, burn, thin, all.at("x"), all.at("y"), sub(all, "cov."), sub(all, "prior."), sub(all, "icpt."), init, \
+                       prior, ints(all.at("grp_id")), ints(all.at("own_id")), ints(all.at("cross_id")), ints(all.at("grp_mat")), mean, seeds, false, 1).returnRecords()
+    if (sv && ggl) RUN(SvMcmc); else if (sv) RUN(SvGrpMcmc); else if (ggl) RUN(McmcLdlt); else RUN(McmcLdltGrp);
+    FILE* f = std::fopen(argv[2], "wb");
+    for (int c = 0; c < chains; ++c)
+      for (auto& kv : rec[c]) {
+        const std::string name = "c" + std::to_string(c) + "." + kv.first;
+        const int32_t nl = (int32_t)name.size();
+        std::fwrite(&nl, sizeof nl, 1, f); std::fwrite(name.data(), 1, nl, f);
+        std::fwrite(&kv.second.rows, sizeof(int64_t), 1, f); std::fwrite(&kv.second.cols, sizeof(int64_t), 1, f);
+        std::fwrite(kv.second.data.data(), sizeof(double), kv.second.data.size(), f);
+      }
+    std::fclose(f);
+    return 0;
+  } catch (const std::exception& e) {
+    std::fprintf(stderr, "bvhar_b200 adapter error: %s\n", e.what());
+    return 3;
+  }
+}

