@@ -106,7 +106,7 @@ struct bvhar_fit {
   DevBuf<long long> d_off, g1_b, g1_c, g2_b, g2_c, g3_a, g3_b, g3_y;
   DevBuf<uint32_t> seeds, iter;
   DevBuf<double> H, Z, Dinv, YLD, S, Cm, Acoef, alpha, cvec, prec, contem, L, chol_prec, sparse_coef, sparse_contem;
-  DevBuf<double> lvol_init, lvol_sig, diag, znorm, hN[4], hG[3], hq[4], hs, vscratch, gscratch, Pfac;
+  DevBuf<double> lvol_init, lvol_sig, diag, znorm, hN[4], hG[3], hq[4], hs, vscratch, pscratch, gscratch, Pfac;
   bool coef_v2 = false;
   std::map<std::string, std::unique_ptr<DevBuf<double>>> rec;
   std::vector<RecordSpec> rec_order;
@@ -174,7 +174,7 @@ struct bvhar_fit {
       LAUNCH("coef_chol", launch_coef_v2(1, D, P, Pfac.p, smem_limit, st));
       LAUNCH("coef_seq", launch_coef_v2(2, D, P, Pfac.p, smem_limit, st));
     } else {
-      LAUNCH("coef_draw", launch_coef(D, P, vscratch.p, smem_limit, st));
+      LAUNCH("coef_draw", launch_coef(D, P, vscratch.p, pscratch.p, smem_limit, st));
     }
     if (D.prior != 1) LAUNCH("prior_contem", launch_prior(D, P, PC, 1, st));
     LAUNCH("latent_dmma", launch_dgemm_tn(g3, st));
@@ -588,13 +588,14 @@ int build(const bvhar_fit_desc* d, bvhar_fit** out) {
   g3.epi = EPI_Y_MINUS; g3.Y = P.Y; g3.y_off = F->g3_y.p; g3.ldy = k; g3.ymod = k; g3.aligned16 = F->g3_aligned ? 1 : 0;
 
   // ---- scratch + setup kernels ----
-  bool need_v = false;
+  bool need_v = false, need_p = false;
   int ch_plan = 0;
   F->coef_v2 = coef_v2_fits(D, F->smem_limit) && getenv("BVHAR_COEF_V1") == nullptr;
   if (F->coef_v2) CU(F->Pfac.alloc((size_t)U * k * D.ldS));
-  else if (!coef_plan(D, F->smem_limit, &ch_plan, &need_v))
+  else if (!coef_plan(D, F->smem_limit, &ch_plan, &need_v, &need_p))
     return fail(BVHAR_ERR_UNSUPPORTED, "dim_design too large for the shared-memory Cholesky of this build (packed d(d+1)/2 doubles must fit 227 KB)");
   if (need_v) CU(F->vscratch.alloc((size_t)U * 2 * k * dd));
+  if (need_p) CU(F->pscratch.alloc((size_t)U * D.ldS));
   CU(F->gscratch.alloc((size_t)U * impact_gsize(D)));
   if (!impact_supported(D, F->smem_limit))
     return fail(BVHAR_ERR_UNSUPPORTED, "dim too large for the shared-memory contemporaneous draw of this build");
@@ -1062,7 +1063,7 @@ int bvhar_cuda_fit_run_stage(bvhar_fit* fit, int stage, int iter) {
         CU(launch_coef_v2(1, D, fit->P, fit->Pfac.p, fit->smem_limit, fit->st));
         CU(launch_coef_v2(2, D, fit->P, fit->Pfac.p, fit->smem_limit, fit->st));
       } else {
-        CU(launch_coef(D, fit->P, fit->vscratch.p, fit->smem_limit, fit->st));
+        CU(launch_coef(D, fit->P, fit->vscratch.p, fit->pscratch.p, fit->smem_limit, fit->st));
       }
       break;
     case 5: CU(launch_prior(D, fit->P, fit->PC, 1, fit->st)); break;

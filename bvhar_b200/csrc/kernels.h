@@ -7,8 +7,8 @@
 namespace bvhar {
 
 cudaError_t launch_sv_prep(const Dims& D, const DevPtrs& P, cudaStream_t st);
-bool coef_plan(const Dims& D, size_t smem_limit, int* CH_out, bool* vglobal_out);
-cudaError_t launch_coef(const Dims& D, const DevPtrs& P, double* vscratch, size_t smem_limit, cudaStream_t st);
+bool coef_plan(const Dims& D, size_t smem_limit, int* CH_out, bool* vglobal_out, bool* pglobal_out);
+cudaError_t launch_coef(const Dims& D, const DevPtrs& P, double* vscratch, double* pscratch, size_t smem_limit, cudaStream_t st);
 cudaError_t launch_draw_coef_batched(long long batch, int d, const double* Pp, const double* b, const double* z, double* out,
                                      cudaStream_t st);
 bool coef_v2_fits(const Dims& D, size_t smem_limit);

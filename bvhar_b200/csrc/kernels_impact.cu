@@ -40,8 +40,8 @@ constexpr int IMP_WARPS = 8;
 
 // ---- phase 2, shared by both covariance models ---------------------------------------------------------
 template <bool SV>
-__device__ void impact_draw_rows(const Dims& D, const DevPtrs& P, const double* G, double* wbuf, int u, int* bad) {
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+__device__ void impact_draw_rows(const Dims& D, const DevPtrs& P, const double* G, double* wbuf, int u, int* bad, int nw) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;  // nw = warps that own a workspace in wbuf
   const int k = D.k, q = D.q;
   const Philox rng(P.seeds[u], (uint32_t)(D.ubase + u), *P.iter);
   const int wstride = k * (k + 1) / 2 + 3 * k;
@@ -50,7 +50,8 @@ __device__ void impact_draw_rows(const Dims& D, const DevPtrs& P, const double* 
   double* z = r + k;
   double* x = z + k;
   double* Lu = P.L + (size_t)u * k * k;
-  if (tid < k) Lu[tid] = tid == 0 ? 1.0 : 0.0;  // row 0 of L (build_inv_lower, draw.h:124-132)
+  for (int b = tid; b < k; b += blockDim.x) Lu[b] = b == 0 ? 1.0 : 0.0;  // row 0 of L (build_inv_lower, draw.h:124-132)
+  if (warp >= nw) return;
   for (int j = 1 + warp; j < k; j += nw) {
     const int id = j * (j - 1) / 2;
     const double inv_dj = SV ? 1.0 : 1.0 / P.diag[(size_t)u * k + j];
@@ -85,7 +86,7 @@ __device__ void impact_draw_rows(const Dims& D, const DevPtrs& P, const double* 
 // NT = number of 8-wide tiles over the equation index j (k <= 8 NT); IMP_MT = m-tiles (8 pairs each) per warp
 // and pass (accumulators: IMP_MT * NT * 2 doubles per thread).
 template <int NT, int IMP_MT>
-__global__ void __launch_bounds__(IMP_WARPS * 32) impact_sv_kernel(const Dims D, const DevPtrs P, double* gscratch, const int gsize) {
+__global__ void __launch_bounds__(IMP_WARPS * 32) impact_sv_kernel(const Dims D, const DevPtrs P, double* gscratch, const int gsize, const int pw) {
   extern __shared__ __align__(16) double sm[];
   const int u = blockIdx.x, w = u / D.C, c = u % D.C;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -199,13 +200,13 @@ __global__ void __launch_bounds__(IMP_WARPS * 32) impact_sv_kernel(const Dims D,
   if (tid < k) P.znorm[(size_t)u * k + tid] = nacc;
   __threadfence_block();
   __syncthreads();
-  impact_draw_rows<true>(D, P, G, wbuf, u, &bad);
+  impact_draw_rows<true>(D, P, G, wbuf, u, &bad, pw);
   __syncthreads();
   if (tid == 0 && bad) atomicOr(&P.flags[u], 2);
 }
 
 // ---- LDLT: one Z'Z per unit (weights are constant in time), then the row draws ---------------------------
-__global__ void __launch_bounds__(256) impact_ldlt_kernel(const Dims D, const DevPtrs P, double* gscratch, const int gsize) {
+__global__ void __launch_bounds__(256) impact_ldlt_kernel(const Dims D, const DevPtrs P, double* gscratch, const int gsize, const int pw) {
   extern __shared__ __align__(16) double sm[];
   const int u = blockIdx.x, w = u / D.C, c = u % D.C;
   const int tid = threadIdx.x;
@@ -244,7 +245,7 @@ __global__ void __launch_bounds__(256) impact_ldlt_kernel(const Dims D, const De
   }
   __threadfence_block();
   __syncthreads();
-  impact_draw_rows<false>(D, P, G, wbuf, u, &bad);
+  impact_draw_rows<false>(D, P, G, wbuf, u, &bad, pw);
   __syncthreads();
   if (tid == 0 && bad) atomicOr(&P.flags[u], 2);
 }
@@ -257,25 +258,34 @@ int impact_gsize(const Dims& D) {
   return ((k - 1) * k * (2 * k - 1) / 6 + 3 * (k - 1) * k / 2) / 2 + 8;
 }
 
-size_t impact_smem(const Dims& D) {
+// shared memory with `pw` phase-2 workspaces (one per working warp)
+static size_t impact_smem_pw(const Dims& D, int pw) {
   const int k = D.k;
-  const size_t work = (size_t)IMP_WARPS * (k * (k + 1) / 2 + 3 * k);
+  const size_t work = (size_t)pw * (k * (k + 1) / 2 + 3 * k);
   if (D.sv) return (2 * (size_t)IMP_STAGES * IMP_TT * (k | 1) + ((k + 1) & ~1) + work) * sizeof(double);
   return (16 * (size_t)k + work) * sizeof(double);
 }
+static int impact_warps(const Dims& D, size_t smem_limit) {  // as many of the 8 warps as fit a workspace
+  int pw = IMP_WARPS;
+  while (pw > 0 && impact_smem_pw(D, pw) > smem_limit) --pw;
+  return pw;
+}
+size_t impact_smem(const Dims& D) { return impact_smem_pw(D, 1); }
 
 bool impact_supported(const Dims& D, size_t smem_limit) {
-  return impact_smem(D) <= smem_limit && (!D.sv || D.k <= 104);
+  return impact_warps(D, smem_limit) >= 1 && (!D.sv || D.k <= 104);
 }
 
 cudaError_t launch_impact(const Dims& D, const DevPtrs& P, double* gscratch, cudaStream_t st) {
-  const size_t smem = impact_smem(D);
+  const int pw = impact_warps(D, 227 * 1024);
+  if (pw < 1) return cudaErrorInvalidConfiguration;
+  const size_t smem = impact_smem_pw(D, pw);
   const int gs = impact_gsize(D);
   if (D.sv) {
 #define BV_IMPACT(NTV, MTV)                                                                                   \
   do {                                                                                                        \
     cudaFuncSetAttribute(impact_sv_kernel<NTV, MTV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-    impact_sv_kernel<NTV, MTV><<<D.U, IMP_WARPS * 32, smem, st>>>(D, P, gscratch, gs);                        \
+    impact_sv_kernel<NTV, MTV><<<D.U, IMP_WARPS * 32, smem, st>>>(D, P, gscratch, gs, pw);                        \
   } while (0)
     const int nt = (D.k + 7) / 8;
     if (nt <= 1) BV_IMPACT(1, 4);
@@ -288,7 +298,7 @@ cudaError_t launch_impact(const Dims& D, const DevPtrs& P, double* gscratch, cud
 #undef BV_IMPACT
   } else {
     cudaFuncSetAttribute(impact_ldlt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    impact_ldlt_kernel<<<D.U, 256, smem, st>>>(D, P, gscratch, gs);
+    impact_ldlt_kernel<<<D.U, 256, smem, st>>>(D, P, gscratch, gs, pw);
   }
   return cudaGetLastError();
 }

@@ -68,13 +68,14 @@ __global__ void __launch_bounds__(256, (KMAX <= 32 ? 2 : 1)) sv_prep_kernel(cons
 // The packed S_i are streamed through shared memory in row chunks of <= CH doubles; the symmetric
 // product S_i v is split into a row pass (warp per row) and a column pass (thread per column).
 template <bool SV>
-__global__ void __launch_bounds__(256) coef_kernel(const Dims D, const DevPtrs P, const int CH, double* vscratch) {
+__global__ void __launch_bounds__(256) coef_kernel(const Dims D, const DevPtrs P, const int CH, double* vscratch, double* pscratch) {
   extern __shared__ __align__(16) double sm[];
   const int u = blockIdx.x, w = u / D.C, c = u % D.C;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int k = D.k, d = D.d, Pp = D.Pp, ldM = D.ldM;
-  double* Pk = sm;
-  double* Sbuf = Pk + ((Pp + 1) & ~1);
+  // the packed precision / factor lives in shared memory when it fits, else in a per-unit global (L2-resident) scratch
+  double* Pk = pscratch ? pscratch + (size_t)u * ((Pp + 1) & ~1) : sm;
+  double* Sbuf = pscratch ? sm : sm + ((Pp + 1) & ~1);
   double* Lsm = Sbuf + CH;
   double* rhs = Lsm + k * k;
   double* outv = rhs + d;
@@ -540,36 +541,39 @@ __global__ void bump_kernel(uint32_t* iter, int* rec_row, int bump_iter, int bum
 }
 
 // ------------------------------------------------------------------ launch wrappers
-static size_t coef_smem(const Dims& D, int CH, bool vglobal) {
-  size_t n = ((D.Pp + 1) & ~1) + CH + (size_t)D.k * D.k + 6 * (size_t)D.d + D.k;
+static size_t coef_smem(const Dims& D, int CH, bool vglobal, bool pglobal) {
+  size_t n = CH + (size_t)D.k * D.k + 6 * (size_t)D.d + D.k;
+  if (!pglobal) n += (D.Pp + 1) & ~1;
   if (!vglobal) n += 2 * (size_t)D.k * D.d;
   return n * sizeof(double);
 }
-bool coef_plan(const Dims& D, size_t smem_limit, int* CH_out, bool* vglobal_out) {
+bool coef_plan(const Dims& D, size_t smem_limit, int* CH_out, bool* vglobal_out, bool* pglobal_out) {
   int CH = D.Pp < 4096 ? D.Pp : 4096;
   if (CH < D.d) CH = D.d;
-  bool vglobal = false;
-  if (coef_smem(D, CH, false) > smem_limit) vglobal = true;
-  if (coef_smem(D, CH, vglobal) > smem_limit) {
+  bool vglobal = false, pglobal = false;
+  if (coef_smem(D, CH, false, false) > smem_limit) vglobal = true;
+  if (coef_smem(D, CH, vglobal, false) > smem_limit) pglobal = true;
+  if (coef_smem(D, CH, vglobal, pglobal) > smem_limit) {
     CH = D.d;
-    if (coef_smem(D, CH, vglobal) > smem_limit) return false;
+    if (coef_smem(D, CH, vglobal, pglobal) > smem_limit) return false;
   }
   *CH_out = CH;
   *vglobal_out = vglobal;
+  *pglobal_out = pglobal;
   return true;
 }
-cudaError_t launch_coef(const Dims& D, const DevPtrs& P, double* vscratch, size_t smem_limit, cudaStream_t st) {
+cudaError_t launch_coef(const Dims& D, const DevPtrs& P, double* vscratch, double* pscratch, size_t smem_limit, cudaStream_t st) {
   int CH = 0;
-  bool vglobal = false;
-  if (!coef_plan(D, smem_limit, &CH, &vglobal)) return cudaErrorInvalidConfiguration;
-  if (vglobal && !vscratch) return cudaErrorInvalidValue;
-  const size_t smem = coef_smem(D, CH, vglobal);
+  bool vglobal = false, pglobal = false;
+  if (!coef_plan(D, smem_limit, &CH, &vglobal, &pglobal)) return cudaErrorInvalidConfiguration;
+  if ((vglobal && !vscratch) || (pglobal && !pscratch)) return cudaErrorInvalidValue;
+  const size_t smem = coef_smem(D, CH, vglobal, pglobal);
   if (D.sv) {
     cudaFuncSetAttribute(coef_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    coef_kernel<true><<<D.U, 256, smem, st>>>(D, P, CH, vglobal ? vscratch : nullptr);
+    coef_kernel<true><<<D.U, 256, smem, st>>>(D, P, CH, vglobal ? vscratch : nullptr, pglobal ? pscratch : nullptr);
   } else {
     cudaFuncSetAttribute(coef_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    coef_kernel<false><<<D.U, 256, smem, st>>>(D, P, CH, vglobal ? vscratch : nullptr);
+    coef_kernel<false><<<D.U, 256, smem, st>>>(D, P, CH, vglobal ? vscratch : nullptr, pglobal ? pscratch : nullptr);
   }
   return cudaGetLastError();
 }
