@@ -106,8 +106,8 @@ struct bvhar_fit {
   DevBuf<long long> d_off, g1_b, g1_c, g2_b, g2_c, g3_a, g3_b, g3_y;
   DevBuf<uint32_t> seeds, iter;
   DevBuf<double> H, Z, Dinv, YLD, S, Cm, Acoef, alpha, cvec, prec, contem, L, chol_prec, sparse_coef, sparse_contem;
-  DevBuf<double> lvol_init, lvol_sig, diag, znorm, hN[4], hG[3], hq[4], hs, vscratch, pscratch, gscratch, Pfac;
-  bool coef_v2 = false;
+  DevBuf<double> lvol_init, lvol_sig, diag, znorm, hN[4], hG[3], hq[4], hs, vscratch, pscratch, gscratch, Pfac, hscr;
+  bool coef_v2 = false, coef_big = false;
   std::map<std::string, std::unique_ptr<DevBuf<double>>> rec;
   std::vector<RecordSpec> rec_order;
   GemmArgs g1{}, g2{}, g3{};
@@ -169,7 +169,11 @@ struct bvhar_fit {
       LAUNCH("gram_S_dmma", launch_dgemm_tn(g1, st));
       LAUNCH("gram_C_dmma", launch_dgemm_tn(g2, st));
     }
-    if (coef_v2) {
+    if (coef_big) {
+      if (D.sv) LAUNCH("coef_pbuild", launch_coef_v2(0, D, P, Pfac.p, smem_limit, st));
+      LAUNCH("coef_chol_cta", launch_coef_big(1, D, P, Pfac.p, hscr.p, smem_limit, st));
+      LAUNCH("coef_seq_big", launch_coef_big(2, D, P, Pfac.p, hscr.p, smem_limit, st));
+    } else if (coef_v2) {
       if (D.sv) LAUNCH("coef_pbuild", launch_coef_v2(0, D, P, Pfac.p, smem_limit, st));
       LAUNCH("coef_chol", launch_coef_v2(1, D, P, Pfac.p, smem_limit, st));
       LAUNCH("coef_seq", launch_coef_v2(2, D, P, Pfac.p, smem_limit, st));
@@ -590,9 +594,15 @@ int build(const bvhar_fit_desc* d, bvhar_fit** out) {
   // ---- scratch + setup kernels ----
   bool need_v = false, need_p = false;
   int ch_plan = 0;
-  F->coef_v2 = coef_v2_fits(D, F->smem_limit) && getenv("BVHAR_COEF_V1") == nullptr;
-  if (F->coef_v2) CU(F->Pfac.alloc((size_t)U * k * D.ldS));
-  else if (!coef_plan(D, F->smem_limit, &ch_plan, &need_v, &need_p))
+  // coefficient stage: warp-per-matrix kernels for small designs, CTA-per-matrix blocked kernels for large ones,
+  // the single-kernel path (everything inside one CTA per unit) as the last resort
+  const bool force_v1 = getenv("BVHAR_COEF_V1") != nullptr, force_big = getenv("BVHAR_COEF_BIG") != nullptr;
+  F->coef_v2 = coef_v2_fits(D, F->smem_limit) && !force_v1;
+  F->coef_big = coef_big_fits(D, F->smem_limit) && !force_v1 && (D.d > 128 || !F->coef_v2 || force_big);
+  if (F->coef_big) F->coef_v2 = false;
+  if (F->coef_v2 || F->coef_big) CU(F->Pfac.alloc((size_t)U * k * D.ldS));
+  if (F->coef_big) CU(F->hscr.alloc((size_t)U * k * dd));
+  if (!F->coef_v2 && !F->coef_big && !coef_plan(D, F->smem_limit, &ch_plan, &need_v, &need_p))
     return fail(BVHAR_ERR_UNSUPPORTED, "dim_design too large for the shared-memory Cholesky of this build (packed d(d+1)/2 doubles must fit 227 KB)");
   if (need_v) CU(F->vscratch.alloc((size_t)U * 2 * k * dd));
   if (need_p) CU(F->pscratch.alloc((size_t)U * D.ldS));
@@ -1058,7 +1068,11 @@ int bvhar_cuda_fit_run_stage(bvhar_fit* fit, int stage, int iter) {
     case 3: if (D.sv) CU(launch_sv_prep(D, fit->P, fit->st)); break;
     case 4:
       if (D.sv) { CU(launch_dgemm_tn(fit->g1, fit->st)); CU(launch_dgemm_tn(fit->g2, fit->st)); }
-      if (fit->coef_v2) {
+      if (fit->coef_big) {
+        if (D.sv) CU(launch_coef_v2(0, D, fit->P, fit->Pfac.p, fit->smem_limit, fit->st));
+        CU(launch_coef_big(1, D, fit->P, fit->Pfac.p, fit->hscr.p, fit->smem_limit, fit->st));
+        CU(launch_coef_big(2, D, fit->P, fit->Pfac.p, fit->hscr.p, fit->smem_limit, fit->st));
+      } else if (fit->coef_v2) {
         CU(launch_coef_v2(0, D, fit->P, fit->Pfac.p, fit->smem_limit, fit->st));
         CU(launch_coef_v2(1, D, fit->P, fit->Pfac.p, fit->smem_limit, fit->st));
         CU(launch_coef_v2(2, D, fit->P, fit->Pfac.p, fit->smem_limit, fit->st));

@@ -23,6 +23,8 @@ inline cudaError_t launch_coef_chol(int nc, const Dims& D, const DevPtrs& P, dou
        : nc <= 4 ? launch_coef_chol_nc4(D, P, Pfac, smem_limit, st)
                  : launch_coef_chol_nc8(D, P, Pfac, smem_limit, st);
 }
+bool coef_big_fits(const Dims& D, size_t smem_limit);
+cudaError_t launch_coef_big(int part, const Dims& D, const DevPtrs& P, double* Pfac, double* hscr, size_t smem_limit, cudaStream_t st);
 int impact_gsize(const Dims& D);
 size_t impact_smem(const Dims& D);
 bool impact_supported(const Dims& D, size_t smem_limit);

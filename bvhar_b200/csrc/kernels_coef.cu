@@ -35,19 +35,20 @@ __global__ void __launch_bounds__(256) coef_pbuild_kernel(const Dims D, const De
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int fr = lane >> 2, fc = lane & 3;
   const double* Lu = P.L + (size_t)u * k * k;
+  const int mtb = blockIdx.z * MT;  // first row tile of this pass (k > 32 takes two passes over S)
   double af[MT][KS];  // A[m = j][kk = i] = L_ij^2 for i >= j
 #pragma unroll
   for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
     for (int ks = 0; ks < KS; ++ks) {
-      const int j = 8 * mt + fr, i = 4 * ks + fc;
+      const int j = 8 * (mtb + mt) + fr, i = 4 * ks + fc;
       const double l = (i < k && j <= i) ? Lu[i * k + j] : 0.0;
       af[mt][ks] = l * l;
     }
   const double* Su = P.S + (size_t)u * k * D.ldS;
   double* Pu = Pfac + (size_t)u * k * D.ldS;
   const int ntiles = (D.Pp + 7) / 8;
-  constexpr int NQ = 4;  // n-tiles per warp iteration (loads of all of them in flight together)
+  constexpr int NQ = KS > 8 ? 2 : 4;  // n-tiles per warp iteration (loads of all of them in flight together)
   for (int nt0 = (blockIdx.y * 8 + warp) * NQ; nt0 < ntiles; nt0 += gridDim.y * 8 * NQ) {
     double bf[NQ][KS];
 #pragma unroll
@@ -65,7 +66,7 @@ __global__ void __launch_bounds__(256) coef_pbuild_kernel(const Dims D, const De
         double c0 = 0.0, c1 = 0.0;
 #pragma unroll
         for (int ks = 0; ks < KS; ++ks) dmma_m8n8k4(c0, c1, af[mt][ks], bf[q][ks]);
-        const int j = 8 * mt + fr;
+        const int j = 8 * (mtb + mt) + fr;
         if (j < k && p < D.Pp) {  // ldS is even and p is even: 16-byte aligned pair inside the padded row
           *reinterpret_cast<double2*>(Pu + (size_t)j * D.ldS + p) = make_double2(c0, c1);
         }
@@ -244,6 +245,7 @@ cudaError_t launch_part(int part, const Dims& D, const DevPtrs& P, double* Pfac,
     else if (k <= 16) coef_pbuild_kernel<2, 4><<<grid, 256, 0, st>>>(D, P, Pfac);
     else if (k <= 24) coef_pbuild_kernel<3, 6><<<grid, 256, 0, st>>>(D, P, Pfac);
     else if (k <= 32) coef_pbuild_kernel<4, 8><<<grid, 256, 0, st>>>(D, P, Pfac);
+    else if (k <= 64) coef_pbuild_kernel<4, 16><<<dim3(D.U, 4, 2), 256, 0, st>>>(D, P, Pfac);
     else coef_pbuild_generic_kernel<<<D.U, 256, 0, st>>>(D, P, Pfac);
   } else if (part == 1) {
     return launch_coef_chol(NC, D, P, Pfac, smem_limit, st);

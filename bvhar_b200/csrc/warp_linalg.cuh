@@ -21,6 +21,29 @@ __device__ __forceinline__ double wl_wsum(double v) {
 }
 #define wsum wl_wsum
 
+// Cholesky of one 32 x 32 block held in registers, one row per lane (dg[c] = A[lane][c], c <= lane; rows >= nv
+// must be passed as identity rows).  On exit dg holds L, and the return value is 1 / L[lane][lane].
+__device__ __forceinline__ double chol32_registers(double (&dg)[32], int* bad) {
+  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  double dinv = 1.0;
+#pragma unroll
+  for (int c = 0; c < 32; ++c) {
+    const double pc = __shfl_sync(FULL, dg[c], c);
+    const double piv = sqrt(pc), inv = 1.0 / piv;
+    if (lane == c && !(pc > 0.0)) *bad = 1;
+    const double lc = lane > c ? dg[c] * inv : 0.0;
+    if (lane == c) { dg[c] = piv; dinv = inv; }
+    else dg[c] = lc;
+#pragma unroll
+    for (int b = c + 1; b < 32; ++b) {
+      const double lbc = __shfl_sync(FULL, lc, b);
+      dg[b] = fma(-lc, lbc, dg[b]);
+    }
+  }
+  return dinv;
+}
+
 template <int NB>
 __device__ __forceinline__ void chol_blocked_warp(double* Pk, int d, int* bad) {
   const unsigned FULL = 0xffffffffu;
@@ -115,8 +138,11 @@ __device__ __forceinline__ void chol_blocked_warp(double* Pk, int d, int* bad) {
 // (part[r], static indices) and its own column contribution S_ab x_a, with the loads of 8 rows in flight at
 // a time; ONE butterfly reduce-scatter per block (31 shuffles for 32 rows instead of 5 per row) then leaves
 // the total of row 32 rb + l on lane l.
+// With (first, step) a warp takes only the 32-row blocks rb = first, first + step, ... (its `out` is then a partial
+// result to be summed over the cooperating warps).
 template <int NC>
-__device__ __forceinline__ void symv_packed_warp(const double* __restrict__ S, const double* x, int d, double (&out)[NC]) {
+__device__ __forceinline__ void symv_packed_warp(const double* __restrict__ S, const double* x, int d, double (&out)[NC],
+                                                 int first = 0, int step = 1) {
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   double xb[NC];
@@ -129,6 +155,7 @@ __device__ __forceinline__ void symv_packed_warp(const double* __restrict__ S, c
 #pragma unroll
   for (int rb = 0; rb < NC; ++rb) {
     if (32 * rb >= d) break;
+    if (step > 1 && (rb % step) != first) continue;  // warp-uniform
     double part[32];
     constexpr int RB = 8;
 #pragma unroll

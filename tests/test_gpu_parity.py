@@ -134,6 +134,32 @@ def test_stage_parity_model_variants(prior, sv, kw):
     _stage_check(prior, sv, **kw)
 
 
+@pytest.mark.parametrize("kw", [
+    dict(dim=3, T=70, lag=7),                 # d = 22: one 32-column panel
+    dict(dim=4, T=120, lag=9),                # d = 37: two panels, the second partial
+    dict(dim=7, T=150, lag=10, chains=1),     # d = 71
+    dict(dim=6, T=260, lag=16, chains=2),     # d = 97: four panels (one of them full width below the diagonal)
+], ids=lambda k: ",".join(f"{a}={b}" for a, b in k.items()))
+@pytest.mark.parametrize("prior,sv", [("Horseshoe", True), ("SSVS", False), ("GDP", False), ("NG", True)])
+def test_stage_parity_large_design_path(monkeypatch, prior, sv, kw):
+    """The CTA-per-matrix blocked Cholesky + blocked CTA solve (kernels_coef_big.cu) that dim_design > 128 uses,
+    forced on small designs so that the oracle stays cheap."""
+    monkeypatch.setenv("BVHAR_COEF_BIG", "1")
+    _stage_check(prior, sv, **kw)
+
+
+@pytest.mark.parametrize("prior,sv,kw", [("NG", True, dict(dim=10, T=200, lag=13, chains=2)),       # d = 131, k = 10
+                                          ("GDP", False, dict(dim=36, T=150, lag=4, chains=1)),    # d = 145, k = 36 (two-pass P build n/a: LDLT)
+                                          ("DL", True, dict(dim=34, T=150, lag=4, chains=1))])     # d = 137, k = 34 > 32: two-pass DMMA P build
+def test_large_design_natural(prior, sv, kw):
+    pk, _ = pr.pack(prior=prior, sv=sv, iters=2, burn=0, **kw)
+    o = ob.OracleFit(pk); g = CudaFit(pk)
+    o.step(2, True); g.step(2, True)
+    for nm in ("alpha_record", "a_record", "alpha_sparse_record"):
+        for c in range(pk.n_chains):
+            assert relerr(o.record(nm, 0, c), g.record(nm, 0, c)) < TRAJ_TOL, (prior, nm)
+
+
 def test_stage_parity_windows():
     """Rolling (equal) and expanding (ragged) window tables in one batch (forecaster.h:851-859, 920-928)."""
     _stage_check("NG", True, dim=2, T=48, chains=2, windows=[(0, 30), (1, 30), (5, 30), (16, 30)])
