@@ -88,9 +88,17 @@ class ForecastDesc(C.Structure):
         ("abi_version", C.c_int32), ("device", C.c_int32), ("n_units", C.c_int32), ("dim", C.c_int32),
         ("nrow_coef", C.c_int32), ("include_mean", C.c_int32), ("cov_type", C.c_int32), ("step", C.c_int32),
         ("var_lag", C.c_int32), ("is_vhar", C.c_int32), ("sv", C.c_int32), ("get_lpl", C.c_int32),
-        ("n_draws", C.c_int32), ("reserved", C.c_int32),
+        ("n_draws", C.c_int32), ("unit_id_base", C.c_int32),
         ("har_trans", c_dp), ("coef_record", c_dp), ("contem_record", c_dp), ("diag_record", c_dp),
         ("sigh_record", c_dp), ("last_obs", c_dp), ("valid_vec", c_dp), ("seed", c_up),
+    ]
+
+
+class OutforecastParams(C.Structure):
+    _fields_ = [
+        ("abi_version", C.c_int32), ("step", C.c_int32), ("var_lag", C.c_int32), ("is_vhar", C.c_int32),
+        ("sv", C.c_int32), ("get_lpl", C.c_int32), ("sparse", C.c_int32), ("reserved", C.c_int32),
+        ("har_trans", c_dp), ("y_full", c_dp), ("y_rows", C.c_int64), ("valid_vec", c_dp), ("seed_forecast", c_up),
     ]
 
 
@@ -335,6 +343,8 @@ def load_library():
     L.bvhar_cuda_fit_destroy.argtypes = [vp]
     L.bvhar_cuda_fit_destroy.restype = None
     L.bvhar_cuda_forecast_density.argtypes = [C.POINTER(ForecastDesc), c_dp, c_dp]
+    L.bvhar_cuda_outforecast_run.argtypes = [C.POINTER(FitDesc), C.POINTER(OutforecastParams), c_dp, c_dp]
+    L.bvhar_cuda_outforecast_params_size.argtypes = [C.POINTER(C.c_int64)]
     L.bvhar_cuda_dgemm_tn.argtypes = [C.c_int, C.c_int64, C.c_int64, C.c_int64, c_dp, C.c_int64, c_dp, C.c_int64, c_dp, C.c_int64]
     L.bvhar_cuda_draw_coef_batched.argtypes = [C.c_int, C.c_int64, C.c_int32, c_dp, c_dp, c_dp, c_dp]
     L.bvhar_cuda_bench_fp64_peak.argtypes = [C.c_int, C.c_int, c_dp]
@@ -346,6 +356,10 @@ def load_library():
     mine = [C.sizeof(FitDesc), C.sizeof(ChainInit), C.sizeof(ForecastDesc), C.sizeof(PriorParams)]
     if [v.value for v in sz] != mine:
         raise RuntimeError(f"bvhar_b200: ctypes struct layout {mine} differs from the library's {[v.value for v in sz]}")
+    osz = C.c_int64()
+    L.bvhar_cuda_outforecast_params_size(C.byref(osz))
+    if osz.value != C.sizeof(OutforecastParams):
+        raise RuntimeError("bvhar_b200: ctypes layout of bvhar_outforecast_params differs from the library's")
     _LIB = L
     return L
 

@@ -888,6 +888,10 @@ int bvhar_cuda_struct_sizes(int64_t* fit_desc, int64_t* chain_init, int64_t* for
   return 0;
 }
 
+int bvhar_cuda_outforecast_params_size(int64_t* bytes) {
+  if (bytes) *bytes = sizeof(bvhar_outforecast_params);
+  return 0;
+}
 int bvhar_cuda_host_alloc(int64_t bytes, void** out) {
   if (!out || bytes < 0) return fail(BVHAR_ERR_BAD_ARG, "bad host_alloc arguments");
   *out = nullptr;
@@ -1127,12 +1131,93 @@ int bvhar_cuda_forecast_density(const bvhar_forecast_desc* d, double* out_densit
   CU(seed.upload(std::vector<uint32_t>(d->seed, d->seed + U)));
   CU(out.alloc((size_t)U * S * k * d->step));
   if (A.get_lpl) CU(lpl.alloc((size_t)U * d->step));
-  A.har = har.p; A.coef = coef.p; A.contem = contem.p; A.diag = diag.p; A.sigh = sigh.p; A.last_obs = last.p;
+  A.unit_base = (unsigned)d->unit_id_base;
+  A.har = har.p;
+  A.coef = {coef.p, (long long)S * ncoef, 1, S};  // host records: column-major n_draws x cols per unit
+  A.cst = {coef.p + (size_t)d->nrow_coef * k * S, (long long)S * ncoef, 1, S};
+  A.contem = {contem.p, (long long)S * q, 1, S};
+  A.diag = {diag.p, (long long)S * k, 1, S};
+  A.sigh = {sigh.p, (long long)S * k, 1, S};
+  A.last_obs = last.p;
   A.valid = valid.p; A.seed = seed.p; A.out = out.p; A.lpl = lpl.p;
   CU(launch_forecast(A, 0));
   CU(cudaDeviceSynchronize());
   CU(cudaMemcpy(out_density, out.p, out.n * sizeof(double), cudaMemcpyDeviceToHost));
   if (A.get_lpl) CU(cudaMemcpy(out_lpl, lpl.p, lpl.n * sizeof(double), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+// ---- out-of-sample refits + forecasts in one call (McmcOutforecastRun::returnForecast, forecaster.h:616-650,
+// 755-806): every (window, chain) of the descriptor's window table is refitted, then forecast straight from the
+// device-resident records (no host round trip of the draws).
+int bvhar_cuda_outforecast_run(const bvhar_fit_desc* fd, const bvhar_outforecast_params* fp, double* out_forecast, double* out_lpl) {
+  if (!fd || !fp || !out_forecast) return fail(BVHAR_ERR_BAD_ARG, "null argument");
+  if (fp->abi_version != BVHAR_CUDA_ABI_VERSION) return fail(BVHAR_ERR_BAD_ARG, "descriptor ABI version mismatch");
+  if (fp->step < 1 || fp->step > 64) return fail(BVHAR_ERR_UNSUPPORTED, "forecast step must be in 1..64");
+  if (!fp->y_full || !fp->seed_forecast) return fail(BVHAR_ERR_BAD_ARG, "y_full / seed_forecast missing");
+  if (fp->is_vhar && !fp->har_trans) return fail(BVHAR_ERR_BAD_ARG, "har_trans missing");
+  bvhar_fit_desc d2 = *fd;
+  d2.record_mask = BVHAR_REC_COEF | BVHAR_REC_LVOL_LAST | (fp->sparse ? BVHAR_REC_SPARSE : 0u);  // all the forecaster reads (config.h:998-1001)
+  bvhar_fit* fit = nullptr;
+  int rc = build(&d2, &fit);
+  if (rc) return rc;
+  std::unique_ptr<bvhar_fit> guard(fit);
+  rc = bvhar_cuda_fit_run(fit, nullptr, nullptr);
+  if (rc && rc != BVHAR_ERR_NUMERICAL) return rc;  // a non-PD flag does not abort (the reference would carry NaNs)
+  const Dims& D = fit->D;
+  const int k = D.k, U = D.U, q = D.q, p = fp->var_lag, step = fp->step;
+  const int S = (fit->rec_filled + fit->thin - 1) / fit->thin;
+  if (S < 1) return fail(BVHAR_ERR_BAD_ARG, "No stable MCMC draws");  // forecaster.h:286, 322
+  const int dd_fc = p * k + (D.mean ? 1 : 0);
+  if (fp->is_vhar ? (D.nrow != 3 * k) : (D.nrow != p * k)) return fail(BVHAR_ERR_BAD_ARG, "var_lag does not match the coefficient matrix");
+  (void)dd_fc;
+  ForecastArgs A{};
+  A.n_units = U; A.k = k; A.nrow = D.nrow; A.mean = D.mean; A.sv_model = D.sv; A.step = step; A.p = p; A.is_vhar = fp->is_vhar;
+  A.sv = fp->sv; A.get_lpl = fp->get_lpl && fp->valid_vec && out_lpl; A.S = S; A.unit_base = (unsigned)D.ubase;
+  A.har_r = 3 * k + (D.mean ? 1 : 0); A.har_c = p * k + (D.mean ? 1 : 0);
+  const RecPtrs& R = fit->R;
+  const long long cap = R.cap, th = fit->thin;
+  const double* coefp = fp->sparse ? R.alpha_sparse : R.alpha;
+  const double* cstp = fp->sparse ? R.c_sparse : R.c;
+  const double* ap = fp->sparse ? R.a_sparse : R.a;
+  A.coef = {coefp, cap * D.N, th * D.N, 1};
+  A.cst = {cstp, cap * k, th * k, 1};
+  A.contem = {ap, cap * q, th * q, 1};
+  A.diag = {D.sv ? R.h_last : R.d, cap * k, th * k, 1};
+  A.sigh = {R.sigh, cap * k, th * k, 1};
+  // last var_lag observations of every window: response rows of window w sit at y_full rows [p + row0, p + row0 + n)
+  std::vector<double> hlast((size_t)U * p * k);
+  for (int w = 0; w < D.W; ++w) {
+    const int64_t end = (int64_t)p + fit->win_row0[w] + fit->win_n[w];
+    if (end > fp->y_rows) return fail(BVHAR_ERR_BAD_ARG, "y_full is shorter than the window table implies");
+    for (int c = 0; c < D.C; ++c)
+      for (int jj = 0; jj < k; ++jj)
+        for (int l = 0; l < p; ++l) hlast[((size_t)(w * D.C + c) * k + jj) * p + l] = fp->y_full[(size_t)jj * fp->y_rows + (end - p + l)];
+  }
+  std::vector<uint32_t> hseed((size_t)U);
+  for (int u = 0; u < U; ++u) hseed[u] = fp->seed_forecast[u % D.C];  // the same seed for every window (forecaster.h:1028)
+  DevBuf<double> har, last, valid, out, lpl;
+  DevBuf<uint32_t> seed;
+  if (fp->is_vhar) CU(har.upload(std::vector<double>(fp->har_trans, fp->har_trans + (size_t)A.har_r * A.har_c)));
+  CU(last.upload(hlast)); CU(seed.upload(hseed));
+  if (A.get_lpl) CU(valid.upload(std::vector<double>(fp->valid_vec, fp->valid_vec + k)));
+  CU(out.alloc((size_t)U * S * k * step));
+  if (A.get_lpl) CU(lpl.alloc((size_t)U * step));
+  A.har = har.p; A.last_obs = last.p; A.valid = valid.p; A.seed = seed.p; A.out = out.p; A.lpl = lpl.p;
+  CU(launch_forecast(A, 0));
+  CU(cudaDeviceSynchronize());
+  std::vector<double> hout(out.n);
+  CU(cudaMemcpy(hout.data(), out.p, out.n * sizeof(double), cudaMemcpyDeviceToHost));
+  for (size_t e = 0; e < (size_t)U * S * k; ++e) out_forecast[e] = hout[e * step + (step - 1)];  // .bottomRows(1), forecaster.h:803
+  if (A.get_lpl) {
+    std::vector<double> hl(lpl.n);
+    CU(cudaMemcpy(hl.data(), lpl.p, lpl.n * sizeof(double), cudaMemcpyDeviceToHost));
+    for (int u = 0; u < U; ++u) {
+      double s = 0.0;
+      for (int h = 0; h < step; ++h) s += hl[(size_t)u * step + h];
+      out_lpl[u] = s / step;
+    }
+  }
   return 0;
 }
 

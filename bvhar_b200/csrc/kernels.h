@@ -39,9 +39,16 @@ cudaError_t launch_prior(const Dims& D, const DevPtrs& P, const PriorConst& C, i
 cudaError_t launch_scatter_lvol(const double* src, double* dst, int n, int M, int ldM, int nsrc, cudaStream_t st);
 cudaError_t launch_build_xx(const Dims& D, const DevPtrs& P, double* XX, cudaStream_t st);
 // forecast (kernels_forecast.cu)
+struct RecView {  // element (unit u, draw i, column c) = p[u * us + i * sd + c * sc]
+  const double* p;
+  long long us, sd, sc;
+};
 struct ForecastArgs {
   int n_units, k, nrow, mean, sv_model, step, p, is_vhar, sv, get_lpl, S, har_r, har_c;
-  const double *har, *coef, *contem, *diag, *sigh, *last_obs, *valid;
+  unsigned unit_base;  // Philox key word 1 of unit u = unit_base + u
+  const double* har;
+  RecView coef, cst, contem, diag, sigh;  // alpha | constants | a | d or h(last) | sigh
+  const double *last_obs, *valid;
   const uint32_t* seed;
   double *out, *lpl;
 };

@@ -60,7 +60,6 @@ __global__ void __launch_bounds__(128) forecast_kernel(const ForecastArgs A) {
   const int u = blockIdx.y;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int k = A.k, nrow = A.nrow, S = A.S, p = A.p, step = A.step;
-  const int ncoef = nrow * k + (A.mean ? k : 0), q = k * (k - 1) / 2;
   const int dd = p * k + (A.mean ? 1 : 0);
   // per-thread workspace in shared memory: last_pvec (dd), tmp ((p-1)k), post_mean (k), sv (k), z (k), hx (har_r)
   const int per = dd + (p - 1) * k + 3 * k + (A.is_vhar ? A.har_r : 0);
@@ -75,18 +74,15 @@ __global__ void __launch_bounds__(128) forecast_kernel(const ForecastArgs A) {
   for (int h = threadIdx.x; h < step && h < 64; h += blockDim.x) lpl_acc[h] = 0.0;
   __syncthreads();
   if (i < S) {
-    const double* coef = A.coef + (size_t)u * S * ncoef;
-    const double* arec = A.contem + (size_t)u * S * q;
-    const double* dg = A.diag + (size_t)u * S * k;
-    const double* sg = A.sv_model ? A.sigh + (size_t)u * S * k : nullptr;
+    auto at = [&](const RecView& v, int col) { return v.p[(long long)u * v.us + (long long)i * v.sd + (long long)col * v.sc]; };
     const double* last = A.last_obs + (size_t)u * p * k;
-    const Philox rng(A.seed[u], (uint32_t)u, (uint32_t)i);
+    const Philox rng(A.seed[u], A.unit_base + (uint32_t)u, (uint32_t)i);
     for (int l = 0; l < p; ++l)
       for (int j = 0; j < k; ++j) last_pvec[l * k + j] = last[(size_t)j * p + (p - 1 - l)];
     if (A.mean) last_pvec[dd - 1] = 1.0;
     for (int j = 0; j < k; ++j) pm[j] = last_pvec[j];
     for (int e = 0; e < (p - 1) * k; ++e) tmp[e] = last_pvec[k + e];
-    for (int j = 0; j < k; ++j) svu[j] = A.sv_model ? dg[(size_t)j * S + i] : sqrt(dg[(size_t)j * S + i]);
+    for (int j = 0; j < k; ++j) svu[j] = A.sv_model ? at(A.diag, j) : sqrt(at(A.diag, j));
     for (int h = 0; h < step; ++h) {
       for (int e = 0; e < (p - 1) * k; ++e) last_pvec[k + e] = tmp[e];
       for (int j = 0; j < k; ++j) last_pvec[j] = pm[j];
@@ -103,13 +99,13 @@ __global__ void __launch_bounds__(128) forecast_kernel(const ForecastArgs A) {
       const double* xin = A.is_vhar ? hx : last_pvec;
       for (int j = 0; j < k; ++j) {
         double s = 0.0;
-        for (int r = 0; r < nrow; ++r) s += coef[(size_t)(j * nrow + r) * S + i] * xin[r];
-        if (A.mean) s += coef[(size_t)(nrow * k + j) * S + i] * xin[nrow];
+        for (int r = 0; r < nrow; ++r) s += at(A.coef, j * nrow + r) * xin[r];
+        if (A.mean) s += at(A.cst, j) * xin[nrow];
         pm[j] = s;
       }
       if (A.sv_model) {
         if (A.sv)
-          for (int j = 0; j < k; ++j) svu[j] += rng.normal_elem(ST_FORECAST_H, (uint32_t)(h * k + j)) * sqrt(sg[(size_t)j * S + i]);
+          for (int j = 0; j < k; ++j) svu[j] += rng.normal_elem(ST_FORECAST_H, (uint32_t)(h * k + j)) * sqrt(at(A.sigh, j));
         for (int j = 0; j < k; ++j) zn[j] = rng.normal_elem(ST_FORECAST_Y, (uint32_t)(h * k + j)) * exp(svu[j] / 2);
       } else {
         for (int j = 0; j < k; ++j) zn[j] = rng.normal_elem(ST_FORECAST_Y, (uint32_t)(h * k + j)) * svu[j];
@@ -118,7 +114,7 @@ __global__ void __launch_bounds__(128) forecast_kernel(const ForecastArgs A) {
       for (int j = 0; j < k; ++j) {
         double s = zn[j];
         const int id = j * (j - 1) / 2;
-        for (int m = 0; m < j; ++m) s -= arec[(size_t)(id + m) * S + i] * zn[m];
+        for (int m = 0; m < j; ++m) s -= at(A.contem, id + m) * zn[m];
         zn[j] = s;
       }
       for (int j = 0; j < k; ++j) {
@@ -130,7 +126,7 @@ __global__ void __launch_bounds__(128) forecast_kernel(const ForecastArgs A) {
         for (int j = 0; j < k; ++j) {
           double s = pm[j] - A.valid[j];
           const int id = j * (j - 1) / 2;
-          for (int m = 0; m < j; ++m) s += arec[(size_t)(id + m) * S + i] * (pm[m] - A.valid[m]);
+          for (int m = 0; m < j; ++m) s += at(A.contem, id + m) * (pm[m] - A.valid[m]);
           if (A.sv_model) { s *= exp(-svu[j] / 2); lg += svu[j] / 2; }
           else { s /= svu[j]; lg += log(svu[j]); }
           quad += s * s;

@@ -21,7 +21,7 @@ import numpy as np
 from . import _abi
 from ._abi import REC_ALL, REC_COEF, REC_LVOL_LAST, REC_SPARSE, PackedFit
 from ._design import build_design, build_grpmat, build_response, build_vhar, build_vhar_design
-from ._engine import CudaFit, forecast_density
+from ._engine import CudaFit, forecast_density, outforecast
 from ._spec import (PRIOR_TYPE, DlConfig, GdpConfig, HorseshoeConfig, InterceptConfig, LdltConfig, MinnesotaConfig,
                     NgConfig, SsvsConfig, SvConfig, _BayesConfig, make_inits)
 
@@ -99,13 +99,13 @@ class _AutoregBayes:
     def _seeds(self, *shape):
         return self._rng.integers(1, np.iinfo(np.int32).max, size=shape)
 
-    def _pack(self, x, y, seeds, win_row0=None, win_nrow=None, record_mask=None, lvol_from_init=False) -> PackedFit:
+    def _pack(self, x, y, seeds, win_row0=None, win_nrow=None, record_mask=None, lvol_from_init=False, unit_id_base=0) -> PackedFit:
         return PackedFit(self.chains_, self.iter_, self.burn_, self.thin_, x, y, self.cov_spec_.to_dict(),
                          self.spec_.to_dict(), self.intercept_spec_.to_dict(), self.init_, int(self._prior_type),
                          self._group_id, self._own_id, self._cross_id, self.group_, self.fit_intercept, seeds,
                          is_group=self._ggl, win_row0=win_row0, win_nrow=win_nrow,
                          record_mask=self._record_mask if record_mask is None else record_mask, device=self._device,
-                         lvol_from_init=lvol_from_init)
+                         lvol_from_init=lvol_from_init, unit_id_base=unit_id_base)
 
     def _coef_name(self) -> str:
         return "alpha"
@@ -209,40 +209,37 @@ class _AutoregBayes:
             nrow = [n0] * n_hor
         seeds = self._seeds(self.chains_, n_hor).T  # _bayes.py: reshape(chains, -1).T
         seed_fc = self._seeds(self.chains_)
-        units: List[Dict[str, np.ndarray]] = list(self._chain_records())
-        if n_hor > 1:
-            mask = REC_COEF | REC_SPARSE | REC_LVOL_LAST
-            packed = self._pack(x_tot, y_tot, seeds[1:], win_row0=row0[1:], win_nrow=nrow[1:], record_mask=mask,
-                                lvol_from_init=self._is_sv and expanding)
-            fit = CudaFit(packed)
-            try:
-                fit.run(None)
-            except _abi.BvharCudaError as e:
-                if e.status != 3:
-                    raise
-                warnings.warn(str(e))
-            bulk = {nm: fit.record_all(nm) for nm in fit.record_names()}
-            for u in range((n_hor - 1) * self.chains_):
-                units.append({nm: arr[u] for nm, arr in bulk.items()})
-            fit.close()
-        last = []
-        for w in range(n_hor):
-            end = self.lag_ + row0[w] + nrow[w]  # rows of the window's response end here in `tot`
-            for c in range(self.chains_):
-                last.append(tot[:end])
         valid = test[n_ahead] if test.shape[0] > n_ahead else None  # y_test.row(step), forecaster.h:802
-        dens, lpl = forecast_density(units, last, n_ahead, self.lag_, self.fit_intercept, self._is_sv,
-                                     np.tile(seed_fc, n_hor), har_trans=self._har(), sv=sv, valid_vec=valid, stable=stable,
-                                     sparse=sparse, device=self._device)
+        C_ = self.chains_
+        # window 0 reuses the existing fit (forecaster.h:799-801)
+        dens0, lpl0 = forecast_density(list(self._chain_records()), [tot[: self.lag_ + nrow[0]]] * C_, n_ahead, self.lag_,
+                                       self.fit_intercept, self._is_sv, seed_fc, har_trans=self._har(), sv=sv, valid_vec=valid,
+                                       stable=stable, sparse=sparse, device=self._device)
+        last0 = np.stack([d[-1].reshape(-1, k) for d in dens0])  # [chain, draw, variable], last step (forecaster.h:803)
+        per_window = [last0]
+        lpls = [lpl0.mean(axis=1)] if lpl0 is not None else None
+        if n_hor > 1:
+            if stable:
+                raise NotImplementedError("stable=True is only available for window 0 / predict() in this build")
+            # windows >= 1: refit + forecast of every (window, chain) in one native call, draws stay on the device
+            packed = self._pack(x_tot, y_tot, seeds[1:], win_row0=row0[1:], win_nrow=nrow[1:], record_mask=0,
+                                lvol_from_init=self._is_sv and expanding, unit_id_base=C_)
+            try:
+                fc, lp = outforecast(packed, tot, n_ahead, self.lag_, seed_fc, har_trans=self._har(), sv=sv, valid_vec=valid,
+                                     sparse=sparse)
+            except _abi.BvharCudaError as e:
+                raise
+            per_window += [fc[w] for w in range(n_hor - 1)]
+            if lpls is not None:
+                lpls += [lp[w] for w in range(n_hor - 1)]
         out = {"forecast": [], "se": [], "lower": [], "upper": []}
         for w in range(n_hor):
-            d = np.concatenate([dens[w * self.chains_ + c][-1:, :].reshape(1, -1, k) for c in range(self.chains_)], axis=1)
-            s = self._summarise(d.reshape(1, -1), k, level, med)  # only the last step is kept (forecaster.h:803)
+            s = self._summarise(per_window[w].reshape(1, -1), k, level, med)  # all chains' draws of the window pooled
             for key in out:
                 out[key].append(s[key])
         res = {key: np.concatenate(v, axis=0) for key, v in out.items()}
-        if lpl is not None:
-            l = lpl.reshape(n_hor, self.chains_, n_ahead).mean(axis=2)  # returnLpl(): mean over steps
+        if lpls is not None:
+            l = np.stack(lpls)  # [window, chain]
             res["lpl"] = np.median(l, axis=1) if med else np.mean(l, axis=1)
         return res
 

@@ -187,6 +187,7 @@ int bvhar_cuda_abi_version(void);
 int bvhar_cuda_device_count(int* count);
 /* sizeof() of the descriptor structs as compiled, so that FFI mirrors can verify their layout. */
 int bvhar_cuda_struct_sizes(int64_t* fit_desc, int64_t* chain_init, int64_t* forecast_desc, int64_t* prior_params);
+int bvhar_cuda_outforecast_params_size(int64_t* bytes);
 
 /* Page-locked host buffers for record / forecast outputs (cudaHostAlloc): device-to-host copies into them run at
  * PCIe speed instead of the pageable staging path.  Optional: every entry point accepts ordinary memory too. */
@@ -254,7 +255,7 @@ typedef struct {
   int32_t sv;       /* SvForecaster `sv` flag (forecaster.h:248-254) */
   int32_t get_lpl;
   int32_t n_draws;  /* draws per unit (after thinning / stability filter) */
-  int32_t reserved;
+  int32_t unit_id_base; /* Philox key word 1 of forecaster u is unit_id_base + u */
   const double* har_trans; /* (3k+1) x (month*k+1) column-major when is_vhar, else NULL */
   /* per unit, column-major n_draws x cols, concatenated over units */
   const double* coef_record;   /* n_draws x (nrow_coef*k + k*include_mean) */
@@ -269,6 +270,33 @@ typedef struct {
 /* out_density: per unit, step x (n_draws*k) column-major (McmcForecaster::predictive_distn,
  * forecaster.h:39); out_lpl: per unit, `step` averages (forecaster.h:83) or NULL. */
 int bvhar_cuda_forecast_density(const bvhar_forecast_desc* desc, double* out_density, double* out_lpl);
+
+/* ---- rolling / expanding out-of-sample forecasts in one call ---------------------------------
+ * Replaces McmcVarforecastRun / McmcVharforecastRun<McmcRollforecastRun | McmcExpandforecastRun, ...>::returnForecast()
+ * (forecaster.h:575-1121; bound by src/triangular.cpp:159-630 roll_* / expand_* and _cta.cpp:40-208) for the windows
+ * of `fit`'s window table: every (window, chain) is refitted (forecaster.h:755-790) and forecast from its own draws
+ * (forecaster.h:798-806) without moving the draws to the host.  Window 0 of the reference reuses an existing fit
+ * (forecaster.h:799-801): the caller passes windows >= 1 here (unit_id_base = n_chains) and forecasts window 0 with
+ * bvhar_cuda_forecast_density. */
+typedef struct {
+  int32_t abi_version;
+  int32_t step;     /* forecast horizon; only the last step is returned (forecaster.h:803) */
+  int32_t var_lag;  /* p, or `month` for VHAR */
+  int32_t is_vhar;
+  int32_t sv;       /* SvForecaster `sv` flag */
+  int32_t get_lpl;
+  int32_t sparse;   /* forecast from the SAVS draws (alpha_sparse / c_sparse / a_sparse) */
+  int32_t reserved;
+  const double* har_trans;      /* (3k+1) x (month*k+1) column-major when is_vhar */
+  const double* y_full;         /* y_rows x k column-major: training + test series the window table was built on */
+  int64_t y_rows;
+  const double* valid_vec;      /* k (y_test.row(step), forecaster.h:802) or NULL */
+  const uint32_t* seed_forecast;/* n_chains (forecaster.h:1028) */
+} bvhar_outforecast_params;
+/* out_forecast: [window][chain][draw * k + variable] (n_windows * n_chains * S * k doubles, S = kept draws);
+ * out_lpl: [window][chain] average log-predictive likelihood over the steps, or NULL. */
+int bvhar_cuda_outforecast_run(const bvhar_fit_desc* fit, const bvhar_outforecast_params* fc, double* out_forecast,
+                               double* out_lpl);
 
 /* ---- fp64 building blocks exported for stage-level parity tests and the roofline bench ---- */
 /* C[M x N] (row-major, ldc) = alpha * A^T B + beta * C with A stored K x M row-major (lda) and

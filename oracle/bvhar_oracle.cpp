@@ -1145,7 +1145,7 @@ static void forecast_unit(const bvhar_forecast_desc* D, int u, bool philox, doub
   const double* sg_rec = sv_model ? D->sigh_record + (size_t)u * S * k : nullptr;
   const double* last = D->last_obs + (size_t)u * p * k;  // p x k col-major, oldest row first
   Rng rng;
-  rng.seed(D->seed[u], (uint32_t)u, philox);
+  rng.seed(D->seed[u], (uint32_t)(D->unit_id_base + u), philox);
   Vec obs(dim_design, 0.0);  // [y_T, y_{T-1}, ..., 1]  fc.h:45-46
   if (mean) obs[dim_design - 1] = 1.0;
   for (int l = 0; l < p; ++l)

@@ -22,7 +22,7 @@ def _declared_symbols():
 def test_header_declares_the_expected_entry_points():
     syms = _declared_symbols()
     for must in ("bvhar_cuda_fit_create", "bvhar_cuda_fit_run", "bvhar_cuda_fit_record", "bvhar_cuda_fit_destroy",
-                 "bvhar_cuda_forecast_density", "bvhar_cuda_last_error"):
+                 "bvhar_cuda_forecast_density", "bvhar_cuda_last_error", "bvhar_cuda_outforecast_run"):
         assert must in syms
 
 

@@ -141,3 +141,34 @@ def test_pinned_output_pool_ownership():
     small = g.record_all("sigh_record")
     assert getattr(small, "_blk", None) is None
     _hostpool.trim()
+
+
+@pytest.mark.parametrize("vhar,sv_model,sparse", [(False, True, False), (True, False, True), (True, True, False)])
+def test_native_outforecast_matches_fit_plus_forecast(vhar, sv_model, sparse):
+    """bvhar_cuda_outforecast_run (refit + forecast of every (window, chain) in one call, draws kept on the device)
+    equals fit_run -> records -> bvhar_cuda_forecast_density on the same window table, bit for bit."""
+    import problems as pr
+    from bvhar_b200._abi import PackedFit
+    from bvhar_b200._design import build_vhar
+    from bvhar_b200._engine import CudaFit, forecast_density, outforecast
+    wins = [(1, 40), (2, 40), (3, 40)]
+    kw, meta = pr.make_problem(prior="Horseshoe", sv=sv_model, dim=3, T=60, vhar=vhar, week=2, month=4, chains=2, iters=8, burn=2,
+                               thin=2, windows=wins)
+    kw["unit_id_base"] = 2
+    if sv_model:
+        kw["lvol_from_init"] = False
+    lag = 4 if vhar else 2
+    har = build_vhar(3, 2, 4, True) if vhar else None
+    y = meta["y"]
+    valid = y[-1] * 1.1
+    seed_fc = [5, 6]
+    fc, lpl = outforecast(PackedFit(**kw), y, 3, lag, seed_fc, har_trans=har, valid_vec=valid, sparse=sparse)
+    assert fc.shape == (3, 2, 3, 3) and lpl.shape == (3, 2)
+    g = CudaFit(PackedFit(**kw)); g.run()
+    units = [g.records(w, c) for w in range(3) for c in range(2)]
+    last = [y[: lag + r0 + n] for (r0, n) in wins for _ in range(2)]
+    dens, lp = forecast_density(units, last, 3, lag, True, sv_model, np.tile(seed_fc, 3), har_trans=har, valid_vec=valid,
+                                sparse=sparse, unit_id_base=2)
+    for u in range(6):
+        assert np.array_equal(dens[u][-1].reshape(3, 3), fc[u // 2, u % 2])
+    np.testing.assert_allclose(lp.mean(axis=1).reshape(3, 2), lpl, rtol=1e-12)
