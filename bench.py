@@ -104,6 +104,43 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
 
 
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of the G1 launch from the committed `ncu --set full` capture
+    (profiles/r01_gram_traffic.json: same workload, 1 024 chains), or None."""
+    p = os.path.join(ROOT, "profiles", "r01_gram_traffic.json")
+    try:
+        with open(p) as f:
+            return json.load(f)["traffic_bytes_per_launch"]
+    except Exception:
+        return None
+
+
+def roll_metric(device, n_windows=32, chains=4, iters=12, burn=4):
+    """forecast_roll() on BASELINE config C4 (synthetic 50-variable VAR(4), NG prior + SV, 4 chains per window), a bounded
+    sample of the 2 000 windows: every (window, chain) refitted and forecast one step ahead through the native
+    out-of-sample runner, host buffers in, forecast draws out.  windows/s scales as 1 / iters, so the sweep rate is
+    reported too, and windows/s is extrapolated to the 1 000-iteration setting of SURVEY.md section 8(d)."""
+    from bvhar_b200 import _spec as sp
+    from bvhar_b200 import datasets
+    from bvhar_b200._engine import outforecast
+    from bvhar_b200.model import VarBayes
+    y = datasets.simulate_var_sv(404 + n_windows, 50, 4)
+    m = VarBayes(y[:404], 4, chains, iters, burn, 1, sp.NgConfig(), sp.SvConfig(), seed=1, device=device)
+    x_tot, y_tot = m._design_of(y)
+    n0 = m.response_.shape[0]
+    pk = m._pack(x_tot, y_tot, m._seeds(n_windows, chains), win_row0=list(range(1, n_windows + 1)), win_nrow=[n0] * n_windows,
+                 record_mask=0, unit_id_base=chains)
+    outforecast(pk, y, 1, 4, m._seeds(chains))  # warm-up (module load, memory pools)
+    t0 = time.perf_counter()
+    fc, _ = outforecast(pk, y, 1, 4, m._seeds(chains))
+    dt = time.perf_counter() - t0
+    assert np.all(np.isfinite(fc))
+    return {"metric": "forecast_roll_windows_per_s", "config": f"C4 sample: {n_windows} rolling windows x {chains} chains, k=50 d=201 n=400, "
+            f"NG prior + SV, {iters} sweeps per refit ({burn} burn-in), 1-step forecast", "value": n_windows / dt, "unit": "windows/s",
+            "seconds": dt, "unit_sweeps_per_s": n_windows * chains * iters / dt,
+            "windows_per_s_at_1000_iters": n_windows * iters / dt / 1000.0, "path": "bvhar_cuda_outforecast_run (end to end, host buffers)"}
+
+
 def cpu_arm(mode_faithful: bool, chains: int, sweeps: int, warm: int, threads: int = 0):
     """Time the CPU oracle on a bounded sample of the same workload; returns chain-sweeps/s."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
@@ -153,6 +190,7 @@ def main():
     ap.add_argument("--prior", default="DL")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-roll", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = max(args.warmup, 1) if args.impl == "reference" else 3
@@ -265,13 +303,20 @@ def main():
     roofline = {
         "kernel": "dgemm_tn_kernel (G1: S = Dinv' XX, SV-weighted Gram of every (chain, equation))",
         "bound": "tensor", "achieved": achieved, "peak": cublas_peak, "unit": "TFLOP/s",
-        "frac": achieved / cublas_peak if achieved else None, "traffic": None,
+        "frac": achieved / cublas_peak if achieved else None, "traffic": ncu_traffic(),
         "peak_source": "fp64 is absent from MEASURED_PEAKS.json: cuBLAS DGEMM 8192^3 measured in this run (burst, best of 3); "
                        f"DMMA issue peak {dmma_peak:.1f} TFLOP/s; HBM {peaks.get('hbm_gbs')} GB/s ({peak_src})",
         "algorithmic_flops_per_launch": args.chains * fl["gram"], "avg_launch_ms": g_avg_ms,
         "share_of_step": g_ms / tot_prof_ms if tot_prof_ms > 0 else None,
         "kernel_ms_per_step": {nm: v[1] / K for nm, v in prof.items()},
     }
+    # ---- second metric of BASELINE.json: forecast_roll windows/s (C4, bounded sample) --------------
+    roll = None
+    if world == 1 and not args.no_roll:
+        try:
+            roll = roll_metric(local)
+        except Exception as e:  # the headline line must still be printed
+            roll = {"error": str(e)[:200]}
     cpu = None
     if not args.no_cpu_baseline:
         ncpu = os.cpu_count() or 1
@@ -290,7 +335,7 @@ def main():
                    "timed_path": "CUDA graph replay of the sweep; roofline from a second pass with per-kernel events"},
         "algorithmic_gflop_per_step": args.chains * fl["total"] / 1e9,
         "sustained_tflops_algorithmic": world * args.chains * fl["total"] * K / (ms * 1e-3) / 1e12,
-        "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu,
+        "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu, "forecast_roll": roll,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
