@@ -147,13 +147,18 @@ def cpu_arm(mode_faithful: bool, chains: int, sweeps: int, warm: int, threads: i
     import binding as ob  # test infrastructure; only this baseline leg of bench.py may use it
     m = build_model(chains, 10, 0, seed=7, device=0)
     pk = m._pack(m.design_, m.response_, m._seeds(1, chains))
+    if threads == 0:  # every host core this process may use (torchrun exports OMP_NUM_THREADS=1: do not rely on it)
+        try:
+            threads = len(os.sched_getaffinity(0))
+        except AttributeError:
+            threads = os.cpu_count() or 1
     f = ob.OracleFit(pk, faithful=mode_faithful, threads=threads)
     if warm:
         f.step(warm, False)
     t0 = time.perf_counter()
     f.step(sweeps, False)
     dt = time.perf_counter() - t0
-    cores = ob.lib().oracle_max_threads() if threads == 0 else threads
+    cores = threads
     f.close()
     return chains * sweeps / dt, cores, dt
 
@@ -320,8 +325,12 @@ def main():
     cpu = None
     if not args.no_cpu_baseline:
         ncpu = os.cpu_count() or 1
-        vf, cores, dtf = cpu_arm(True, 2, 3, 1)
-        ve, _, _ = cpu_arm(False, max(ncpu, 8), 3, 1)
+        # in a fresh process (this one carries torch's / CUDA's thread pools), exactly as the --impl reference arm runs it
+        env = {k2: v2 for k2, v2 in os.environ.items() if k2 not in ("OMP_NUM_THREADS", "RANK", "WORLD_SIZE", "LOCAL_RANK")}
+        out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "3", "--warmup", "1"],
+                             capture_output=True, text=True, env=env, timeout=900).stdout.strip().splitlines()[-1]
+        ref = json.loads(out)
+        vf, cores, ve = ref["value"], ref["cpu_baseline"]["cores"], ref["cpu_baseline"]["value_efficient_formulation"]
         cpu = {"value": vf, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": "2 chains x 3 sweeps after 1 warm-up of the same workload, reference-faithful formulation "
                          "(Kronecker design, dense n x n SV precision), all host threads; hand-written loops, no BLAS",
