@@ -89,7 +89,8 @@ struct bvhar_fit {
   int device = 0;
   int num_iter = 0, num_burn = 0, thin = 1;
   uint32_t rec_mask = 0;
-  cudaStream_t st = nullptr;
+  cudaStream_t st = nullptr, s2 = nullptr, s3 = nullptr;
+  cudaEvent_t evf[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   cudaGraphExec_t graph[2] = {nullptr, nullptr};
   double last_ms = 0.0;
@@ -106,7 +107,7 @@ struct bvhar_fit {
   DevBuf<long long> d_off, g1_b, g1_c, g2_b, g2_c, g3_a, g3_b, g3_y;
   DevBuf<uint32_t> seeds, iter;
   DevBuf<double> H, Z, Dinv, YLD, S, Cm, Acoef, alpha, cvec, prec, contem, L, chol_prec, sparse_coef, sparse_contem;
-  DevBuf<double> lvol_init, lvol_sig, diag, znorm, hN[4], hG[3], hq[4], hs, vscratch, pscratch, gscratch, Pfac, hscr;
+  DevBuf<double> lvol_init, lvol_sig, diag, znorm, hN[4], hG[3], hq[4], hs, vscratch, pscratch, gscratch, Pfac, hscr, Qn;
   bool coef_v2 = false, coef_big = false;
   std::map<std::string, std::unique_ptr<DevBuf<double>>> rec;
   std::vector<RecordSpec> rec_order;
@@ -147,6 +148,9 @@ struct bvhar_fit {
       if (g) cudaGraphExecDestroy(g);
     for (auto& pe : prof_pending) { cudaEventDestroy(pe.a); cudaEventDestroy(pe.b); }
     for (auto& e : prof_pool) cudaEventDestroy(e);
+    for (auto& e : evf) if (e) cudaEventDestroy(e);
+    if (s2) cudaStreamDestroy(s2);
+    if (s3) cudaStreamDestroy(s3);
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
     if (st) cudaStreamDestroy(st);
@@ -162,25 +166,39 @@ struct bvhar_fit {
       if (profiling) { cudaEventRecord(eb__, st); prof_pending.push_back({prof_id(name), ea__, eb__}); } \
       ++nl;                                                                    \
     } while (0)
+    // Independent updaters run on side streams (parallel branches of the captured graph): the prior hyper-parameter
+    // kernels (stages 1 and 5 read only the PREVIOUS sweep's coefficients) overlap the SV weights + Gram contractions,
+    // and the small G2 contraction fills the tail of G1.  Per-kernel profiling keeps everything on one stream.
+    const bool fork = !profiling && s2 && s3;
+    cudaStream_t sp = fork ? s2 : st, sg = fork ? s3 : st;
     LAUNCH("bump", launch_bump(P, 1, 0, st));
-    if (D.prior != 1) LAUNCH("prior_coef", launch_prior(D, P, PC, 0, st));
+    if (fork) { CU(cudaEventRecord(evf[0], st)); CU(cudaStreamWaitEvent(s2, evf[0], 0)); }
+    if (D.prior != 1) {
+      LAUNCH("prior_coef", launch_prior(D, P, PC, 0, sp));
+      LAUNCH("prior_contem", launch_prior(D, P, PC, 1, sp));
+    }
+    if (fork) CU(cudaEventRecord(evf[1], s2));
     if (D.sv) {
       LAUNCH("sv_prep", launch_sv_prep(D, P, st));
+      if (fork) { CU(cudaEventRecord(evf[2], st)); CU(cudaStreamWaitEvent(s3, evf[2], 0)); }
+      LAUNCH("gram_C_dmma", launch_dgemm_tn(g2, sg));
+      if (fork) CU(cudaEventRecord(evf[3], s3));
       LAUNCH("gram_S_dmma", launch_dgemm_tn(g1, st));
-      LAUNCH("gram_C_dmma", launch_dgemm_tn(g2, st));
     }
     if (coef_big) {
-      if (D.sv) LAUNCH("coef_pbuild", launch_coef_v2(0, D, P, Pfac.p, smem_limit, st));
+      if (D.sv) LAUNCH("coef_pbuild", launch_coef_v2(0, D, P, Pfac.p, Qn.p, smem_limit, st));
+      if (fork) { CU(cudaStreamWaitEvent(st, evf[1], 0)); if (D.sv) CU(cudaStreamWaitEvent(st, evf[3], 0)); }
       LAUNCH("coef_chol_cta", launch_coef_big(1, D, P, Pfac.p, hscr.p, smem_limit, st));
       LAUNCH("coef_seq_big", launch_coef_big(2, D, P, Pfac.p, hscr.p, smem_limit, st));
     } else if (coef_v2) {
-      if (D.sv) LAUNCH("coef_pbuild", launch_coef_v2(0, D, P, Pfac.p, smem_limit, st));
-      LAUNCH("coef_chol", launch_coef_v2(1, D, P, Pfac.p, smem_limit, st));
-      LAUNCH("coef_seq", launch_coef_v2(2, D, P, Pfac.p, smem_limit, st));
+      if (D.sv) LAUNCH("coef_pbuild", launch_coef_v2(0, D, P, Pfac.p, Qn.p, smem_limit, st));
+      if (fork) { CU(cudaStreamWaitEvent(st, evf[1], 0)); if (D.sv) CU(cudaStreamWaitEvent(st, evf[3], 0)); }
+      LAUNCH("coef_chol", launch_coef_v2(1, D, P, Pfac.p, Qn.p, smem_limit, st));
+      LAUNCH("coef_seq", launch_coef_v2(2, D, P, Pfac.p, Qn.p, smem_limit, st));
     } else {
+      if (fork) { CU(cudaStreamWaitEvent(st, evf[1], 0)); if (D.sv) CU(cudaStreamWaitEvent(st, evf[3], 0)); }
       LAUNCH("coef_draw", launch_coef(D, P, vscratch.p, pscratch.p, smem_limit, st));
     }
-    if (D.prior != 1) LAUNCH("prior_contem", launch_prior(D, P, PC, 1, st));
     LAUNCH("latent_dmma", launch_dgemm_tn(g3, st));
     if (D.k > 1) LAUNCH("impact_draw", launch_impact(D, P, gscratch.p, st));
     if (D.sv) {
@@ -566,6 +584,10 @@ int build(const bvhar_fit_desc* d, bvhar_fit** out) {
 
   CU(cudaStreamCreateWithFlags(&F->st, cudaStreamNonBlocking));
   CU(cudaEventCreate(&F->ev0)); CU(cudaEventCreate(&F->ev1));
+  if (getenv("BVHAR_NO_FORK") == nullptr) {
+    CU(cudaStreamCreateWithFlags(&F->s2, cudaStreamNonBlocking)); CU(cudaStreamCreateWithFlags(&F->s3, cudaStreamNonBlocking));
+    for (auto& e : F->evf) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  }
   CU(cudaDeviceSynchronize());  // uploads / memsets were ordered on stream 0; the setup kernels below run on F->st
 
   // ---- contraction descriptors ----
@@ -602,6 +624,7 @@ int build(const bvhar_fit_desc* d, bvhar_fit** out) {
   if (F->coef_big) F->coef_v2 = false;
   if (F->coef_v2 || F->coef_big) CU(F->Pfac.alloc((size_t)U * k * D.ldS));
   if (F->coef_big) CU(F->hscr.alloc((size_t)U * k * dd));
+  if (F->coef_v2 && coef_pipe_fits(D, F->smem_limit) && getenv("BVHAR_COEF_NOPIPE") == nullptr) CU(F->Qn.alloc((size_t)U * k * D.ldS));
   if (!F->coef_v2 && !F->coef_big && !coef_plan(D, F->smem_limit, &ch_plan, &need_v, &need_p))
     return fail(BVHAR_ERR_UNSUPPORTED, "dim_design too large for the shared-memory Cholesky of this build (packed d(d+1)/2 doubles must fit 227 KB)");
   if (need_v) CU(F->vscratch.alloc((size_t)U * 2 * k * dd));
@@ -1073,13 +1096,13 @@ int bvhar_cuda_fit_run_stage(bvhar_fit* fit, int stage, int iter) {
     case 4:
       if (D.sv) { CU(launch_dgemm_tn(fit->g1, fit->st)); CU(launch_dgemm_tn(fit->g2, fit->st)); }
       if (fit->coef_big) {
-        if (D.sv) CU(launch_coef_v2(0, D, fit->P, fit->Pfac.p, fit->smem_limit, fit->st));
+        if (D.sv) CU(launch_coef_v2(0, D, fit->P, fit->Pfac.p, fit->Qn.p, fit->smem_limit, fit->st));
         CU(launch_coef_big(1, D, fit->P, fit->Pfac.p, fit->hscr.p, fit->smem_limit, fit->st));
         CU(launch_coef_big(2, D, fit->P, fit->Pfac.p, fit->hscr.p, fit->smem_limit, fit->st));
       } else if (fit->coef_v2) {
-        CU(launch_coef_v2(0, D, fit->P, fit->Pfac.p, fit->smem_limit, fit->st));
-        CU(launch_coef_v2(1, D, fit->P, fit->Pfac.p, fit->smem_limit, fit->st));
-        CU(launch_coef_v2(2, D, fit->P, fit->Pfac.p, fit->smem_limit, fit->st));
+        CU(launch_coef_v2(0, D, fit->P, fit->Pfac.p, fit->Qn.p, fit->smem_limit, fit->st));
+        CU(launch_coef_v2(1, D, fit->P, fit->Pfac.p, fit->Qn.p, fit->smem_limit, fit->st));
+        CU(launch_coef_v2(2, D, fit->P, fit->Pfac.p, fit->Qn.p, fit->smem_limit, fit->st));
       } else {
         CU(launch_coef(D, fit->P, fit->vscratch.p, fit->pscratch.p, fit->smem_limit, fit->st));
       }

@@ -12,7 +12,8 @@ cudaError_t launch_coef(const Dims& D, const DevPtrs& P, double* vscratch, doubl
 cudaError_t launch_draw_coef_batched(long long batch, int d, const double* Pp, const double* b, const double* z, double* out,
                                      cudaStream_t st);
 bool coef_v2_fits(const Dims& D, size_t smem_limit);
-cudaError_t launch_coef_v2(int part, const Dims& D, const DevPtrs& P, double* Pfac, size_t smem_limit, cudaStream_t st);
+bool coef_pipe_fits(const Dims& D, size_t smem_limit);
+cudaError_t launch_coef_v2(int part, const Dims& D, const DevPtrs& P, double* Pfac, double* Qn, size_t smem_limit, cudaStream_t st);
 cudaError_t launch_coef_chol_nc1(const Dims& D, const DevPtrs& P, double* Pfac, size_t smem_limit, cudaStream_t st);
 cudaError_t launch_coef_chol_nc2(const Dims& D, const DevPtrs& P, double* Pfac, size_t smem_limit, cudaStream_t st);
 cudaError_t launch_coef_chol_nc4(const Dims& D, const DevPtrs& P, double* Pfac, size_t smem_limit, cudaStream_t st);

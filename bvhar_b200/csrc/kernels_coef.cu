@@ -29,8 +29,10 @@ namespace {
 // weights held in registers as A fragments for the whole kernel and the B fragments S_i[p] loaded straight
 // from global memory (each S element is read exactly once, each P element written once: HBM-bound).
 // MT = ceil(k / 8) row tiles (j), KS = ceil(k / 4) k-steps (i).
+// With Qn != nullptr it also emits the cross matrices Q_j = sum_{i>=j+1} L_{i,j+1} L_ij S_i (slot j of Qn): Q_j delta_j is
+// the only part of equation j+1's right-hand side that depends on equation j's draw (coef_seq_pipe_kernel).
 template <int MT, int KS>
-__global__ void __launch_bounds__(256) coef_pbuild_kernel(const Dims D, const DevPtrs P, double* __restrict__ Pfac) {
+__global__ void __launch_bounds__(256) coef_pbuild_kernel(const Dims D, const DevPtrs P, double* __restrict__ Pfac, double* __restrict__ Qn) {
   const int u = blockIdx.x, k = D.k;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int fr = lane >> 2, fc = lane & 3;
@@ -45,6 +47,15 @@ __global__ void __launch_bounds__(256) coef_pbuild_kernel(const Dims D, const De
       const double l = (i < k && j <= i) ? Lu[i * k + j] : 0.0;
       af[mt][ks] = l * l;
     }
+  double aq[MT][KS];  // A2[m = j][kk = i] = L_{i,j+1} L_ij for i >= j + 1
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+      const int j = 8 * (mtb + mt) + fr, i = 4 * ks + fc;
+      aq[mt][ks] = (Qn && i < k && j + 1 <= i) ? Lu[i * k + j] * Lu[i * k + j + 1] : 0.0;
+    }
+  double* Qu = Qn ? Qn + (size_t)u * k * D.ldS : nullptr;
   const double* Su = P.S + (size_t)u * k * D.ldS;
   double* Pu = Pfac + (size_t)u * k * D.ldS;
   const int ntiles = (D.Pp + 7) / 8;
@@ -69,6 +80,12 @@ __global__ void __launch_bounds__(256) coef_pbuild_kernel(const Dims D, const De
         const int j = 8 * (mtb + mt) + fr;
         if (j < k && p < D.Pp) {  // ldS is even and p is even: 16-byte aligned pair inside the padded row
           *reinterpret_cast<double2*>(Pu + (size_t)j * D.ldS + p) = make_double2(c0, c1);
+        }
+        if (Qu) {  // warp-uniform
+          double q0 = 0.0, q1 = 0.0;
+#pragma unroll
+          for (int ks = 0; ks < KS; ++ks) dmma_m8n8k4(q0, q1, aq[mt][ks], bf[q][ks]);
+          if (j + 1 < k && p < D.Pp) *reinterpret_cast<double2*>(Qu + (size_t)j * D.ldS + p) = make_double2(q0, q1);
         }
       }
     }
@@ -234,22 +251,181 @@ __global__ void __launch_bounds__(SEQ_THREADS) coef_seq_kernel(const Dims D, con
   }
 }
 
+// ---- B' (SV): the same sequential part, software-pipelined across equations ------------------------------------
+// Only Q_j delta_j, with Q_j = sum_{i>=j+1} L_{i,j+1} L_ij S_i precomputed by coef_pbuild_kernel, separates the solve of
+// equation j from the solve of equation j + 1:
+//     r_{j+1} = rbase_{j+1} - Q_j delta_j,   rbase_{j+1} = prec o (mean - a_{j+1}) + sum_{i>=j+1} L_{i,j+1} h_i^{(lag)}
+// where h^{(lag)} carries the updates of delta_0 .. delta_{j-1} only.  So while warp 0 solves equation j, warps 1..7
+// apply delta_{j-1} to the h_i (k-j-1 products S_i delta from L2), build rbase_{j+1} and prefetch the next factor and the
+// next Q; the critical path per equation is one 15 KB shared-memory matvec plus the solve.
+constexpr int PIPE_WORKERS = SEQ_THREADS - 32;  // threads of warps 1..7
+__device__ __forceinline__ void worker_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(PIPE_WORKERS)); }
+
+__host__ __device__ inline size_t coef_pipe_smem_doubles(int k, int d, int ppad) {
+  return 4 * (size_t)ppad + 3 * (size_t)k * d + (size_t)k * k + 6 * (size_t)d + (size_t)(SEQ_THREADS / 32) * d + 8;
+}
+
+template <int NC>
+__global__ void __launch_bounds__(SEQ_THREADS) coef_seq_pipe_kernel(const Dims D, const DevPtrs P, const double* __restrict__ Pfac,
+                                                                     const double* __restrict__ Qn) {
+  extern __shared__ __align__(16) double sm[];
+  const int u = blockIdx.x, w = u / D.C, c = u % D.C;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+  const int k = D.k, d = D.d, ldM = D.ldM;
+  const int ppad = D.ldS;
+  double* Lc = sm;                          // [2][ppad] Cholesky factor of equation j / j + 1
+  double* Qc = Lc + 2 * (size_t)ppad;       // [2][ppad] Q_{j-1} / Q_j
+  double* h = Qc + 2 * (size_t)ppad;        // [k][d]
+  double* Asm = h + (size_t)k * d;          // [k][d]
+  double* zall = Asm + (size_t)k * d;       // [k][d]
+  double* Lsm = zall + (size_t)k * d;       // [k][k]
+  double* rv = Lsm + k * k;                 // [d] right-hand side of the current equation
+  double* rbase = rv + d;                   // [2][d]
+  double* dl = rbase + 2 * d;               // [2][d] delta_j (even / odd equations)
+  double* wscr = dl + 2 * d + d;            // [nw][d]
+  const Philox rng(P.seeds[u], (uint32_t)(D.ubase + u), *P.iter);
+  double* Ac = P.Acoef + (size_t)w * d * ldM + (size_t)c * k;
+  const double* prec_u = P.prec + (size_t)u * k * d;
+  const double* xn = P.xnorm + (size_t)w * d;
+
+  auto prefetch = [&](const double* src, double* dst, int t0, int nthr) {
+    for (int p = 2 * t0; p < ppad; p += 2 * nthr) cp_async16(dst + p, src + p, 16);
+  };
+  prefetch(Pfac + ((size_t)u * k) * D.ldS, Lc, tid, SEQ_THREADS);
+  cp_async_commit();
+
+  for (int e = tid; e < k * k; e += blockDim.x) Lsm[e] = P.L[(size_t)u * k * k + e];
+  for (int e = tid; e < d * k; e += blockDim.x) {
+    const int a = e / k, m = e - a * k;
+    Asm[m * d + a] = Ac[(size_t)a * ldM + m];
+  }
+  for (int e = tid; e < (k * d + 1) / 2; e += blockDim.x) {
+    double z0, z1;
+    rng.normal_pair(ST_COEF_Z, (uint32_t)e, 0, z0, z1);
+    zall[2 * e] = z0;
+    if (2 * e + 1 < k * d) zall[2 * e + 1] = z1;
+  }
+  __syncthreads();
+  for (int i = warp; i < k; i += nw) {  // h_i = C_i - S_i v_i, v_i = A L_i'
+    double* v = wscr + (size_t)warp * d;
+    for (int a = lane; a < d; a += 32) {
+      double sacc = 0.0;
+      for (int m = 0; m <= i; ++m) sacc = fma(Lsm[i * k + m], Asm[m * d + a], sacc);
+      v[a] = sacc;
+    }
+    __syncwarp();
+    double out[NC];
+    symv_packed_warp<NC>(P.S + ((size_t)u * k + i) * D.ldS, v, d, out);
+#pragma unroll
+    for (int sidx = 0; sidx < NC; ++sidx) {
+      const int b = lane + 32 * sidx;
+      if (b < d) h[(size_t)i * d + b] = P.Cm[((size_t)u * k + i) * D.ldX + b] - out[sidx];
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  for (int a = tid; a < d; a += blockDim.x) {  // rbase_0
+    double acc = prec_u[a] * (P.prior_mean[a] - Asm[a]);
+    for (int i = 0; i < k; ++i) acc = fma(Lsm[i * k], h[(size_t)i * d + a], acc);
+    rbase[a] = acc;
+  }
+  // threads-per-row of the shared-memory matvec (power of two, tpr * d <= 256)
+  int tpr = 1;
+  while (tpr < 8 && 2 * tpr * d <= SEQ_THREADS) tpr <<= 1;
+
+  for (int j = 0; j < k; ++j) {
+    cp_async_wait<0>();
+    __syncthreads();  // factor j and Q_{j-1} landed; delta_{j-1}, rbase_j, Asm of the previous equation are final
+    // ---- phase A (all warps): r_j = rbase_j - Q_{j-1} delta_{j-1}
+    {
+      const double* Qp = Qc + (size_t)((j - 1) & 1) * ppad;
+      const double* dprev = dl + (size_t)((j - 1) & 1) * d;
+      const double* rb = rbase + (size_t)(j & 1) * d;
+      const int a = tid / tpr, sub = tid - a * tpr;
+      double acc = 0.0;
+      if (j > 0 && a < d) {
+        const int ra = a * (a + 1) / 2;
+        for (int b = sub; b < d; b += tpr) acc = fma(b <= a ? Qp[ra + b] : Qp[b * (b + 1) / 2 + a], dprev[b], acc);
+      }
+      for (int o = tpr >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (sub == 0 && a < d) rv[a] = rb[a] - acc;
+    }
+    __syncthreads();
+    // ---- phase B
+    double* dcur = dl + (size_t)(j & 1) * d;
+    if (warp == 0) {
+      precision_solve_blocked<NC>(Lc + (size_t)(j & 1) * ppad, d, rv, zall + (size_t)j * d, dcur);
+    } else {
+      const int wt = tid - 32;  // 0 .. PIPE_WORKERS-1
+      if (j + 1 < k) {
+        prefetch(Pfac + ((size_t)u * k + j + 1) * D.ldS, Lc + (size_t)((j + 1) & 1) * ppad, wt, PIPE_WORKERS);
+        prefetch(Qn + ((size_t)u * k + j) * D.ldS, Qc + (size_t)(j & 1) * ppad, wt, PIPE_WORKERS);
+      }
+      cp_async_commit();
+      if (j > 0) {  // h_i -= L_{i,j-1} S_i delta_{j-1}, i >= j + 1
+        const double* dprev = dl + (size_t)((j - 1) & 1) * d;
+        for (int i = j + 1 + (warp - 1); i < k; i += nw - 1) {
+          double out[NC];
+          symv_packed_warp<NC>(P.S + ((size_t)u * k + i) * D.ldS, dprev, d, out);
+          const double lij = Lsm[i * k + j - 1];
+#pragma unroll
+          for (int sidx = 0; sidx < NC; ++sidx) {
+            const int b = lane + 32 * sidx;
+            if (b < d) h[(size_t)i * d + b] = fma(-lij, out[sidx], h[(size_t)i * d + b]);
+          }
+        }
+      }
+      worker_barrier();
+      if (j + 1 < k) {  // rbase_{j+1} from h^{(lag)} (delta_j not applied: it enters through Q_j in the next phase A)
+        double* rb = rbase + (size_t)((j + 1) & 1) * d;
+        for (int a = wt; a < d; a += PIPE_WORKERS) {
+          double acc = prec_u[(j + 1) * d + a] * (P.prior_mean[(j + 1) * d + a] - Asm[(j + 1) * d + a]);
+          for (int i = j + 1; i < k; ++i) acc = fma(Lsm[i * k + j + 1], h[(size_t)i * d + a], acc);
+          rb[a] = acc;
+        }
+      }
+    }
+    __syncthreads();
+    for (int a = tid; a < d; a += blockDim.x) {
+      const double val = Asm[j * d + a] + dcur[a];
+      Asm[j * d + a] = val;
+      Ac[(size_t)a * ldM + j] = val;
+      double pen = 0.0;
+      if (a < D.nrow) {
+        P.alpha[(size_t)u * D.N + j * D.nrow + a] = val;
+        pen = P.own_flag[j * D.nrow + a] ? 0.0 : 1.0;
+      } else {
+        P.cvec[(size_t)u * k + j] = val;
+      }
+      const double fit = fabs(val) * xn[a];  // draw_mn_savs, draw.h:417-430
+      P.sparse_coef[(size_t)u * d * k + j * d + a] = val * fmax(fit - pen / (val * val), 0.0) / fit;
+    }
+  }
+}
+
 template <bool SV, int NC>
-cudaError_t launch_part(int part, const Dims& D, const DevPtrs& P, double* Pfac, size_t smem_limit, cudaStream_t st) {
+cudaError_t launch_part(int part, const Dims& D, const DevPtrs& P, double* Pfac, double* Qn, size_t smem_limit, cudaStream_t st) {
   const int k = D.k, d = D.d;
   const size_t ppad = (D.Pp + 1) & ~1;
   if (part == 0) {
     if (!SV) return cudaSuccess;
     const dim3 grid(D.U, 4);
-    if (k <= 8) coef_pbuild_kernel<1, 2><<<grid, 256, 0, st>>>(D, P, Pfac);
-    else if (k <= 16) coef_pbuild_kernel<2, 4><<<grid, 256, 0, st>>>(D, P, Pfac);
-    else if (k <= 24) coef_pbuild_kernel<3, 6><<<grid, 256, 0, st>>>(D, P, Pfac);
-    else if (k <= 32) coef_pbuild_kernel<4, 8><<<grid, 256, 0, st>>>(D, P, Pfac);
-    else if (k <= 64) coef_pbuild_kernel<4, 16><<<dim3(D.U, 4, 2), 256, 0, st>>>(D, P, Pfac);
+    if (k <= 8) coef_pbuild_kernel<1, 2><<<grid, 256, 0, st>>>(D, P, Pfac, Qn);
+    else if (k <= 16) coef_pbuild_kernel<2, 4><<<grid, 256, 0, st>>>(D, P, Pfac, Qn);
+    else if (k <= 24) coef_pbuild_kernel<3, 6><<<grid, 256, 0, st>>>(D, P, Pfac, Qn);
+    else if (k <= 32) coef_pbuild_kernel<4, 8><<<grid, 256, 0, st>>>(D, P, Pfac, Qn);
+    else if (k <= 64) coef_pbuild_kernel<4, 16><<<dim3(D.U, 4, 2), 256, 0, st>>>(D, P, Pfac, Qn);
     else coef_pbuild_generic_kernel<<<D.U, 256, 0, st>>>(D, P, Pfac);
   } else if (part == 1) {
     return launch_coef_chol(NC, D, P, Pfac, smem_limit, st);
   } else {
+    if (SV && Qn) {
+      const size_t smp = coef_pipe_smem_doubles(k, d, D.ldS) * sizeof(double);
+      if (smp > smem_limit) return cudaErrorInvalidConfiguration;
+      cudaFuncSetAttribute(coef_seq_pipe_kernel<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smp);
+      coef_seq_pipe_kernel<NC><<<D.U, SEQ_THREADS, smp, st>>>(D, P, Pfac, Qn);
+      return cudaGetLastError();
+    }
     const size_t sm3 = coef_seq_smem_doubles<SV>(k, d, D.ldS) * sizeof(double);
     if (sm3 > smem_limit) return cudaErrorInvalidConfiguration;
     cudaFuncSetAttribute(coef_seq_kernel<SV, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm3);
@@ -268,10 +444,15 @@ bool coef_v2_fits(const Dims& D, size_t smem_limit) {
 }
 
 // part 0: P build (SV only), 1: batched Cholesky, 2: sequential draws
-cudaError_t launch_coef_v2(int part, const Dims& D, const DevPtrs& P, double* Pfac, size_t smem_limit, cudaStream_t st) {
+bool coef_pipe_fits(const Dims& D, size_t smem_limit) {
+  // two CTAs per SM keep the chain latency hidden: use the pipelined kernel only while two of them fit
+  return D.sv && D.k > 1 && D.k <= 64 && D.d <= 128 && 2 * coef_pipe_smem_doubles(D.k, D.d, D.ldS) * sizeof(double) <= smem_limit;
+}
+
+cudaError_t launch_coef_v2(int part, const Dims& D, const DevPtrs& P, double* Pfac, double* Qn, size_t smem_limit, cudaStream_t st) {
   const int nc = (D.d + 31) / 32;
 #define BV_DISPATCH(NCV)                                                                                  \
-  return D.sv ? launch_part<true, NCV>(part, D, P, Pfac, smem_limit, st) : launch_part<false, NCV>(part, D, P, Pfac, smem_limit, st)
+  return D.sv ? launch_part<true, NCV>(part, D, P, Pfac, Qn, smem_limit, st) : launch_part<false, NCV>(part, D, P, Pfac, Qn, smem_limit, st)
   if (nc <= 1) BV_DISPATCH(1);
   if (nc <= 2) BV_DISPATCH(2);
   if (nc <= 4) BV_DISPATCH(4);

@@ -134,10 +134,10 @@ __device__ __forceinline__ void chol_blocked_warp(double* Pk, int d, int* bad) {
 
 // out (lane-distributed: element b = lane + 32 c in out[c]) = S x, S packed lower (row-major packed) in
 // global memory, x in shared memory.  NC = ceil(d / 32).
-// Rows are taken in blocks of 32.  Within a block, lane b accumulates the row partials S_ab x_b in registers
-// (part[r], static indices) and its own column contribution S_ab x_a, with the loads of 8 rows in flight at
-// a time; ONE butterfly reduce-scatter per block (31 shuffles for 32 rows instead of 5 per row) then leaves
-// the total of row 32 rb + l on lane l.
+// Rows are taken 16 at a time with ALL their loads in flight together (16 (rb + 1) independent 8-byte loads per
+// lane: the product is latency-bound, S comes from L2 / HBM).  Lane b accumulates the row partials S_ab x_b in
+// registers (part[r], static indices) and its own column contribution S_ab x_a; one butterfly reduce-scatter per
+// 16 rows (16 shuffles instead of 5 per row) leaves the total of row 16 g + (l & 15) on lanes l and l ^ 16.
 // With (first, step) a warp takes only the 32-row blocks rb = first, first + step, ... (its `out` is then a partial
 // result to be summed over the cooperating warps).
 template <int NC>
@@ -156,14 +156,14 @@ __device__ __forceinline__ void symv_packed_warp(const double* __restrict__ S, c
   for (int rb = 0; rb < NC; ++rb) {
     if (32 * rb >= d) break;
     if (step > 1 && (rb % step) != first) continue;  // warp-uniform
-    double part[32];
-    constexpr int RB = 8;
 #pragma unroll
-    for (int r0 = 0; r0 < 32; r0 += RB) {
-      double s[RB][NC];
+    for (int hb = 0; hb < 2; ++hb) {
+      const int a0 = 32 * rb + 16 * hb;
+      if (a0 >= d) break;
+      double s[16][NC];
 #pragma unroll
-      for (int r = 0; r < RB; ++r) {
-        const int a = 32 * rb + r0 + r;
+      for (int r = 0; r < 16; ++r) {
+        const int a = a0 + r;
         const int ra = a * (a + 1) / 2;
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
@@ -171,9 +171,10 @@ __device__ __forceinline__ void symv_packed_warp(const double* __restrict__ S, c
           s[r][c] = (c <= rb && a < d && b <= a) ? S[ra + b] : 0.0;
         }
       }
+      double part[16];
 #pragma unroll
-      for (int r = 0; r < RB; ++r) {
-        const int a = 32 * rb + r0 + r;
+      for (int r = 0; r < 16; ++r) {
+        const int a = a0 + r;
         const double xa = a < d ? x[a] : 0.0;
         double p = 0.0;
 #pragma unroll
@@ -183,20 +184,21 @@ __device__ __forceinline__ void symv_packed_warp(const double* __restrict__ S, c
           p = fma(s[r][c], xb[c], p);
           out[c] = fma(s[r][c], b < a ? xa : 0.0, out[c]);
         }
-        part[r0 + r] = p;
+        part[r] = p;
       }
-    }
 #pragma unroll
-    for (int off = 16; off >= 1; off >>= 1) {
-      const bool up = (lane & off) != 0;
+      for (int off = 8; off >= 1; off >>= 1) {
+        const bool up = (lane & off) != 0;
 #pragma unroll
-      for (int i = 0; i < off; ++i) {
-        const double send = up ? part[i] : part[i + off];
-        const double keep = up ? part[i + off] : part[i];
-        part[i] = keep + __shfl_xor_sync(FULL, send, off);
+        for (int i = 0; i < off; ++i) {
+          const double send = up ? part[i] : part[i + off];
+          const double keep = up ? part[i + off] : part[i];
+          part[i] = keep + __shfl_xor_sync(FULL, send, off);
+        }
       }
+      const double tot = part[0] + __shfl_xor_sync(FULL, part[0], 16);  // row a0 + (lane & 15)
+      if ((lane >> 4) == hb) out[rb] += tot;
     }
-    out[rb] += part[0];
   }
 }
 
