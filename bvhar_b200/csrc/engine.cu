@@ -90,7 +90,7 @@ struct bvhar_fit {
   int num_iter = 0, num_burn = 0, thin = 1;
   uint32_t rec_mask = 0;
   cudaStream_t st = nullptr, s2 = nullptr, s3 = nullptr;
-  cudaEvent_t evf[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t evf[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   cudaGraphExec_t graph[2] = {nullptr, nullptr};
   double last_ms = 0.0;
@@ -179,7 +179,7 @@ struct bvhar_fit {
     }
     if (fork) CU(cudaEventRecord(evf[1], s2));
     if (D.sv) {
-      LAUNCH("sv_prep", launch_sv_prep(D, P, st));
+      // (updateSv, stage 3, was already done at the end of the previous sweep - see below - or at create time)
       if (fork) { CU(cudaEventRecord(evf[2], st)); CU(cudaStreamWaitEvent(s3, evf[2], 0)); }
       LAUNCH("gram_C_dmma", launch_dgemm_tn(g2, sg));
       if (fork) CU(cudaEventRecord(evf[3], s3));
@@ -204,6 +204,11 @@ struct bvhar_fit {
     if (D.sv) {
       LAUNCH("sv_mix", launch_sv_state(0, D, P, st));
       LAUNCH("sv_solve", launch_sv_state(1, D, P, st));
+      // updateSv of the NEXT sweep (Dinv = exp(-h), YLD) depends only on h and L, both final here: it runs beside
+      // sv_finish / the record copy instead of at the head of the next sweep's critical path
+      if (fork) { CU(cudaEventRecord(evf[4], st)); CU(cudaStreamWaitEvent(s2, evf[4], 0)); }
+      LAUNCH("sv_prep", launch_sv_prep(D, P, sp));
+      if (fork) CU(cudaEventRecord(evf[5], s2));
       LAUNCH("sv_finish", launch_sv_state(2, D, P, st));
     }
     else LAUNCH("ldlt_state", launch_ldlt_state(D, P, st));
@@ -211,6 +216,7 @@ struct bvhar_fit {
       LAUNCH("record", launch_record(D, P, R, st));
       LAUNCH("bump", launch_bump(P, 0, 1, st));
     }
+    if (D.sv && fork) CU(cudaStreamWaitEvent(st, evf[5], 0));
 #undef LAUNCH
     if (count) launches_per_sweep[record ? 1 : 0] = nl;
     return 0;
@@ -537,7 +543,7 @@ int build(const bvhar_fit_desc* d, bvhar_fit** out) {
   }
   CU(F->Acoef.upload(hA)); CU(F->alpha.upload(halpha)); CU(F->cvec.upload(hc)); CU(F->prec.upload(hprec));
   CU(F->contem.upload(hcontem)); CU(F->L.upload(hL)); CU(F->chol_prec.upload(hcp));
-  CU(F->sparse_coef.alloc((size_t)U * dd * k)); CU(F->sparse_contem.alloc((size_t)U * q)); CU(F->znorm.alloc((size_t)U * k));
+  CU(F->sparse_coef.alloc((size_t)U * dd * k)); CU(F->sparse_contem.alloc((size_t)U * q)); CU(F->znorm.alloc((size_t)2 * U * k));  // [U][k] column norms of Z, then [U][k] per-series sums of squared lvol increments
   CU(F->Z.alloc((size_t)tm_total));
   if (D.sv) {
     CU(F->H.alloc((size_t)tm_total)); CU(F->lvol_init.upload(hli)); CU(F->lvol_sig.upload(hls));
@@ -632,7 +638,7 @@ int build(const bvhar_fit_desc* d, bvhar_fit** out) {
   CU(F->gscratch.alloc((size_t)U * impact_gsize(D)));
   if (!impact_supported(D, F->smem_limit))
     return fail(BVHAR_ERR_UNSUPPORTED, "dim too large for the shared-memory contemporaneous draw of this build");
-  if (D.sv) CU(launch_build_xx(D, P, F->XX.p, F->st));
+  if (D.sv) { CU(launch_build_xx(D, P, F->XX.p, F->st)); CU(launch_sv_prep(D, P, F->st)); }  // updateSv for the first sweep
   else {
     // X'X (packed) and X'Y per window through the same contraction kernel
     CU(F->XtX.alloc((size_t)D.W * D.ldS)); CU(F->XtY.alloc((size_t)D.W * dd * k));
@@ -1080,7 +1086,12 @@ int bvhar_cuda_fit_get_state(bvhar_fit* fit, int window, int chain, const char* 
   return state_io(fit, window, chain, name, out, len, true);
 }
 int bvhar_cuda_fit_set_state(bvhar_fit* fit, int window, int chain, const char* name, const double* in, int64_t len) {
-  return state_io(fit, window, chain, name, const_cast<double*>(in), len, false);
+  int rc = state_io(fit, window, chain, name, const_cast<double*>(in), len, false);
+  if (rc == 0 && fit->D.sv && (!strcmp(name, "lvol_draw") || !strcmp(name, "chol_lower"))) {  // keep the cached updateSv coherent
+    CU(launch_sv_prep(fit->D, fit->P, fit->st));
+    CU(cudaStreamSynchronize(fit->st));
+  }
+  return rc;
 }
 int bvhar_cuda_fit_run_stage(bvhar_fit* fit, int stage, int iter) {
   if (!fit) return fail(BVHAR_ERR_BAD_ARG, "null fit handle");
@@ -1117,6 +1128,7 @@ int bvhar_cuda_fit_run_stage(bvhar_fit* fit, int stage, int iter) {
       break;
     default: return fail(BVHAR_ERR_BAD_ARG, "stage must be 1..9");
   }
+  if (D.sv && (stage == 7 || stage == 9)) CU(launch_sv_prep(D, fit->P, fit->st));  // keep the cached updateSv coherent with L / h
   return fit->sync();
 }
 

@@ -401,7 +401,7 @@ __global__ void __launch_bounds__(128) sv_solve_kernel(const Dims D, const DevPt
       }
     }
   }
-  double next = 0.0;
+  double next = 0.0, ssq = 0.0;
   const int nb = (n + SVS_B - 1) / SVS_B;
   double wvn[SVS_B], yvn[SVS_B];
 #pragma unroll
@@ -441,11 +441,15 @@ __global__ void __launch_bounds__(128) sv_solve_kernel(const Dims D, const DevPt
     for (int r = SVS_B - 1; r >= 0; --r) {
       const int t = t0 + r;
       if (t < n) {
+        const double hnext = next;
         next = fma(del[r], next, gam[r]);
         P.H[off + (long long)t * D.ldM] = next;
+        if (t < n - 1) ssq = fma(hnext - next, hnext - next, ssq);
       }
     }
   }
+  ssq = fma(next - h0, next - h0, ssq);  // t = 0 against the initial state (draw.h:502-506)
+  P.znorm[(size_t)D.U * D.k + (size_t)u * D.k + i] = ssq;  // per-series sum of squared increments, consumed by sv_finish
 }
 
 // varsv_sigh (draw.h:498-512, the squared increments are summed over ALL series, integer n/2) and
@@ -464,14 +468,10 @@ __global__ void __launch_bounds__(128) sv_finish_kernel(const Dims D, const DevP
   double* x = z + k;
   double* sig = x + k;
   if (threadIdx.x == 0) bad = 0;
+  // S = sum over ALL series and t of (h_t - h_{t-1})^2 (quirk draw.h:508): the per-series sums come from sv_solve
   double ss = 0.0;
-  for (int e = threadIdx.x; e < n * k; e += blockDim.x) {
-    const int t = e / k, i = e % k;
-    const double cur = P.H[off + (long long)t * D.ldM + i];
-    const double prev = t == 0 ? P.lvol_init[(size_t)u * k + i] : P.H[off + (long long)(t - 1) * D.ldM + i];
-    ss += (cur - prev) * (cur - prev);
-  }
-  ss = block_sum(ss, scratch);
+  for (int i = 0; i < k; ++i) ss += P.znorm[(size_t)D.U * k + (size_t)u * k + i];  // fixed order: deterministic
+  (void)scratch; (void)n;
   for (int i = threadIdx.x; i < k; i += blockDim.x) {
     const double s = 1.0 / rng.gamma(ST_SV_SIGH, (uint32_t)i, P.sig_shp[i] + (double)(n / 2), 1.0 / (P.sig_scl[i] + ss / 2));
     sig[i] = s;
