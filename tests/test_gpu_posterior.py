@@ -3,7 +3,7 @@ INDEPENDENT random stream (std::mt19937 sequential draws, as the reference's one
 triangular.h:207) must agree in posterior means, standard deviations and forecast MSE within 3 Monte-Carlo
 standard errors.  MCSE is estimated from the spread of chain means (many short independent chains).
 A handful of the many compared coordinates may exceed 3 sigma by chance: the test bounds the worst |z| by
-4.5 and the fraction beyond 3 by 2 %."""
+4.5 and the number beyond 3 by max(1, 2 %) per record."""
 import numpy as np
 import pytest
 
@@ -29,8 +29,10 @@ def _compare(a_means, b_means, label):
     ok = se > 0
     z = np.abs(ma - mb)[ok] / se[ok]
     assert z.size > 0
-    frac3 = float(np.mean(z > 3.0))
-    assert z.max() < 4.5 and frac3 <= 0.02, f"{label}: max |z| = {z.max():.2f}, {100 * frac3:.1f}% beyond 3 MCSE"
+    n3 = int(np.sum(z > 3.0))
+    # |z| > 3 has probability 0.27 % per coordinate under exact parity and ~400 coordinates are compared per run: one
+    # exceedance per check (or 2 % of a long vector) is expected noise, |z| >= 4.5 (7e-6) is not
+    assert z.max() < 4.5 and n3 <= max(1, int(0.02 * z.size)), f"{label}: max |z| = {z.max():.2f}, {n3} of {z.size} beyond 3 MCSE"
     return z
 
 
