@@ -383,7 +383,7 @@ __global__ void __launch_bounds__(128) sv_solve_kernel(const Dims D, const DevPt
     }
     double wv[SVS_B];
 #pragma unroll
-    for (int r = 0; r < SVS_B; ++r) wv[r] = 1.0 / sqrt(Nr[r] / Dr[r]);  // independent: pipelined
+    for (int r = 0; r < SVS_B; ++r) wv[r] = rsqrt(Nr[r] / Dr[r]);  // independent: pipelined
     Nc = Nr[SVS_B - 1] / Dr[SVS_B - 1];  // re-normalise (q itself) for the next block
     Dc = 1.0;
 #pragma unroll
