@@ -13,19 +13,25 @@ cudaError_t launch_draw_coef_batched(long long batch, int d, const double* Pp, c
                                      cudaStream_t st);
 bool coef_v2_fits(const Dims& D, size_t smem_limit);
 bool coef_pipe_fits(const Dims& D, size_t smem_limit);
+cudaError_t launch_coef_seq_nc1(const Dims& D, const DevPtrs& P, double* Pfac, double* Qn, size_t smem_limit, cudaStream_t st);
+cudaError_t launch_coef_seq_nc2(const Dims& D, const DevPtrs& P, double* Pfac, double* Qn, size_t smem_limit, cudaStream_t st);
+cudaError_t launch_coef_seq_nc4(const Dims& D, const DevPtrs& P, double* Pfac, double* Qn, size_t smem_limit, cudaStream_t st);
 cudaError_t launch_coef_v2(int part, const Dims& D, const DevPtrs& P, double* Pfac, double* Qn, size_t smem_limit, cudaStream_t st);
 cudaError_t launch_coef_chol_nc1(const Dims& D, const DevPtrs& P, double* Pfac, size_t smem_limit, cudaStream_t st);
 cudaError_t launch_coef_chol_nc2(const Dims& D, const DevPtrs& P, double* Pfac, size_t smem_limit, cudaStream_t st);
 cudaError_t launch_coef_chol_nc4(const Dims& D, const DevPtrs& P, double* Pfac, size_t smem_limit, cudaStream_t st);
-cudaError_t launch_coef_chol_nc8(const Dims& D, const DevPtrs& P, double* Pfac, size_t smem_limit, cudaStream_t st);
 inline cudaError_t launch_coef_chol(int nc, const Dims& D, const DevPtrs& P, double* Pfac, size_t smem_limit, cudaStream_t st) {
   return nc <= 1 ? launch_coef_chol_nc1(D, P, Pfac, smem_limit, st)
        : nc <= 2 ? launch_coef_chol_nc2(D, P, Pfac, smem_limit, st)
-       : nc <= 4 ? launch_coef_chol_nc4(D, P, Pfac, smem_limit, st)
-                 : launch_coef_chol_nc8(D, P, Pfac, smem_limit, st);
+                 : launch_coef_chol_nc4(D, P, Pfac, smem_limit, st);
 }
 bool coef_big_fits(const Dims& D, size_t smem_limit);
 cudaError_t launch_coef_big(int part, const Dims& D, const DevPtrs& P, double* Pfac, double* hscr, size_t smem_limit, cudaStream_t st);
+cudaError_t launch_chol_big(const Dims& D, const DevPtrs& P, double* Pfac, size_t smem_limit, cudaStream_t st);
+cudaError_t launch_seq_big_nc8(const Dims& D, const DevPtrs& P, const double* Pfac, double* hscr, size_t smem, cudaStream_t st);
+cudaError_t launch_seq_big_nc16(const Dims& D, const DevPtrs& P, const double* Pfac, double* hscr, size_t smem, cudaStream_t st);
+size_t chol_cta_smem(const Dims& D);
+size_t seq_big_smem(const Dims& D);
 int impact_gsize(const Dims& D);
 size_t impact_smem(const Dims& D);
 bool impact_supported(const Dims& D, size_t smem_limit);

@@ -1,0 +1,200 @@
+// kernels_chol_big.cu (+ kernels_seq_big.cu) — stage 4 (updateCoef, triangular.h:281-316 + draw_coef draw.h:372-383) for LARGE designs
+// (dim_design > 96: BASELINE configs C4, d = 201, and C5, d = 301), where one packed precision matrix is too big
+// for the one-warp-per-matrix / everything-in-shared-memory kernels of kernels_chol.cu / kernels_coef.cu:
+//
+//   coef_chol_cta_kernel   chol(diag(prec_j) + P_j) for every (unit, equation), ONE CTA PER MATRIX, in place in
+//                          global memory (the 148 x <= 2 matrices in flight stay L2-resident).  Left-looking
+//                          blocked factorisation, 32-column panels: the panel update
+//                              A[:, jb] -= L[:, <jb] L[jb, <jb]'
+//                          holds ~all of the d^3/3 flops and runs on the fp64 tensor pipe (DMMA m8n8k4, A fragments
+//                          straight from L2, B fragments from a shared-memory tile); the 32 x 32 diagonal block is
+//                          factored in registers by one warp (warp_linalg.cuh) and the rows below it are solved
+//                          one thread per row.
+//   coef_seq_big_kernel    the part that is sequential in j (one CTA per unit) with the factor read from
+//                          global / L2 by a blocked two-sided triangular solve that uses all warps, and the
+//                          k x d work vectors h_i = C_i - S_i v_i in a global scratch.
+#include "block_linalg.cuh"
+#include "engine.cuh"
+#include "gemm_tn.cuh"
+#include "kernels.h"
+#include "rng.cuh"
+#include "warp_linalg.cuh"
+
+namespace bvhar {
+
+namespace {
+
+constexpr int CB_THREADS = 256;
+constexpr int CB_PB = 36;  // pitch of the 32 x 32 B tile: 36 = 4 (mod 16) => conflict-free DMMA fragment loads
+
+__device__ __forceinline__ size_t rowoff(int a) { return (size_t)a * (a + 1) / 2; }
+
+// ---- A2 (large d): one CTA per matrix --------------------------------------------------------------------
+// MTW = m-tiles (8 rows) per warp: ceil(ceil(d / 8) / 8).
+template <int MTW>
+__global__ void __launch_bounds__(CB_THREADS) coef_chol_cta_kernel(const Dims D, const DevPtrs P, double* Pfac) {
+  extern __shared__ __align__(16) double sm[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int fr = lane >> 2, fc = lane & 3;
+  const long long job = blockIdx.x;
+  const int u = (int)(job / D.k), j = (int)(job % D.k), w = u / D.C;
+  const int k = D.k, d = D.d;
+  const bool SV = D.sv != 0;
+  double* pan = sm;                       // [d][33] current panel, rows c0 .. d-1
+  double* bt = pan + (size_t)d * 33;      // [32][CB_PB] rows of the diagonal block, 32 previous columns at a time
+  double* red = bt + 32 * CB_PB;          // [64] scratch
+  __shared__ int bad;
+  if (tid == 0) bad = 0;
+  double* Lg = Pfac + ((size_t)u * k + j) * D.ldS;  // in/out (SV: holds P_j on entry)
+  const double* src = Lg;
+  double scale = 1.0;
+  if (!SV) {  // P_j = (sum_{i>=j} L_ij^2 / d_i) X'X
+    double ws = 0.0;
+    for (int i = j + tid; i < k; i += CB_THREADS) {
+      const double l = P.L[((size_t)u * k + i) * k + j];
+      ws += l * l / P.diag[(size_t)u * k + i];
+    }
+    scale = block_sum(ws, red);
+    src = P.XtX + (size_t)w * D.ldS;
+  }
+  const double* pr = P.prec + (size_t)u * k * d + (size_t)j * d;
+
+  for (int c0 = 0; c0 < d; c0 += 32) {
+    const int m = d - c0;            // rows of the panel
+    const int nc = min(32, m);       // columns of the panel
+    __syncthreads();
+    // 1. load the panel (rows r = c0 + rr, columns c0 .. min(c0 + 31, r)), add the prior precision on the diagonal
+    for (int e = tid; e < m * 32; e += CB_THREADS) {
+      const int rr = e >> 5, cc = e & 31;
+      const int r = c0 + rr, c = c0 + cc;
+      double v = 0.0;
+      if (c <= r && cc < nc) {
+        v = scale * src[rowoff(r) + c];
+        if (c == r) v += pr[r];
+      }
+      pan[rr * 33 + cc] = v;
+    }
+    // 2. panel -= L[rows, 0:c0] * L[c0:c0+32, 0:c0]'   (DMMA; K = c0 in chunks of 32)
+    if (c0 > 0) {
+      double acc[MTW][4][2];
+#pragma unroll
+      for (int i = 0; i < MTW; ++i)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) acc[i][nt][0] = acc[i][nt][1] = 0.0;
+      const int mtiles = (m + 7) / 8;
+      for (int kk0 = 0; kk0 < c0; kk0 += 32) {
+        __syncthreads();
+        for (int e = tid; e < 32 * 32; e += CB_THREADS) {  // bt[n][kk] = L[c0 + n][kk0 + kk]
+          const int nn = e >> 5, kk = e & 31;
+          bt[nn * CB_PB + kk] = (c0 + nn < d) ? Lg[rowoff(c0 + nn) + kk0 + kk] : 0.0;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < MTW; ++i) {
+          const int mt = warp + 8 * i;
+          if (mt >= mtiles) continue;  // warp-uniform
+          const int r = c0 + 8 * mt + fr;
+          const double* Lr = Lg + rowoff(min(r, d - 1)) + kk0 + fc;
+          double af[8];
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks) af[ks] = r < d ? Lr[4 * ks] : 0.0;
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks)
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) dmma_m8n8k4(acc[i][nt][0], acc[i][nt][1], af[ks], bt[(8 * nt + fr) * CB_PB + 4 * ks + fc]);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < MTW; ++i) {  // fragments: row 8 mt + fr, columns 8 nt + 2 fc + {0, 1}
+        const int mt = warp + 8 * i;
+        if (mt >= mtiles) continue;
+        const int rr = 8 * mt + fr;
+        if (rr < m) {
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt) {
+            pan[rr * 33 + 8 * nt + 2 * fc] -= acc[i][nt][0];
+            pan[rr * 33 + 8 * nt + 2 * fc + 1] -= acc[i][nt][1];
+          }
+        }
+      }
+    }
+    __syncthreads();
+    // 3. factor the diagonal block: one warp, the block in registers (one row per lane)
+    if (warp == 0) {
+      double dg[32];
+#pragma unroll
+      for (int c = 0; c < 32; ++c) dg[c] = (lane < nc && c <= lane) ? pan[lane * 33 + c] : (c == lane ? 1.0 : 0.0);
+      const double dinv = chol32_registers(dg, &bad);
+#pragma unroll
+      for (int c = 0; c < 32; ++c)
+        if (lane < nc && c <= lane) pan[lane * 33 + c] = dg[c];
+      red[lane] = dinv;  // 1 / L_cc for the row solves
+    }
+    __syncthreads();
+    // 4. rows below the block: x = a L_diag^-T, one thread per row (forward substitution against the 32 x 32 block)
+    for (int rr = 32 + tid; rr < m; rr += CB_THREADS) {
+      double x[32];
+#pragma unroll
+      for (int c = 0; c < 32; ++c) x[c] = pan[rr * 33 + c];
+#pragma unroll
+      for (int c = 0; c < 32; ++c) {
+        double s = x[c];
+#pragma unroll
+        for (int b = 0; b < c; ++b) s = fma(-x[b], pan[c * 33 + b], s);
+        x[c] = s * red[c];
+      }
+#pragma unroll
+      for (int c = 0; c < 32; ++c) pan[rr * 33 + c] = x[c];
+    }
+    __syncthreads();
+    // 5. write the factored panel back (packed lower)
+    for (int e = tid; e < m * 32; e += CB_THREADS) {
+      const int rr = e >> 5, cc = e & 31;
+      const int r = c0 + rr, c = c0 + cc;
+      if (c <= r && cc < nc) Lg[rowoff(r) + c] = pan[rr * 33 + cc];
+    }
+    __threadfence_block();
+  }
+  __syncthreads();
+  if (tid == 0 && bad) atomicOr(&P.flags[u], 1);
+}
+
+}  // namespace
+
+size_t chol_cta_smem(const Dims& D) { return ((size_t)D.d * 33 + 32 * CB_PB + 64) * sizeof(double); }
+size_t seq_big_smem(const Dims& D) {
+  return ((size_t)D.k * D.k + 3 * (size_t)D.d + 32 * 33 + (size_t)(CB_THREADS / 32) * D.d + D.k + 8) * sizeof(double);
+}
+
+bool coef_big_fits(const Dims& D, size_t smem_limit) {
+  return D.d <= 512 && chol_cta_smem(D) <= smem_limit && seq_big_smem(D) <= smem_limit;
+}
+
+cudaError_t launch_chol_big(const Dims& D, const DevPtrs& P, double* Pfac, size_t smem_limit, cudaStream_t st) {
+  const size_t smem = chol_cta_smem(D);
+  if (smem > smem_limit) return cudaErrorInvalidConfiguration;
+  const unsigned grid = (unsigned)((long long)D.U * D.k);
+  const int mtw = ((D.d + 7) / 8 + 7) / 8;
+#define BV_CHOL(MTWV)                                                                                         \
+  do {                                                                                                        \
+    cudaFuncSetAttribute(coef_chol_cta_kernel<MTWV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    coef_chol_cta_kernel<MTWV><<<grid, CB_THREADS, smem, st>>>(D, P, Pfac);                                   \
+  } while (0)
+  if (mtw <= 2) BV_CHOL(2);
+  else if (mtw <= 4) BV_CHOL(4);
+  else if (mtw <= 6) BV_CHOL(6);
+  else BV_CHOL(8);
+#undef BV_CHOL
+  return cudaGetLastError();
+}
+
+// part 1: batched Cholesky (one CTA per matrix), part 2: sequential draws.  (Part 0, the P build, is shared with
+// the small-d path: launch_coef_v2(0, ...).)
+cudaError_t launch_coef_big(int part, const Dims& D, const DevPtrs& P, double* Pfac, double* hscr, size_t smem_limit, cudaStream_t st) {
+  if (part == 1) return launch_chol_big(D, P, Pfac, smem_limit, st);
+  const size_t smem = seq_big_smem(D);
+  if (smem > smem_limit) return cudaErrorInvalidConfiguration;
+  return (D.d + 31) / 32 <= 8 ? launch_seq_big_nc8(D, P, Pfac, hscr, smem, st) : launch_seq_big_nc16(D, P, Pfac, hscr, smem, st);
+}
+
+}  // namespace bvhar

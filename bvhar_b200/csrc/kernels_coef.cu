@@ -14,99 +14,22 @@
 // Packed symmetric products S_i x are done by one warp straight from global/L2 memory, row by row with
 // coalesced loads: lanes own columns (private accumulators for the upper part) and one warp reduction
 // per row gives the lower part.  LDLT models have S_i = X'X / d_i: one product per equation.
+#include "coef_sizes.h"
 #include "engine.cuh"
 #include "gemm_tn.cuh"
 #include "kernels.h"
 #include "rng.cuh"
 #include "warp_linalg.cuh"
 
+#ifndef BV_NC
+#error "compile with -DBV_NC=1|2|4|8 (one translation unit per ceil(d / 32) class)"
+#endif
+#define BV_CAT2(a, b) a##b
+#define BV_CAT(a, b) BV_CAT2(a, b)
+
 namespace bvhar {
 
 namespace {
-
-// ---- A1: P_j = sum_{i>=j} L_ij^2 S_i, all j, one pass over the unit's S ----------------------
-// Per unit this is a [k x k] x [k x Pp] product (upper-triangular weights W_ji = L_ij^2): DMMA m8n8k4 with the
-// weights held in registers as A fragments for the whole kernel and the B fragments S_i[p] loaded straight
-// from global memory (each S element is read exactly once, each P element written once: HBM-bound).
-// MT = ceil(k / 8) row tiles (j), KS = ceil(k / 4) k-steps (i).
-// With Qn != nullptr it also emits the cross matrices Q_j = sum_{i>=j+1} L_{i,j+1} L_ij S_i (slot j of Qn): Q_j delta_j is
-// the only part of equation j+1's right-hand side that depends on equation j's draw (coef_seq_pipe_kernel).
-template <int MT, int KS>
-__global__ void __launch_bounds__(256) coef_pbuild_kernel(const Dims D, const DevPtrs P, double* __restrict__ Pfac, double* __restrict__ Qn) {
-  const int u = blockIdx.x, k = D.k;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int fr = lane >> 2, fc = lane & 3;
-  const double* Lu = P.L + (size_t)u * k * k;
-  const int mtb = blockIdx.z * MT;  // first row tile of this pass (k > 32 takes two passes over S)
-  double af[MT][KS];  // A[m = j][kk = i] = L_ij^2 for i >= j
-#pragma unroll
-  for (int mt = 0; mt < MT; ++mt)
-#pragma unroll
-    for (int ks = 0; ks < KS; ++ks) {
-      const int j = 8 * (mtb + mt) + fr, i = 4 * ks + fc;
-      const double l = (i < k && j <= i) ? Lu[i * k + j] : 0.0;
-      af[mt][ks] = l * l;
-    }
-  double aq[MT][KS];  // A2[m = j][kk = i] = L_{i,j+1} L_ij for i >= j + 1
-#pragma unroll
-  for (int mt = 0; mt < MT; ++mt)
-#pragma unroll
-    for (int ks = 0; ks < KS; ++ks) {
-      const int j = 8 * (mtb + mt) + fr, i = 4 * ks + fc;
-      aq[mt][ks] = (Qn && i < k && j + 1 <= i) ? Lu[i * k + j] * Lu[i * k + j + 1] : 0.0;
-    }
-  double* Qu = Qn ? Qn + (size_t)u * k * D.ldS : nullptr;
-  const double* Su = P.S + (size_t)u * k * D.ldS;
-  double* Pu = Pfac + (size_t)u * k * D.ldS;
-  const int ntiles = (D.Pp + 7) / 8;
-  constexpr int NQ = KS > 8 ? 2 : 4;  // n-tiles per warp iteration (loads of all of them in flight together)
-  for (int nt0 = (blockIdx.y * 8 + warp) * NQ; nt0 < ntiles; nt0 += gridDim.y * 8 * NQ) {
-    double bf[NQ][KS];
-#pragma unroll
-    for (int q = 0; q < NQ; ++q)
-#pragma unroll
-      for (int ks = 0; ks < KS; ++ks) {
-        const int i = 4 * ks + fc, p = 8 * (nt0 + q) + fr;
-        bf[q][ks] = (i < k && p < D.Pp) ? Su[(size_t)i * D.ldS + p] : 0.0;
-      }
-#pragma unroll
-    for (int q = 0; q < NQ; ++q) {
-      const int p = 8 * (nt0 + q) + 2 * fc;
-#pragma unroll
-      for (int mt = 0; mt < MT; ++mt) {
-        double c0 = 0.0, c1 = 0.0;
-#pragma unroll
-        for (int ks = 0; ks < KS; ++ks) dmma_m8n8k4(c0, c1, af[mt][ks], bf[q][ks]);
-        const int j = 8 * (mtb + mt) + fr;
-        if (j < k && p < D.Pp) {  // ldS is even and p is even: 16-byte aligned pair inside the padded row
-          *reinterpret_cast<double2*>(Pu + (size_t)j * D.ldS + p) = make_double2(c0, c1);
-        }
-        if (Qu) {  // warp-uniform
-          double q0 = 0.0, q1 = 0.0;
-#pragma unroll
-          for (int ks = 0; ks < KS; ++ks) dmma_m8n8k4(q0, q1, aq[mt][ks], bf[q][ks]);
-          if (j + 1 < k && p < D.Pp) *reinterpret_cast<double2*>(Qu + (size_t)j * D.ldS + p) = make_double2(q0, q1);
-        }
-      }
-    }
-  }
-}
-// generic fallback for k > 64: one thread per (j, p), streaming i
-__global__ void __launch_bounds__(256) coef_pbuild_generic_kernel(const Dims D, const DevPtrs P, double* __restrict__ Pfac) {
-  const int u = blockIdx.x, k = D.k;
-  const double* Su = P.S + (size_t)u * k * D.ldS;
-  const double* Lu = P.L + (size_t)u * k * k;
-  double* Pu = Pfac + (size_t)u * k * D.ldS;
-  for (int j = 0; j < k; ++j)
-    for (int p = threadIdx.x; p < D.Pp; p += blockDim.x) {
-      double acc = 0.0;
-      for (int i = j; i < k; ++i) {
-        const double l = Lu[i * k + j];
-        acc = fma(l * l, Su[(size_t)i * D.ldS + p], acc);
-      }
-      Pu[(size_t)j * D.ldS + p] = acc;
-    }
-}
 
 // ---- B: the sequential-in-j part, one CTA per unit ---------------------------------------------
 // Shared memory holds everything the dependent chain touches: h_i = C_i - S_i v_i (k x d), the unit's
@@ -114,12 +37,6 @@ __global__ void __launch_bounds__(256) coef_pbuild_generic_kernel(const Dims D, 
 // Cholesky factor of the current equation, double-buffered so that the factor of equation j + 1 streams in
 // (cp.async) while equation j is solved.  Per equation only the solve (one warp) and the k-j-1 products
 // S_i delta (all warps, S_i from L2) remain on the critical path.
-constexpr int SEQ_THREADS = 256;
-template <bool SV>
-__host__ __device__ inline size_t coef_seq_smem_doubles(int k, int d, int ppad) {
-  return 2 * (size_t)ppad + 3 * (size_t)k * d + (size_t)k * k + 4 * (size_t)d + (size_t)(SEQ_THREADS / 32) * d + (size_t)k + 8;
-}
-
 template <bool SV, int NC>
 __global__ void __launch_bounds__(SEQ_THREADS) coef_seq_kernel(const Dims D, const DevPtrs P, const double* __restrict__ Pfac) {
   extern __shared__ __align__(16) double sm[];
@@ -261,10 +178,6 @@ __global__ void __launch_bounds__(SEQ_THREADS) coef_seq_kernel(const Dims D, con
 constexpr int PIPE_WORKERS = SEQ_THREADS - 32;  // threads of warps 1..7
 __device__ __forceinline__ void worker_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(PIPE_WORKERS)); }
 
-__host__ __device__ inline size_t coef_pipe_smem_doubles(int k, int d, int ppad) {
-  return 4 * (size_t)ppad + 3 * (size_t)k * d + (size_t)k * k + 6 * (size_t)d + (size_t)(SEQ_THREADS / 32) * d + 8;
-}
-
 template <int NC>
 __global__ void __launch_bounds__(SEQ_THREADS) coef_seq_pipe_kernel(const Dims D, const DevPtrs P, const double* __restrict__ Pfac,
                                                                      const double* __restrict__ Qn) {
@@ -403,61 +316,29 @@ __global__ void __launch_bounds__(SEQ_THREADS) coef_seq_pipe_kernel(const Dims D
   }
 }
 
-template <bool SV, int NC>
-cudaError_t launch_part(int part, const Dims& D, const DevPtrs& P, double* Pfac, double* Qn, size_t smem_limit, cudaStream_t st) {
-  const int k = D.k, d = D.d;
-  const size_t ppad = (D.Pp + 1) & ~1;
-  if (part == 0) {
-    if (!SV) return cudaSuccess;
-    const dim3 grid(D.U, 4);
-    if (k <= 8) coef_pbuild_kernel<1, 2><<<grid, 256, 0, st>>>(D, P, Pfac, Qn);
-    else if (k <= 16) coef_pbuild_kernel<2, 4><<<grid, 256, 0, st>>>(D, P, Pfac, Qn);
-    else if (k <= 24) coef_pbuild_kernel<3, 6><<<grid, 256, 0, st>>>(D, P, Pfac, Qn);
-    else if (k <= 32) coef_pbuild_kernel<4, 8><<<grid, 256, 0, st>>>(D, P, Pfac, Qn);
-    else if (k <= 64) coef_pbuild_kernel<4, 16><<<dim3(D.U, 4, 2), 256, 0, st>>>(D, P, Pfac, Qn);
-    else coef_pbuild_generic_kernel<<<D.U, 256, 0, st>>>(D, P, Pfac);
-  } else if (part == 1) {
-    return launch_coef_chol(NC, D, P, Pfac, smem_limit, st);
-  } else {
-    if (SV && Qn) {
-      const size_t smp = coef_pipe_smem_doubles(k, d, D.ldS) * sizeof(double);
-      if (smp > smem_limit) return cudaErrorInvalidConfiguration;
-      cudaFuncSetAttribute(coef_seq_pipe_kernel<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smp);
-      coef_seq_pipe_kernel<NC><<<D.U, SEQ_THREADS, smp, st>>>(D, P, Pfac, Qn);
-      return cudaGetLastError();
-    }
-    const size_t sm3 = coef_seq_smem_doubles<SV>(k, d, D.ldS) * sizeof(double);
-    if (sm3 > smem_limit) return cudaErrorInvalidConfiguration;
-    cudaFuncSetAttribute(coef_seq_kernel<SV, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm3);
-    coef_seq_kernel<SV, NC><<<D.U, SEQ_THREADS, sm3, st>>>(D, P, Pfac);
-  }
-  return cudaGetLastError();
-}
-
 }  // namespace
 
-bool coef_v2_fits(const Dims& D, size_t smem_limit) {
-  if (D.d > 256) return false;
-  const size_t ppad = (D.Pp + 1) & ~1;
-  const size_t sm3 = coef_seq_smem_doubles<true>(D.k, D.d, D.ldS) * sizeof(double);
-  return sm3 <= smem_limit && ppad * sizeof(double) <= smem_limit;
-}
-
-// part 0: P build (SV only), 1: batched Cholesky, 2: sequential draws
-bool coef_pipe_fits(const Dims& D, size_t smem_limit) {
-  // two CTAs per SM keep the chain latency hidden: use the pipelined kernel only while two of them fit
-  return D.sv && D.k > 1 && D.k <= 64 && D.d <= 128 && 2 * coef_pipe_smem_doubles(D.k, D.d, D.ldS) * sizeof(double) <= smem_limit;
-}
-
-cudaError_t launch_coef_v2(int part, const Dims& D, const DevPtrs& P, double* Pfac, double* Qn, size_t smem_limit, cudaStream_t st) {
-  const int nc = (D.d + 31) / 32;
-#define BV_DISPATCH(NCV)                                                                                  \
-  return D.sv ? launch_part<true, NCV>(part, D, P, Pfac, Qn, smem_limit, st) : launch_part<false, NCV>(part, D, P, Pfac, Qn, smem_limit, st)
-  if (nc <= 1) BV_DISPATCH(1);
-  if (nc <= 2) BV_DISPATCH(2);
-  if (nc <= 4) BV_DISPATCH(4);
-  BV_DISPATCH(8);
-#undef BV_DISPATCH
+// part 2 of the coefficient stage for designs with ceil(d / 32) <= BV_NC
+cudaError_t BV_CAT(launch_coef_seq_nc, BV_NC)(const Dims& D, const DevPtrs& P, double* Pfac, double* Qn, size_t smem_limit, cudaStream_t st) {
+  constexpr int NC = BV_NC;
+  const int k = D.k, d = D.d;
+  if (D.sv && Qn) {
+    const size_t smp = coef_pipe_smem_doubles(k, d, D.ldS) * sizeof(double);
+    if (smp > smem_limit) return cudaErrorInvalidConfiguration;
+    cudaFuncSetAttribute(coef_seq_pipe_kernel<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smp);
+    coef_seq_pipe_kernel<NC><<<D.U, SEQ_THREADS, smp, st>>>(D, P, Pfac, Qn);
+    return cudaGetLastError();
+  }
+  const size_t sm3 = coef_seq_smem_doubles<true>(k, d, D.ldS) * sizeof(double);
+  if (sm3 > smem_limit) return cudaErrorInvalidConfiguration;
+  if (D.sv) {
+    cudaFuncSetAttribute(coef_seq_kernel<true, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm3);
+    coef_seq_kernel<true, NC><<<D.U, SEQ_THREADS, sm3, st>>>(D, P, Pfac);
+  } else {
+    cudaFuncSetAttribute(coef_seq_kernel<false, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm3);
+    coef_seq_kernel<false, NC><<<D.U, SEQ_THREADS, sm3, st>>>(D, P, Pfac);
+  }
+  return cudaGetLastError();
 }
 
 }  // namespace bvhar
