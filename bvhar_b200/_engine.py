@@ -128,6 +128,14 @@ class CudaFit:
         check(self.L.bvhar_cuda_fit_record_all(self._h, name.encode(), out.ctypes.data_as(c_dp), U, r.value, c.value))
         return out
 
+    def record_mean(self, name: str) -> np.ndarray:
+        """Posterior mean of each column over all units and kept draws (NaNs skipped), reduced on the device."""
+        r, c = C.c_int64(), C.c_int64()
+        check(self.L.bvhar_cuda_fit_record_dims(self._h, name.encode(), C.byref(r), C.byref(c)))
+        out = np.empty(c.value)
+        check(self.L.bvhar_cuda_fit_record_mean(self._h, name.encode(), out.ctypes.data_as(c_dp), c.value))
+        return out
+
     def records(self, window: int = 0, chain: int = 0) -> Dict[str, np.ndarray]:
         return {nm: self.record(nm, window, chain) for nm in self.record_names()}
 

@@ -1054,6 +1054,25 @@ int bvhar_cuda_fit_record_all(bvhar_fit* fit, const char* name, double* out, int
     }
   return fail(BVHAR_ERR_BAD_ARG, std::string("no record named ") + name);
 }
+// Posterior mean of every column of one record over all units and kept draws, NaNs skipped; computed on the device.
+int bvhar_cuda_fit_record_mean(bvhar_fit* fit, const char* name, double* out, int64_t cols) {
+  if (!fit || !name || !out) return fail(BVHAR_ERR_BAD_ARG, "null argument");
+  const Dims& D = fit->D;
+  CU(cudaSetDevice(fit->device));
+  CU(cudaStreamSynchronize(fit->st));
+  for (auto& r : fit->rec_order)
+    if (r.name == name) {
+      const int64_t kept = (fit->rec_filled + fit->thin - 1) / fit->thin;
+      if (cols != r.cols) return fail(BVHAR_ERR_BAD_ARG, "record dims mismatch");
+      if (kept == 0) return fail(BVHAR_ERR_BAD_ARG, "no draws recorded yet");
+      DevBuf<double> dm;
+      CU(dm.alloc((size_t)r.cols));
+      CU(launch_record_mean(*r.slot, D.U, fit->R.cap, r.cols, (int)kept, fit->thin, dm.p, 0));
+      CU(cudaMemcpy(out, dm.p, sizeof(double) * r.cols, cudaMemcpyDeviceToHost));
+      return 0;
+    }
+  return fail(BVHAR_ERR_BAD_ARG, std::string("no record named ") + name);
+}
 int bvhar_cuda_fit_record_names(bvhar_fit* fit, char* buf, int64_t buflen) {
   if (!fit || !buf) return fail(BVHAR_ERR_BAD_ARG, "null argument");
   std::string s;

@@ -44,6 +44,7 @@ cudaError_t launch_bump(const DevPtrs& P, int bump_iter, int bump_rec, cudaStrea
 cudaError_t launch_prior(const Dims& D, const DevPtrs& P, const PriorConst& C, int side, cudaStream_t st);
 // setup helpers (kernels_setup.cu)
 cudaError_t launch_scatter_lvol(const double* src, double* dst, int n, int M, int ldM, int nsrc, cudaStream_t st);
+cudaError_t launch_record_mean(const double* rec, int U, int cap, int cols, int rows, int thin, double* out, cudaStream_t st);
 cudaError_t launch_build_xx(const Dims& D, const DevPtrs& P, double* XX, cudaStream_t st);
 // forecast (kernels_forecast.cu)
 struct RecView {  // element (unit u, draw i, column c) = p[u * us + i * sd + c * sc]

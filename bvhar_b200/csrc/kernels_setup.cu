@@ -51,6 +51,35 @@ cudaError_t launch_scatter_lvol(const double* src, double* dst, int n, int M, in
   return cudaGetLastError();
 }
 
+// Posterior mean of every column of a record over all units and kept draws, NaN entries skipped (the SAVS records hold
+// 0/0 = NaN where a coefficient is exactly zero, draw.h:417-430): on-device counterpart of the colMeans / nanmean that
+// the reference front ends run on the returned draws (R/var-bayes.R:488-617).  One block per column chunk; fixed
+// summation order (deterministic).
+__global__ void __launch_bounds__(256) record_mean_kernel(const double* __restrict__ rec, int U, int cap, int cols, int rows, int thin,
+                                                          double* __restrict__ out) {
+  __shared__ double ssum[256];
+  __shared__ double scnt[256];
+  const int col = blockIdx.x;
+  double s = 0.0, n = 0.0;
+  const long long total = (long long)U * rows;
+  for (long long e = threadIdx.x; e < total; e += blockDim.x) {
+    const int u = (int)(e / rows), r = (int)(e - (long long)u * rows);
+    const double v = rec[((size_t)u * cap + (size_t)r * thin) * cols + col];
+    if (v == v) { s += v; n += 1.0; }
+  }
+  ssum[threadIdx.x] = s; scnt[threadIdx.x] = n;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) { ssum[threadIdx.x] += ssum[threadIdx.x + o]; scnt[threadIdx.x] += scnt[threadIdx.x + o]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[col] = ssum[0] / scnt[0];
+}
+cudaError_t launch_record_mean(const double* rec, int U, int cap, int cols, int rows, int thin, double* out, cudaStream_t st) {
+  record_mean_kernel<<<cols, 256, 0, st>>>(rec, U, cap, cols, rows, thin, out);
+  return cudaGetLastError();
+}
+
 // Density forecast of one (unit, draw) per thread: McmcForecaster::forecastOut fc.h:162-190,
 // RegForecaster fc.h:206-222, SvForecaster fc.h:239-262, computeMean fc.h:300-302 / 338-340.
 // Philox key (seed_forecast[unit], unit), iteration = draw index, stages ST_FORECAST_H / _Y,

@@ -125,18 +125,19 @@ class _AutoregBayes:
             warnings.warn(str(e))
         names = fit.record_names()
         recs = {nm: fit.record_all(nm) for nm in names}  # [chain, draw, column]
+        k = self.n_features_in_
+        # posterior means reduced on the device (no host pass over the draws)
+        self.coef_ = fit.record_mean("alpha_record").reshape(k, -1).T
+        if "alpha_sparse_record" in recs:
+            self.sparse_coef_ = fit.record_mean("alpha_sparse_record").reshape(k, -1).T
+        if self.fit_intercept:
+            self.intercept_ = fit.record_mean("c_record").reshape(k)
+            self.coef_ = np.concatenate([self.coef_, self.intercept_[None, :]], axis=0)
+            if self.sparse_coef_ is not None:
+                self.sparse_coef_ = np.concatenate([self.sparse_coef_, fit.record_mean("c_sparse_record")[None, :]], axis=0)
         fit.close()
         self.param_ = recs
         self.param_names_ = [nm.replace("_record", "") for nm in names]
-        k = self.n_features_in_
-        self.coef_ = recs["alpha_record"].mean(axis=(0, 1)).reshape(k, -1).T
-        if "alpha_sparse_record" in recs:
-            self.sparse_coef_ = np.nanmean(recs["alpha_sparse_record"], axis=(0, 1)).reshape(k, -1).T
-        if self.fit_intercept:
-            self.intercept_ = recs["c_record"].mean(axis=(0, 1)).reshape(k)
-            self.coef_ = np.concatenate([self.coef_, self.intercept_[None, :]], axis=0)
-            if self.sparse_coef_ is not None:
-                self.sparse_coef_ = np.concatenate([self.sparse_coef_, np.nanmean(recs["c_sparse_record"], axis=(0, 1))[None, :]], axis=0)
         self.is_fitted_ = True
         return self
 

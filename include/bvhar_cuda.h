@@ -222,6 +222,10 @@ int bvhar_cuda_fit_record(bvhar_fit* fit, int window, int chain, const char* nam
 /* All units of one record in a single call: out[unit][kept draw][column], C order, unit = window *
  * n_chains + chain. */
 int bvhar_cuda_fit_record_all(bvhar_fit* fit, const char* name, double* out, int64_t units, int64_t rows, int64_t cols);
+/* Posterior mean of every column of one record over ALL units and kept draws (NaN entries of the SAVS records
+ * skipped), reduced on the device: what the front ends compute from the returned draws (R/var-bayes.R:488-617
+ * colMeans; _bayes.py coef_ / intercept_) without shipping the draws first. */
+int bvhar_cuda_fit_record_mean(bvhar_fit* fit, const char* name, double* out, int64_t cols);
 /* Names of the records this fit exports, '\n'-separated, in the reference's list order. */
 int bvhar_cuda_fit_record_names(bvhar_fit* fit, char* buf, int64_t buflen);
 

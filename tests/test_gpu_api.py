@@ -172,3 +172,13 @@ def test_native_outforecast_matches_fit_plus_forecast(vhar, sv_model, sparse):
     for u in range(6):
         assert np.array_equal(dens[u][-1].reshape(3, 3), fc[u // 2, u % 2])
     np.testing.assert_allclose(lp.mean(axis=1).reshape(3, 2), lpl, rtol=1e-12)
+
+
+def test_device_posterior_means_match_host_reduction():
+    import problems as pr
+    from bvhar_b200._engine import CudaFit
+    pk, _ = pr.pack(prior="SSVS", sv=True, dim=3, T=50, chains=5, iters=30, burn=6, thin=2)
+    g = CudaFit(pk); g.run()
+    for nm in ("alpha_record", "alpha_sparse_record", "c_record", "a_sparse_record", "sigh_record"):
+        host = np.nanmean(g.record_all(nm, pinned=False), axis=(0, 1))
+        np.testing.assert_allclose(g.record_mean(nm), host, rtol=1e-12, atol=1e-14, equal_nan=True)
