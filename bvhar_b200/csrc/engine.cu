@@ -13,6 +13,7 @@
 #include <cstring>
 #include <map>
 #include <memory>
+#include <mutex>
 #include <set>
 #include <string>
 #include <thread>
@@ -28,6 +29,12 @@ using namespace bvhar;
 namespace {
 
 thread_local std::string g_err;
+// Several engines may be driven from different host threads (one per GPU, or several on one GPU).  Graph launches and
+// stream syncs run concurrently; what is serialised is everything that uses device-wide synchronisation or stream 0
+// (engine construction / destruction, one-shot helpers) and stream capture, which a device-wide sync issued by another
+// thread would invalidate.
+std::recursive_mutex g_api_mutex;
+#define API_LOCK std::lock_guard<std::recursive_mutex> api_lock__(g_api_mutex)
 int fail(int code, const std::string& msg) {
   g_err = msg;
   return code;
@@ -235,6 +242,7 @@ struct bvhar_fit {
         if (rc) return rc;
       } else {
         if (!graph[gi]) {
+          API_LOCK;
           cudaGraph_t g;
           CU(cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
           int rc = enqueue_sweep(record, false);
@@ -281,6 +289,7 @@ int round_even(int x) { return (x + 1) & ~1; }
 
 int build(const bvhar_fit_desc* d, bvhar_fit** out) {
   if (!d || !out) return fail(BVHAR_ERR_BAD_ARG, "null descriptor");
+  API_LOCK;
   if (d->abi_version != BVHAR_CUDA_ABI_VERSION) return fail(BVHAR_ERR_BAD_ARG, "descriptor ABI version mismatch");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
@@ -1057,6 +1066,7 @@ int bvhar_cuda_fit_record_all(bvhar_fit* fit, const char* name, double* out, int
 // Posterior mean of every column of one record over all units and kept draws, NaNs skipped; computed on the device.
 int bvhar_cuda_fit_record_mean(bvhar_fit* fit, const char* name, double* out, int64_t cols) {
   if (!fit || !name || !out) return fail(BVHAR_ERR_BAD_ARG, "null argument");
+  API_LOCK;
   const Dims& D = fit->D;
   CU(cudaSetDevice(fit->device));
   CU(cudaStreamSynchronize(fit->st));
@@ -1151,11 +1161,15 @@ int bvhar_cuda_fit_run_stage(bvhar_fit* fit, int stage, int iter) {
   return fit->sync();
 }
 
-void bvhar_cuda_fit_destroy(bvhar_fit* fit) { delete fit; }
+void bvhar_cuda_fit_destroy(bvhar_fit* fit) {
+  API_LOCK;
+  delete fit;
+}
 
 // ---- density forecast -------------------------------------------------------------------
 int bvhar_cuda_forecast_density(const bvhar_forecast_desc* d, double* out_density, double* out_lpl) {
   if (!d || !out_density) return fail(BVHAR_ERR_BAD_ARG, "null argument");
+  API_LOCK;
   if (d->abi_version != BVHAR_CUDA_ABI_VERSION) return fail(BVHAR_ERR_BAD_ARG, "descriptor ABI version mismatch");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(BVHAR_ERR_CUDA, "no CUDA device available: no CPU fallback");
@@ -1218,6 +1232,7 @@ int bvhar_cuda_outforecast_run(const bvhar_fit_desc* fd, const bvhar_outforecast
   std::unique_ptr<bvhar_fit> guard(fit);
   rc = bvhar_cuda_fit_run(fit, nullptr, nullptr);
   if (rc && rc != BVHAR_ERR_NUMERICAL) return rc;  // a non-PD flag does not abort (the reference would carry NaNs)
+  API_LOCK;  // the forecast part below works on stream 0 with device-wide syncs
   const Dims& D = fit->D;
   const int k = D.k, U = D.U, q = D.q, p = fp->var_lag, step = fp->step;
   const int S = (fit->rec_filled + fit->thin - 1) / fit->thin;
@@ -1278,6 +1293,7 @@ int bvhar_cuda_outforecast_run(const bvhar_fit_desc* fd, const bvhar_outforecast
 // ---- building blocks ------------------------------------------------------------------------
 int bvhar_cuda_dgemm_tn(int device, int64_t M, int64_t N, int64_t K, const double* A, int64_t lda, const double* B,
                         int64_t ldb, double* C, int64_t ldc) {
+  API_LOCK;
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(BVHAR_ERR_CUDA, "no CUDA device available: no CPU fallback");
   CU(cudaSetDevice(device));
@@ -1297,6 +1313,7 @@ int bvhar_cuda_dgemm_tn(int device, int64_t M, int64_t N, int64_t K, const doubl
 
 int bvhar_cuda_draw_coef_batched(int device, int64_t batch, int32_t d, const double* P_packed, const double* b, const double* z,
                                  double* out) {
+  API_LOCK;
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(BVHAR_ERR_CUDA, "no CUDA device available: no CPU fallback");
   if (batch < 1 || d < 1) return fail(BVHAR_ERR_BAD_ARG, "empty batch");

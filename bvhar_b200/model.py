@@ -110,8 +110,71 @@ class _AutoregBayes:
     def _coef_name(self) -> str:
         return "alpha"
 
-    def fit(self):
-        """Conduct MCMC on the GPU and compute posterior means."""
+    def _fit_sharded(self, devices):
+        """Chains split over several engines (one per entry of ``devices``, normally one per GPU; the same ordinal may
+        appear twice), each driven by its own host thread.  No collective: the Philox keys are global
+        (``unit_id_base``), so the draws equal the single-engine run bit for bit; the records are concatenated."""
+        import threading
+        from ._partition import shard_fit_kwargs, shard_units
+        seeds = self._seeds(1, self.chains_)
+        kw = dict(num_chains=self.chains_, num_iter=self.iter_, num_burn=self.burn_, thin=self.thin_, x=self.design_,
+                  y=self.response_, param_cov=self.cov_spec_.to_dict(), param_prior=self.spec_.to_dict(),
+                  param_intercept=self.intercept_spec_.to_dict(), param_init=self.init_, prior_type=int(self._prior_type),
+                  grp_id=self._group_id, own_id=self._own_id, cross_id=self._cross_id, grp_mat=self.group_,
+                  include_mean=self.fit_intercept, seed_chain=seeds, is_group=self._ggl, record_mask=self._record_mask)
+        world = len(devices)
+        fits, errs = [None] * world, [None] * world
+
+        def work(r):
+            try:
+                skw = shard_fit_kwargs(kw, shard_units(1, self.chains_, world, r))
+                if skw is None:
+                    return
+                skw["device"] = int(devices[r])
+                f = CudaFit(PackedFit(**skw))
+                try:
+                    f.run(None)
+                except _abi.BvharCudaError as e:
+                    if e.status != 3:
+                        raise
+                    warnings.warn(str(e))
+                fits[r] = f
+            except Exception as e:  # re-raised on the caller's thread
+                errs[r] = e
+
+        threads = [threading.Thread(target=work, args=(r,)) for r in range(world)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        for e in errs:
+            if e is not None:
+                raise e
+        live = [f for f in fits if f is not None]
+        names = live[0].record_names()
+        recs = {nm: np.concatenate([f.record_all(nm, pinned=False) for f in live], axis=0) for nm in names}
+        for f in live:
+            f.close()
+        return names, recs
+
+    def fit(self, devices=None):
+        """Conduct MCMC on the GPU and compute posterior means.  ``devices``: optional list of CUDA ordinals to split
+        the chains over (one engine and one host thread per entry)."""
+        if devices is not None and len(devices) > 1:
+            names, recs = self._fit_sharded(list(devices))
+            k = self.n_features_in_
+            self.coef_ = recs["alpha_record"].mean(axis=(0, 1)).reshape(k, -1).T
+            if "alpha_sparse_record" in recs:
+                self.sparse_coef_ = np.nanmean(recs["alpha_sparse_record"], axis=(0, 1)).reshape(k, -1).T
+            if self.fit_intercept:
+                self.intercept_ = recs["c_record"].mean(axis=(0, 1)).reshape(k)
+                self.coef_ = np.concatenate([self.coef_, self.intercept_[None, :]], axis=0)
+                if self.sparse_coef_ is not None:
+                    self.sparse_coef_ = np.concatenate([self.sparse_coef_, np.nanmean(recs["c_sparse_record"], axis=(0, 1))[None, :]], axis=0)
+            self.param_ = recs
+            self.param_names_ = [nm.replace("_record", "") for nm in names]
+            self.is_fitted_ = True
+            return self
         packed = self._pack(self.design_, self.response_, self._seeds(1, self.chains_))
         fit = CudaFit(packed)
         cb = None
