@@ -247,9 +247,14 @@ class _AutoregBayes:
     def predict(self, n_ahead: int, level=.05, stable=False, sparse=False, med=False, sv=True):
         """'n_ahead'-step density forecast from the stored draws (forecaster.h:494-568)."""
         recs = self._chain_records()
-        dens, _ = forecast_density(recs, [self.y_] * self.chains_, n_ahead, self.lag_, self.fit_intercept, self._is_sv,
-                                   self._seeds(self.chains_), har_trans=self._har(), sv=sv, stable=stable, sparse=sparse,
-                                   device=self._device)
+        seeds = self._seeds(self.chains_)
+        if stable:  # the host-side stability filter may keep a different number of draws per chain: one call per chain
+            dens = [forecast_density([rec], [self.y_], n_ahead, self.lag_, self.fit_intercept, self._is_sv, [seeds[c]],
+                                     har_trans=self._har(), sv=sv, stable=True, sparse=sparse, device=self._device,
+                                     unit_id_base=c)[0][0] for c, rec in enumerate(recs)]
+        else:
+            dens, _ = forecast_density(recs, [self.y_] * self.chains_, n_ahead, self.lag_, self.fit_intercept, self._is_sv, seeds,
+                                       har_trans=self._har(), sv=sv, sparse=sparse, device=self._device)
         k = self.n_features_in_
         allchains = np.concatenate([d.reshape(n_ahead, -1, k) for d in dens], axis=1).reshape(n_ahead, -1)
         return self._summarise(allchains, k, level, med)
@@ -275,25 +280,59 @@ class _AutoregBayes:
         seed_fc = self._seeds(self.chains_)
         valid = test[n_ahead] if test.shape[0] > n_ahead else None  # y_test.row(step), forecaster.h:802
         C_ = self.chains_
+        def per_unit(units, lasts, seeds_u, base):
+            """stable=True: the stability filter (subsetStable, config.h:884-914, 1003-1034: companion-matrix eigenvalues
+            per draw) runs on the host and may keep a different number of draws per unit -> one forecaster call per unit."""
+            outs, lps = [], []
+            for i, (rec, lo, sd) in enumerate(zip(units, lasts, seeds_u)):
+                dens, lp = forecast_density([rec], [lo], n_ahead, self.lag_, self.fit_intercept, self._is_sv, [sd],
+                                            har_trans=self._har(), sv=sv, valid_vec=valid, stable=True, sparse=sparse,
+                                            device=self._device, unit_id_base=base + i)
+                outs.append(dens[0][-1].reshape(-1, k))
+                lps.append(float(lp.mean()) if lp is not None else None)
+            return outs, lps
+
         # window 0 reuses the existing fit (forecaster.h:799-801)
-        dens0, lpl0 = forecast_density(list(self._chain_records()), [tot[: self.lag_ + nrow[0]]] * C_, n_ahead, self.lag_,
-                                       self.fit_intercept, self._is_sv, seed_fc, har_trans=self._har(), sv=sv, valid_vec=valid,
-                                       stable=stable, sparse=sparse, device=self._device)
-        last0 = np.stack([d[-1].reshape(-1, k) for d in dens0])  # [chain, draw, variable], last step (forecaster.h:803)
-        per_window = [last0]
-        lpls = [lpl0.mean(axis=1)] if lpl0 is not None else None
-        if n_hor > 1:
-            if stable:
-                raise NotImplementedError("stable=True is only available for window 0 / predict() in this build")
-            # windows >= 1: refit + forecast of every (window, chain) in one native call, draws stay on the device
+        lpls = [] if valid is not None else None
+        if stable:
+            o0, l0 = per_unit(list(self._chain_records()), [tot[: self.lag_ + nrow[0]]] * C_, seed_fc, 0)
+            per_window = [np.concatenate(o0, axis=0)]
+            if lpls is not None:
+                lpls.append(np.asarray(l0))
+        else:
+            dens0, lpl0 = forecast_density(list(self._chain_records()), [tot[: self.lag_ + nrow[0]]] * C_, n_ahead, self.lag_,
+                                           self.fit_intercept, self._is_sv, seed_fc, har_trans=self._har(), sv=sv,
+                                           valid_vec=valid, sparse=sparse, device=self._device)
+            per_window = [np.concatenate([d[-1].reshape(-1, k) for d in dens0], axis=0)]  # last step only (forecaster.h:803)
+            if lpls is not None:
+                lpls.append(lpl0.mean(axis=1))
+        if n_hor > 1 and stable:
+            # the draws come back to the host for the filter, then every (window, chain) is forecast on its own
+            packed = self._pack(x_tot, y_tot, seeds[1:], win_row0=row0[1:], win_nrow=nrow[1:],
+                                record_mask=REC_COEF | REC_SPARSE | REC_LVOL_LAST,
+                                lvol_from_init=self._is_sv and expanding, unit_id_base=C_)
+            fitw = CudaFit(packed)
+            try:
+                fitw.run(None)
+            except _abi.BvharCudaError as e:
+                if e.status != 3:
+                    raise
+                warnings.warn(str(e))
+            bulk = {nm: fitw.record_all(nm, pinned=False) for nm in fitw.record_names()}
+            fitw.close()
+            for w in range(1, n_hor):
+                units = [{nm: arr[(w - 1) * C_ + c] for nm, arr in bulk.items()} for c in range(C_)]
+                ow, lw = per_unit(units, [tot[: self.lag_ + row0[w] + nrow[w]]] * C_, seed_fc, C_ + (w - 1) * C_)
+                per_window.append(np.concatenate(ow, axis=0))
+                if lpls is not None:
+                    lpls.append(np.asarray(lw))
+        elif n_hor > 1:
+            # windows >= 1: refit + forecast of every (window, chain) in ONE native call, the draws stay on the device
             packed = self._pack(x_tot, y_tot, seeds[1:], win_row0=row0[1:], win_nrow=nrow[1:], record_mask=0,
                                 lvol_from_init=self._is_sv and expanding, unit_id_base=C_)
-            try:
-                fc, lp = outforecast(packed, tot, n_ahead, self.lag_, seed_fc, har_trans=self._har(), sv=sv, valid_vec=valid,
-                                     sparse=sparse)
-            except _abi.BvharCudaError as e:
-                raise
-            per_window += [fc[w] for w in range(n_hor - 1)]
+            fc, lp = outforecast(packed, tot, n_ahead, self.lag_, seed_fc, har_trans=self._har(), sv=sv, valid_vec=valid,
+                                 sparse=sparse)
+            per_window += [fc[w].reshape(-1, k) for w in range(n_hor - 1)]
             if lpls is not None:
                 lpls += [lp[w] for w in range(n_hor - 1)]
         out = {"forecast": [], "se": [], "lower": [], "upper": []}

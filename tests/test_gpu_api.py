@@ -194,3 +194,12 @@ def test_fit_over_several_engines_equals_single_engine():
     for nm in a.param_:
         assert np.array_equal(a.param_[nm], b.param_[nm], equal_nan=True), nm
     np.testing.assert_allclose(a.coef_, b.coef_, rtol=1e-12)
+
+
+def test_roll_forecast_with_stability_filter():
+    data, test_y = _data(n_ahead=4)
+    fit = VarBayes(data, 2, 2, 30, 10, 1, HorseshoeConfig(), LdltConfig(), seed=4).fit()
+    a = fit.roll_forecast(1, test_y, stable=True)
+    _check_forecast(a, 4, 2)
+    b = fit.predict(3, stable=True)
+    _check_forecast(b, 3, 2)
