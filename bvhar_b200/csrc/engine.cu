@@ -638,7 +638,7 @@ int build(const bvhar_fit_desc* d, bvhar_fit** out) {
   F->coef_big = coef_big_fits(D, F->smem_limit) && !force_v1 && (D.d > 128 || !F->coef_v2 || force_big);
   if (F->coef_big) F->coef_v2 = false;
   if (F->coef_v2 || F->coef_big) CU(F->Pfac.alloc((size_t)U * k * D.ldS));
-  if (F->coef_big) CU(F->hscr.alloc((size_t)U * k * dd));
+  if (F->coef_big) CU(F->hscr.alloc(D.sv ? seq_time_scratch_doubles(D) : (size_t)U * k * dd));
   if (F->coef_v2 && coef_pipe_fits(D, F->smem_limit) && getenv("BVHAR_COEF_NOPIPE") == nullptr) CU(F->Qn.alloc((size_t)U * k * D.ldS));
   if (!F->coef_v2 && !F->coef_big && !coef_plan(D, F->smem_limit, &ch_plan, &need_v, &need_p))
     return fail(BVHAR_ERR_UNSUPPORTED, "dim_design too large for the shared-memory Cholesky of this build (packed d(d+1)/2 doubles must fit 227 KB)");
@@ -1218,12 +1218,8 @@ int bvhar_cuda_forecast_density(const bvhar_forecast_desc* d, double* out_densit
 // ---- out-of-sample refits + forecasts in one call (McmcOutforecastRun::returnForecast, forecaster.h:616-650,
 // 755-806): every (window, chain) of the descriptor's window table is refitted, then forecast straight from the
 // device-resident records (no host round trip of the draws).
-int bvhar_cuda_outforecast_run(const bvhar_fit_desc* fd, const bvhar_outforecast_params* fp, double* out_forecast, double* out_lpl) {
-  if (!fd || !fp || !out_forecast) return fail(BVHAR_ERR_BAD_ARG, "null argument");
-  if (fp->abi_version != BVHAR_CUDA_ABI_VERSION) return fail(BVHAR_ERR_BAD_ARG, "descriptor ABI version mismatch");
-  if (fp->step < 1 || fp->step > 64) return fail(BVHAR_ERR_UNSUPPORTED, "forecast step must be in 1..64");
-  if (!fp->y_full || !fp->seed_forecast) return fail(BVHAR_ERR_BAD_ARG, "y_full / seed_forecast missing");
-  if (fp->is_vhar && !fp->har_trans) return fail(BVHAR_ERR_BAD_ARG, "har_trans missing");
+// one batch of windows that fits in device memory (bvhar_cuda_outforecast_run below splits the window table)
+static int outforecast_batch(const bvhar_fit_desc* fd, const bvhar_outforecast_params* fp, double* out_forecast, double* out_lpl) {
   bvhar_fit_desc d2 = *fd;
   d2.record_mask = BVHAR_REC_COEF | BVHAR_REC_LVOL_LAST | (fp->sparse ? BVHAR_REC_SPARSE : 0u);  // all the forecaster reads (config.h:998-1001)
   bvhar_fit* fit = nullptr;
@@ -1286,6 +1282,73 @@ int bvhar_cuda_outforecast_run(const bvhar_fit_desc* fd, const bvhar_outforecast
       for (int h = 0; h < step; ++h) s += hl[(size_t)u * step + h];
       out_lpl[u] = s / step;
     }
+  }
+  return 0;
+}
+
+// Device bytes one (window, chain) unit of this descriptor needs, dominated by the packed Gram matrices S_i, the
+// factors and the [t][m] state (an estimate with head-room; an out-of-memory batch is halved and retried anyway).
+static size_t outforecast_unit_bytes(const bvhar_fit_desc* fd, int step) {
+  const size_t k = fd->dim, d = fd->dim_design, q = k * (k - 1) / 2, N = k * d;
+  size_t nmax = 1;
+  for (int w = 0; w < fd->n_windows; ++w) nmax = std::max(nmax, (size_t)fd->win_nrow[w]);
+  const size_t pp = d * (d + 1) / 2 + 1;
+  const size_t kept = (size_t)std::max(1, fd->num_iter - fd->num_burn);
+  size_t dbl = 3 * k * pp + k * (d + 1) + 2 * k * std::max(nmax + 3, d) + 5 * nmax * (k + 1) + k * k * k / 2 + 4 * k * k;
+  dbl += kept * 2 * (N + 3 * k + q) + kept * k * (size_t)step + 40 * (N + q + k);
+  return dbl * sizeof(double);
+}
+
+int bvhar_cuda_outforecast_run(const bvhar_fit_desc* fd, const bvhar_outforecast_params* fp, double* out_forecast, double* out_lpl) {
+  if (!fd || !fp || !out_forecast) return fail(BVHAR_ERR_BAD_ARG, "null argument");
+  if (fp->abi_version != BVHAR_CUDA_ABI_VERSION) return fail(BVHAR_ERR_BAD_ARG, "descriptor ABI version mismatch");
+  if (fp->step < 1 || fp->step > 64) return fail(BVHAR_ERR_UNSUPPORTED, "forecast step must be in 1..64");
+  if (!fp->y_full || !fp->seed_forecast) return fail(BVHAR_ERR_BAD_ARG, "y_full / seed_forecast missing");
+  if (fp->is_vhar && !fp->har_trans) return fail(BVHAR_ERR_BAD_ARG, "har_trans missing");
+  if (fd->n_windows < 1 || fd->n_chains < 1 || !fd->win_row0 || !fd->win_nrow || !fd->seed_chain) return fail(BVHAR_ERR_BAD_ARG, "empty window table");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(BVHAR_ERR_CUDA, "no CUDA device available: no CPU fallback");
+  CU(cudaSetDevice(fd->device));
+  // Windows are independent (forecaster.h:628-632): the table is processed in batches sized to the free device memory
+  // (2 000 windows x 4 chains of C4 would need ~130 GB of Gram matrices and factors at once).  Unit u of a batch keeps
+  // its global Philox key (unit_id_base + first unit of the batch), so the result does not depend on the batch size.
+  const int W = fd->n_windows, C = fd->n_chains, k = fd->dim;
+  const int thin = fd->thin < 1 ? 1 : fd->thin;
+  const long long S = ((long long)std::max(0, fd->num_iter - fd->num_burn) + thin - 1) / thin;
+  size_t free_b = 0, total_b = 0;
+  CU(cudaMemGetInfo(&free_b, &total_b));
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, fd->device) == cudaSuccess) {  // memory parked in the stream-ordered pool is reusable
+    unsigned long long reserved = 0, used = 0;
+    if (cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved) == cudaSuccess &&
+        cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used) == cudaSuccess && reserved > used)
+      free_b += (size_t)(reserved - used);
+  }
+  const size_t d_ = fd->dim_design;
+  const size_t shared_b = (size_t)fd->n_rows_total * (d_ * (d_ + 1) / 2 + 2 * d_ + 2 * k + 8) * sizeof(double);  // X, X', XX, Y
+  const size_t unit_b = outforecast_unit_bytes(fd, fp->step);
+  const size_t budget = free_b > shared_b ? (size_t)(0.85 * (double)(free_b - shared_b)) : 0;
+  long long batch = std::max<long long>(1, (long long)(budget / ((size_t)C * unit_b)));
+  if (const char* env = getenv("BVHAR_MAX_WINDOWS_PER_BATCH")) batch = std::max(1, atoi(env));
+  batch = std::min<long long>(batch, W);
+  for (int w0 = 0; w0 < W;) {
+    const int nw = (int)std::min<long long>(batch, W - w0);
+    bvhar_fit_desc sub = *fd;
+    sub.n_windows = nw;
+    sub.win_row0 = fd->win_row0 + w0;
+    sub.win_nrow = fd->win_nrow + w0;
+    sub.seed_chain = fd->seed_chain + (size_t)w0 * C;
+    sub.unit_id_base = fd->unit_id_base + w0 * C;
+    const int rc = outforecast_batch(&sub, fp, out_forecast + (size_t)w0 * C * S * k, out_lpl ? out_lpl + (size_t)w0 * C : nullptr);
+    if (rc == BVHAR_ERR_CUDA && nw > 1 && g_err.find("out of memory") != std::string::npos) {
+      cudaGetLastError();
+      cudaDeviceSynchronize();
+      if (cudaDeviceGetDefaultMemPool(&pool, fd->device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
+      batch = (nw + 1) / 2;
+      continue;  // retry the same windows in smaller batches
+    }
+    if (rc) return rc;
+    w0 += nw;
   }
   return 0;
 }

@@ -30,6 +30,9 @@ cudaError_t launch_coef_big(int part, const Dims& D, const DevPtrs& P, double* P
 cudaError_t launch_chol_big(const Dims& D, const DevPtrs& P, double* Pfac, size_t smem_limit, cudaStream_t st);
 cudaError_t launch_seq_big_nc8(const Dims& D, const DevPtrs& P, const double* Pfac, double* hscr, size_t smem, cudaStream_t st);
 cudaError_t launch_seq_big_nc16(const Dims& D, const DevPtrs& P, const double* Pfac, double* hscr, size_t smem, cudaStream_t st);
+size_t seq_time_smem(const Dims& D);
+size_t seq_time_scratch_doubles(const Dims& D);  // per-fit scratch of the time-domain sequential kernel (SV, large d)
+cudaError_t launch_seq_time(const Dims& D, const DevPtrs& P, const double* Pfac, double* escr, size_t smem_limit, cudaStream_t st);
 size_t chol_cta_smem(const Dims& D);
 size_t seq_big_smem(const Dims& D);
 int impact_gsize(const Dims& D);

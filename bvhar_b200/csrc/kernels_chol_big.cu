@@ -10,6 +10,11 @@
 //                          straight from L2, B fragments from a shared-memory tile); the 32 x 32 diagonal block is
 //                          factored in registers by one warp (warp_linalg.cuh) and the rows below it are solved
 //                          one thread per row.
+//   invert_diag_kernel     replaces every 32 x 32 DIAGONAL BLOCK of the factors by its INVERSE (lower triangular),
+//                          one warp per block, one thread per column (forward substitution L x = e_c from a
+//                          shared-memory copy of the block): the blocked triangular solves of kernels_seq_big.cu are
+//                          then matrix-vector products instead of 32-step dependent substitutions.  This is the
+//                          storage convention of Pfac on the large-design path.
 //   coef_seq_big_kernel    the part that is sequential in j (one CTA per unit) with the factor read from
 //                          global / L2 by a blocked two-sided triangular solve that uses all warps, and the
 //                          k x d work vectors h_i = C_i - S_i v_i in a global scratch.
@@ -159,6 +164,36 @@ __global__ void __launch_bounds__(CB_THREADS) coef_chol_cta_kernel(const Dims D,
   if (tid == 0 && bad) atomicOr(&P.flags[u], 1);
 }
 
+
+// ---- A3: invert the diagonal blocks in place, one warp per (matrix, block) ---------------------------------------
+constexpr int ID_WARPS = 4;
+__global__ void __launch_bounds__(32 * ID_WARPS) invert_diag_kernel(const Dims D, double* Pfac, long long nblocks_total, int nb) {
+  __shared__ double blks[ID_WARPS][32 * 33];
+  __shared__ double dinvs[ID_WARPS][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long job = (long long)blockIdx.x * ID_WARPS + warp;
+  if (job >= nblocks_total) return;
+  const long long mat = job / nb;
+  const int jb = (int)(job % nb), c0 = 32 * jb, nc = min(32, D.d - c0);
+  double* Lg = Pfac + (size_t)mat * D.ldS;
+  double* blk = blks[warp];
+#pragma unroll 4
+  for (int r = 0; r < 32; ++r)  // coalesced row segments of the packed factor
+    blk[r * 33 + lane] = (r < nc && lane <= r) ? Lg[rowoff(c0 + r) + c0 + lane] : 0.0;
+  __syncwarp();
+  dinvs[warp][lane] = lane < nc ? 1.0 / blk[lane * 33 + lane] : 1.0;
+  __syncwarp();
+  double x[32];
+  inv32_column([&](int r) { return blk + r * 33; }, dinvs[warp], lane, nc, x);
+  __syncwarp();
+#pragma unroll
+  for (int r = 0; r < 32; ++r) blk[r * 33 + lane] = x[r];  // column `lane` of the inverse
+  __syncwarp();
+#pragma unroll 4
+  for (int r = 0; r < 32; ++r)
+    if (r < nc && lane <= r) Lg[rowoff(c0 + r) + c0 + lane] = blk[r * 33 + lane];
+}
+
 }  // namespace
 
 size_t chol_cta_smem(const Dims& D) { return ((size_t)D.d * 33 + 32 * CB_PB + 64) * sizeof(double); }
@@ -167,7 +202,7 @@ size_t seq_big_smem(const Dims& D) {
 }
 
 bool coef_big_fits(const Dims& D, size_t smem_limit) {
-  return D.d <= 512 && chol_cta_smem(D) <= smem_limit && seq_big_smem(D) <= smem_limit;
+  return D.d <= 512 && chol_cta_smem(D) <= smem_limit && (D.sv ? seq_time_smem(D) : seq_big_smem(D)) <= smem_limit;
 }
 
 cudaError_t launch_chol_big(const Dims& D, const DevPtrs& P, double* Pfac, size_t smem_limit, cudaStream_t st) {
@@ -185,6 +220,11 @@ cudaError_t launch_chol_big(const Dims& D, const DevPtrs& P, double* Pfac, size_
   else if (mtw <= 6) BV_CHOL(6);
   else BV_CHOL(8);
 #undef BV_CHOL
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  const int nb = (D.d + 31) / 32;
+  const long long nblk = (long long)D.U * D.k * nb;
+  invert_diag_kernel<<<(unsigned)((nblk + ID_WARPS - 1) / ID_WARPS), 32 * ID_WARPS, 0, st>>>(D, Pfac, nblk, nb);
   return cudaGetLastError();
 }
 
@@ -192,6 +232,7 @@ cudaError_t launch_chol_big(const Dims& D, const DevPtrs& P, double* Pfac, size_
 // the small-d path: launch_coef_v2(0, ...).)
 cudaError_t launch_coef_big(int part, const Dims& D, const DevPtrs& P, double* Pfac, double* hscr, size_t smem_limit, cudaStream_t st) {
   if (part == 1) return launch_chol_big(D, P, Pfac, smem_limit, st);
+  if (D.sv) return launch_seq_time(D, P, Pfac, hscr, smem_limit, st);  // SV: time-domain recurrence (kernels_seq_big.cu)
   const size_t smem = seq_big_smem(D);
   if (smem > smem_limit) return cudaErrorInvalidConfiguration;
   return (D.d + 31) / 32 <= 8 ? launch_seq_big_nc8(D, P, Pfac, hscr, smem, st) : launch_seq_big_nc16(D, P, Pfac, hscr, smem, st);

@@ -44,6 +44,26 @@ __device__ __forceinline__ double chol32_registers(double (&dg)[32], int* bad) {
   return dinv;
 }
 
+// Column `c` (one thread per column) of the inverse of a 32 x 32 lower-triangular block whose rows are read through
+// `Lrow(r)` (pointer to L[r][0], the same address for every thread => shared-memory broadcasts) and whose reciprocal
+// diagonal is dinv[r]: forward substitution L x = e_c, 496 predicated FMAs per thread with two partial sums.  Rows >= nv
+// are identity rows.
+template <typename RowFn>
+__device__ __forceinline__ void inv32_column(RowFn Lrow, const double* dinv, int c, int nv, double (&x)[32]) {
+#pragma unroll
+  for (int r = 0; r < 32; ++r) {
+    const double* lr = Lrow(r);
+    double s0 = (r == c) ? 1.0 : 0.0, s1 = 0.0;
+#pragma unroll
+    for (int m = 0; m + 1 < r; m += 2) {
+      s0 = fma(-lr[m], x[m], s0);
+      s1 = fma(-lr[m + 1], x[m + 1], s1);
+    }
+    if (r & 1) s0 = fma(-lr[r - 1], x[r - 1], s0);
+    x[r] = (r < c) ? 0.0 : (r < nv ? (s0 + s1) * dinv[r] : ((r == c) ? 1.0 : 0.0));
+  }
+}
+
 template <int NB>
 __device__ __forceinline__ void chol_blocked_warp(double* Pk, int d, int* bad) {
   const unsigned FULL = 0xffffffffu;

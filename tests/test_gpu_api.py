@@ -143,10 +143,14 @@ def test_pinned_output_pool_ownership():
     _hostpool.trim()
 
 
+@pytest.mark.parametrize("batch", [None, 2, 1])
 @pytest.mark.parametrize("vhar,sv_model,sparse", [(False, True, False), (True, False, True), (True, True, False)])
-def test_native_outforecast_matches_fit_plus_forecast(vhar, sv_model, sparse):
+def test_native_outforecast_matches_fit_plus_forecast(monkeypatch, vhar, sv_model, sparse, batch):
     """bvhar_cuda_outforecast_run (refit + forecast of every (window, chain) in one call, draws kept on the device)
-    equals fit_run -> records -> bvhar_cuda_forecast_density on the same window table, bit for bit."""
+    equals fit_run -> records -> bvhar_cuda_forecast_density on the same window table, bit for bit - also when the
+    window table is processed in memory-sized batches (here forced to 2 + 1 and 1 + 1 + 1 windows)."""
+    if batch:
+        monkeypatch.setenv("BVHAR_MAX_WINDOWS_PER_BATCH", str(batch))
     import problems as pr
     from bvhar_b200._abi import PackedFit
     from bvhar_b200._design import build_vhar

@@ -142,8 +142,9 @@ def test_stage_parity_model_variants(prior, sv, kw):
 ], ids=lambda k: ",".join(f"{a}={b}" for a, b in k.items()))
 @pytest.mark.parametrize("prior,sv", [("Horseshoe", True), ("SSVS", False), ("GDP", False), ("NG", True)])
 def test_stage_parity_large_design_path(monkeypatch, prior, sv, kw):
-    """The CTA-per-matrix blocked Cholesky + blocked CTA solve (kernels_coef_big.cu) that dim_design > 128 uses,
-    forced on small designs so that the oracle stays cheap."""
+    """The CTA-per-matrix blocked Cholesky + inverted diagonal blocks (kernels_chol_big.cu) and the blocked CTA solves /
+    time-domain recurrence (kernels_seq_big.cu) that dim_design > 128 uses, forced on small designs so that the oracle
+    stays cheap."""
     monkeypatch.setenv("BVHAR_COEF_BIG", "1")
     _stage_check(prior, sv, **kw)
 
