@@ -115,7 +115,7 @@ def ncu_traffic():
         return None
 
 
-def roll_metric(device, n_windows=32, chains=4, iters=12, burn=4):
+def roll_metric(device, n_windows=256, chains=4, iters=12, burn=4):
     """forecast_roll() on BASELINE config C4 (synthetic 50-variable VAR(4), NG prior + SV, 4 chains per window), a bounded
     sample of the 2 000 windows: every (window, chain) refitted and forecast one step ahead through the native
     out-of-sample runner, host buffers in, forecast draws out.  windows/s scales as 1 / iters, so the sweep rate is
