@@ -49,7 +49,28 @@ class CudaFit:
             cb = _abi.PROGRESS_FN()
         else:
             cb = _abi.PROGRESS_FN(lambda ctx, done, total: int(bool(progress(done, total))))
+        self._bind_sinks()
         check(self.L.bvhar_cuda_fit_run(self._h, cb, None))
+
+    def _bind_sinks(self, min_bytes: int = 8 << 20):
+        """Large records stream to pooled page-locked host buffers while the sampler runs (bvhar_cuda_fit_bind_record_sink);
+        record_all() then hands the buffer back without a device-to-host pass at the end."""
+        pk = self.packed
+        thin = max(1, int(pk.desc.thin))
+        kept = (max(0, int(pk.desc.num_iter) - int(pk.desc.num_burn)) + thin - 1) // thin
+        U = pk.n_windows * pk.n_chains
+        if kept < 1 or getattr(self, "_sinks", None):
+            return
+        self._sinks = {}
+        from . import _hostpool
+        for nm in self.record_names():
+            r, c = C.c_int64(), C.c_int64()
+            check(self.L.bvhar_cuda_fit_record_dims(self._h, nm.encode(), C.byref(r), C.byref(c)))
+            if r.value != 0 or U * kept * c.value * 8 < min_bytes:
+                continue  # (already recording, or small: fetched at the end)
+            out = _hostpool.empty((U, kept, c.value))
+            check(self.L.bvhar_cuda_fit_bind_record_sink(self._h, nm.encode(), out.ctypes.data_as(c_dp), U, kept, c.value))
+            self._sinks[nm] = out
 
     def step(self, n: int = 1, record: bool = False, sync: bool = True):
         check(self.L.bvhar_cuda_fit_step(self._h, int(n), int(record)))
@@ -120,6 +141,10 @@ class CudaFit:
         check(self.L.bvhar_cuda_fit_record_dims(self._h, name.encode(), C.byref(r), C.byref(c)))
         U = self.packed.n_windows * self.packed.n_chains
         shape = (U, r.value, c.value)
+        sink = (getattr(self, "_sinks", None) or {}).pop(name, None)  # handed out once: the caller owns it from here on
+        if sink is not None and sink.shape == shape:  # streamed during run(): only waits for the tail of the copy stream
+            check(self.L.bvhar_cuda_fit_record_all(self._h, name.encode(), sink.ctypes.data_as(c_dp), U, r.value, c.value))
+            return sink
         if pinned and U * r.value * c.value * 8 >= (8 << 20):
             from . import _hostpool
             out = _hostpool.empty(shape)

@@ -158,9 +158,48 @@ struct bvhar_fit {
     for (auto& e : evf) if (e) cudaEventDestroy(e);
     if (s2) cudaStreamDestroy(s2);
     if (s3) cudaStreamDestroy(s3);
+    if (sc) { cudaStreamSynchronize(sc); cudaStreamDestroy(sc); }
+    if (evc) cudaEventDestroy(evc);
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
     if (st) cudaStreamDestroy(st);
+  }
+
+  // record sinks: host buffers that receive record rows while later sweeps are still running (copy engine)
+  struct Sink { const RecordSpec* rec; double* host; int64_t rows; int copied; };
+  std::vector<Sink> sinks;
+  cudaStream_t sc = nullptr;
+  cudaEvent_t evc = nullptr;
+  int stream_out() {
+    if (sinks.empty()) return 0;
+    CU(cudaSetDevice(device));
+    if (!sc) { CU(cudaStreamCreateWithFlags(&sc, cudaStreamNonBlocking)); CU(cudaEventCreateWithFlags(&evc, cudaEventDisableTiming)); }
+    CU(cudaEventRecord(evc, st));
+    CU(cudaStreamWaitEvent(sc, evc, 0));
+    for (auto& k : sinks) {
+      const int from = k.copied, to = rec_filled;
+      if (to <= from) continue;
+      const size_t cols = (size_t)k.rec->cols, row_b = cols * sizeof(double);
+      const size_t spitch = (size_t)R.cap * row_b, dpitch = (size_t)k.rows * row_b;
+      const double* dev = *k.rec->slot;
+      if (thin == 1 && spitch < (1ull << 31) && dpitch < (1ull << 31)) {
+        CU(cudaMemcpy2DAsync(k.host + (size_t)from * cols, dpitch, dev + (size_t)from * cols, spitch, (size_t)(to - from) * row_b, (size_t)D.U,
+                             cudaMemcpyDeviceToHost, sc));
+      } else {
+        for (int dr = from; dr < to; ++dr) {
+          if (dr % thin) continue;
+          const size_t i = (size_t)(dr / thin);
+          if (spitch < (1ull << 31) && dpitch < (1ull << 31)) {
+            CU(cudaMemcpy2DAsync(k.host + i * cols, dpitch, dev + (size_t)dr * cols, spitch, row_b, (size_t)D.U, cudaMemcpyDeviceToHost, sc));
+          } else {
+            for (int u = 0; u < D.U; ++u)
+              CU(cudaMemcpyAsync(k.host + ((size_t)u * k.rows + i) * cols, dev + ((size_t)u * R.cap + dr) * cols, row_b, cudaMemcpyDeviceToHost, sc));
+          }
+        }
+      }
+      k.copied = to;
+    }
+    return 0;
   }
 
   int enqueue_sweep(bool record, bool count) {
@@ -265,6 +304,7 @@ struct bvhar_fit {
   int sync() {
     CU(cudaSetDevice(device));
     CU(cudaStreamSynchronize(st));
+    if (sc) CU(cudaStreamSynchronize(sc));
     prof_collect();
     if (timed) {
       float ms = 0.f;
@@ -967,6 +1007,7 @@ int bvhar_cuda_fit_run(bvhar_fit* fit, bvhar_progress_fn progress, void* ctx) {
     int chunk = std::min(freq - done % freq, (rec ? total : burn) - done);
     int rc = fit->step(chunk, rec);
     if (rc) return rc;
+    if (rec && (rc = fit->stream_out())) return rc;
     done += chunk;
     if (progress) {
       rc = fit->sync();
@@ -1041,11 +1082,30 @@ int bvhar_cuda_fit_record(bvhar_fit* fit, int window, int chain, const char* nam
 }
 // Every unit's record at once: out[unit][kept draw][column] (C order), i.e. the device layout, moved with
 // one 2-D copy per unit (a single flat copy when nothing was thinned or left unfilled).
+int bvhar_cuda_fit_bind_record_sink(bvhar_fit* fit, const char* name, double* host, int64_t units, int64_t rows, int64_t cols) {
+  if (!fit || !name || !host) return fail(BVHAR_ERR_BAD_ARG, "null argument");
+  const int64_t kept_final = ((int64_t)fit->R.cap + fit->thin - 1) / fit->thin;
+  for (auto& r : fit->rec_order)
+    if (r.name == name) {
+      if (units != fit->D.U || rows != kept_final || cols != r.cols) return fail(BVHAR_ERR_BAD_ARG, "record sink dims mismatch");
+      if (fit->rec_filled > 0) return fail(BVHAR_ERR_BAD_ARG, "record sinks must be bound before the first recorded sweep");
+      for (auto& k : fit->sinks)
+        if (k.rec == &r) { k.host = host; return 0; }
+      fit->sinks.push_back({&r, host, rows, 0});
+      return 0;
+    }
+  return fail(BVHAR_ERR_BAD_ARG, std::string("no record named ") + name);
+}
 int bvhar_cuda_fit_record_all(bvhar_fit* fit, const char* name, double* out, int64_t units, int64_t rows, int64_t cols) {
   if (!fit || !name || !out) return fail(BVHAR_ERR_BAD_ARG, "null argument");
   const Dims& D = fit->D;
   CU(cudaSetDevice(fit->device));
   CU(cudaStreamSynchronize(fit->st));
+  for (auto& k : fit->sinks)  // already streamed to this very buffer while the sampler ran
+    if (k.host == out && k.rec->name == name && k.copied == fit->rec_filled && rows == k.rows && units == D.U && cols == k.rec->cols) {
+      if (fit->sc) CU(cudaStreamSynchronize(fit->sc));
+      return 0;
+    }
   for (auto& r : fit->rec_order)
     if (r.name == name) {
       const int64_t kept = (fit->rec_filled + fit->thin - 1) / fit->thin;

@@ -222,6 +222,12 @@ int bvhar_cuda_fit_record(bvhar_fit* fit, int window, int chain, const char* nam
 /* All units of one record in a single call: out[unit][kept draw][column], C order, unit = window *
  * n_chains + chain. */
 int bvhar_cuda_fit_record_all(bvhar_fit* fit, const char* name, double* out, int64_t units, int64_t rows, int64_t cols);
+/* Optional: bind `host` (units x rows x cols doubles, rows = final kept draws, same layout as _record_all; page-locked
+ * memory makes the copies asynchronous) as the sink of one record BEFORE bvhar_cuda_fit_run.  The run then moves the
+ * record's rows to the host on a copy stream while later sweeps are still sampling, and _record_all on the same pointer
+ * only waits for the tail instead of copying: returnRecords() (triangular.h:1230-1233) without a serial device-to-host
+ * pass at the end.  The buffer must stay valid until the fit is destroyed or the record has been fetched. */
+int bvhar_cuda_fit_bind_record_sink(bvhar_fit* fit, const char* name, double* host, int64_t units, int64_t rows, int64_t cols);
 /* Posterior mean of every column of one record over ALL units and kept draws (NaN entries of the SAVS records
  * skipped), reduced on the device: what the front ends compute from the returned draws (R/var-bayes.R:488-617
  * colMeans; _bayes.py coef_ / intercept_) without shipping the draws first. */

@@ -207,3 +207,28 @@ def test_roll_forecast_with_stability_filter():
     _check_forecast(a, 4, 2)
     b = fit.predict(3, stable=True)
     _check_forecast(b, 3, 2)
+
+
+@pytest.mark.parametrize("thin", [1, 3])
+def test_streamed_record_sinks_equal_bulk_fetch(thin):
+    """Records streamed to bound host sinks while the sampler runs (bvhar_cuda_fit_bind_record_sink) are identical to the
+    bulk device-to-host fetch after the run, with and without thinning and with a progress callback syncing in between."""
+    import problems as pr
+    from bvhar_b200._engine import CudaFit
+    kw = dict(prior="Horseshoe", sv=True, dim=3, T=60, chains=5, iters=17, burn=4, thin=thin)
+    pk, _ = pr.pack(**kw)
+    a = CudaFit(pk)
+    a._bind_sinks(min_bytes=0)               # every record streams
+    assert set(a._sinks) == set(a.record_names())
+    a.run(lambda done, total: False)
+    pk2, _ = pr.pack(**kw)
+    b = CudaFit(pk2)
+    b._bind_sinks(min_bytes=1 << 60)         # nothing streams
+    assert not b._sinks
+    b._sinks = {"_": None}                   # keep run() from binding
+    b.run()
+    for nm in a.record_names():
+        x, y = a.record_all(nm), b.record_all(nm, pinned=False)
+        assert x.shape == y.shape and np.array_equal(x, y, equal_nan=True), nm
+        assert np.array_equal(a.record_all(nm, pinned=False), y, equal_nan=True)  # second fetch: plain copy
+    a.close(); b.close()
