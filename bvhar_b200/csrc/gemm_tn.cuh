@@ -86,7 +86,29 @@ __device__ __forceinline__ void gemm_load_tile(double* sm, const double* __restr
   }
 }
 
-template <bool ALIGNED16>
+// One k-tile of the warp's 64 x 32 block: m-tiles 2 i + wr (wr = warp row 0 | 1, interleaved so that a partial row
+// tile - e.g. rows 128..199 of the M = C k = 200 rows of a 4-chain window at k = 50 - splits its valid m-tiles evenly
+// over the two warp rows), n-tiles j.  NMT = m-tiles this warp owns, a compile-time count: a row tile with 72 valid rows
+// issues 5/8 of the DMMAs of a full one (predicated-off DMMAs still occupy the tensor pipe, so the count must be static).
+template <int NMT>
+__device__ __forceinline__ void gemm_ktile(double (&acc)[8][4][2], const double* as, const double* bs, int wr, int wn0, int fr, int fc) {
+#pragma unroll
+  for (int kk = 0; kk < GBK; kk += 4) {
+    double af[NMT], bf[4];
+#pragma unroll
+    for (int i = 0; i < NMT; ++i) af[i] = as[(kk + fc) * (GBM + GPAD) + (2 * i + wr) * 8 + fr];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) bf[j] = bs[(kk + fc) * (GBN + GPAD) + wn0 + j * 8 + fr];
+#pragma unroll
+    for (int i = 0; i < NMT; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+  }
+}
+
+// PART = false: every row tile is full (M a multiple of 128, e.g. the 1 024-chain C3 batch): the plain loop, m-tiles
+// wr * 8 + i.  PART = true: row tiles may be partial: interleaved m-tiles and a static per-warp m-tile count.
+template <bool ALIGNED16, bool PART>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) dgemm_tn_kernel(const GemmArgs g) {
   extern __shared__ __align__(16) unsigned char gemm_smem_raw[];
   double* As = reinterpret_cast<double*>(gemm_smem_raw);
@@ -100,10 +122,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) dgemm_tn_kernel(const GemmArg
   double* C = g.C + (g.c_off ? g.c_off[grp] : 0);
   const int m0 = blockIdx.y * GBM, n0 = blockIdx.x * GBN;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int wm0 = (warp >> 2) * 64, wn0 = (warp & 3) * 32;
+  const int wr = warp >> 2, wn0 = (warp & 3) * 32;
   const int fr = lane >> 2, fc = lane & 3;  // fragment row (0..7) / k index (0..3)
   const int Mld = ALIGNED16 ? ((M + 1) & ~1) : M;
   const int Nld = ALIGNED16 ? ((g.N + 1) & ~1) : g.N;
+  const int mt_valid = m0 + GBM > M ? (M - m0 + 7) / 8 : 16;  // valid m-tiles of this row tile
+  const int nmt = PART ? (mt_valid - wr + 1) / 2 : 8;         // ... of which this warp row owns 2 i + wr < mt_valid
 
   double acc[8][4][2];
 #pragma unroll
@@ -134,17 +158,31 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) dgemm_tn_kernel(const GemmArg
     }
     const double* as = As + (kt % GSTAGES) * GBK * (GBM + GPAD);
     const double* bs = Bs + (kt % GSTAGES) * GBK * (GBN + GPAD);
+    if (!PART) {
 #pragma unroll
-    for (int kk = 0; kk < GBK; kk += 4) {
-      double af[8], bf[4];
+      for (int kk = 0; kk < GBK; kk += 4) {
+        double af[8], bf[4];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) af[i] = as[(kk + fc) * (GBM + GPAD) + wm0 + i * 8 + fr];
+        for (int i = 0; i < 8; ++i) af[i] = as[(kk + fc) * (GBM + GPAD) + wr * 64 + i * 8 + fr];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) bf[j] = bs[(kk + fc) * (GBN + GPAD) + wn0 + j * 8 + fr];
+        for (int j = 0; j < 4; ++j) bf[j] = bs[(kk + fc) * (GBN + GPAD) + wn0 + j * 8 + fr];
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
+        for (int i = 0; i < 8; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+          for (int j = 0; j < 4; ++j) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+      }
+    } else {
+      switch (nmt) {  // warp-uniform
+        case 8: gemm_ktile<8>(acc, as, bs, wr, wn0, fr, fc); break;
+        case 7: gemm_ktile<7>(acc, as, bs, wr, wn0, fr, fc); break;
+        case 6: gemm_ktile<6>(acc, as, bs, wr, wn0, fr, fc); break;
+        case 5: gemm_ktile<5>(acc, as, bs, wr, wn0, fr, fc); break;
+        case 4: gemm_ktile<4>(acc, as, bs, wr, wn0, fr, fc); break;
+        case 3: gemm_ktile<3>(acc, as, bs, wr, wn0, fr, fc); break;
+        case 2: gemm_ktile<2>(acc, as, bs, wr, wn0, fr, fc); break;
+        case 1: gemm_ktile<1>(acc, as, bs, wr, wn0, fr, fc); break;
+        default: break;
+      }
     }
   }
   cp_async_wait<0>();
@@ -152,7 +190,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) dgemm_tn_kernel(const GemmArg
   const long long yoff = (g.epi == EPI_Y_MINUS && g.y_off) ? g.y_off[grp] : 0;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    const int row = m0 + wm0 + i * 8 + fr;
+    const int row = m0 + (PART ? (2 * i + wr) * 8 : wr * 64 + i * 8) + fr;
     if (row >= M) continue;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -177,14 +215,20 @@ inline cudaError_t launch_dgemm_tn(const GemmArgs& g, cudaStream_t st) {
   dim3 grid((g.N + GBN - 1) / GBN, (g.M + GBM - 1) / GBM, g.groups);
   static bool configured = false;
   if (!configured) {
-    cudaFuncSetAttribute(dgemm_tn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM);
-    cudaFuncSetAttribute(dgemm_tn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM);
+    cudaFuncSetAttribute(dgemm_tn_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM);
+    cudaFuncSetAttribute(dgemm_tn_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM);
+    cudaFuncSetAttribute(dgemm_tn_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM);
+    cudaFuncSetAttribute(dgemm_tn_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM);
     configured = true;
   }
-  if (g.aligned16)
-    dgemm_tn_kernel<true><<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(g);
-  else
-    dgemm_tn_kernel<false><<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(g);
+  const bool part = g.Mg != nullptr || (g.M % GBM) != 0;
+  if (g.aligned16) {
+    if (part) dgemm_tn_kernel<true, true><<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(g);
+    else dgemm_tn_kernel<true, false><<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(g);
+  } else {
+    if (part) dgemm_tn_kernel<false, true><<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(g);
+    else dgemm_tn_kernel<false, false><<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(g);
+  }
   return cudaGetLastError();
 }
 
