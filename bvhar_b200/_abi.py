@@ -336,6 +336,8 @@ def load_library():
     L.bvhar_cuda_fit_record.argtypes = [vp, C.c_int, C.c_int, C.c_char_p, c_dp, C.c_int64, C.c_int64]
     L.bvhar_cuda_fit_record_all.argtypes = [vp, C.c_char_p, c_dp, C.c_int64, C.c_int64, C.c_int64]
     L.bvhar_cuda_fit_bind_record_sink.argtypes = [vp, C.c_char_p, c_dp, C.c_int64, C.c_int64, C.c_int64]
+    L.bvhar_cuda_is_stable.argtypes = [C.c_int, C.c_int64, C.c_int32, C.c_int32, C.c_int32, c_dp, C.c_int64, c_dp, C.c_int64, C.c_double,
+                                       C.POINTER(C.c_int32)]
     L.bvhar_cuda_fit_record_names.argtypes = [vp, C.c_char_p, C.c_int64]
     L.bvhar_cuda_fit_record_mean.argtypes = [vp, C.c_char_p, c_dp, C.c_int64]
     L.bvhar_cuda_fit_state_len.argtypes = [vp, C.c_char_p, C.POINTER(C.c_int64)]

@@ -215,19 +215,26 @@ class SvGrpMcmc(_McmcRun):
 
 
 # ------------------------------------------------------------------------------------------------
-def _stable_rows(coef: np.ndarray, dim: int, nrow: int, har: Optional[np.ndarray]) -> np.ndarray:
-    """``is_stable`` per draw (draw.h:1265-1295): companion-matrix spectral radius < 1."""
-    keep = np.zeros(coef.shape[0], dtype=bool)
-    for i in range(coef.shape[0]):
-        A = coef[i, : nrow * dim].reshape(nrow, dim, order="F")
-        if har is not None:
-            A = har.T @ A
-        m = A.shape[0]
-        comp = np.zeros((m, m))
-        comp[:dim, :] = A.T
-        comp[dim:, : m - dim] = np.eye(m - dim)
-        keep[i] = np.max(np.abs(np.linalg.eigvals(comp))) < 1
-    return keep
+def _stable_rows(coef: np.ndarray, dim: int, nrow: int, har: Optional[np.ndarray], device: int = 0, threshold: float = 1.0) -> np.ndarray:
+    """``is_stable`` per draw (draw.h:1265-1295: companion-matrix spectral radius < threshold), decided on the device by
+    ``bvhar_cuda_is_stable`` (repeated squaring of the companion matrix with the DMMA contraction, kernels_stable.cu).
+    ``har``: the top-left 3 dim x (month dim) corner of the HAR transformation for VHAR draws (forecaster.h:319)."""
+    from ._abi import load_library
+    draws = np.ascontiguousarray(coef, dtype=np.float64)
+    n = draws.shape[0]
+    out = np.zeros(n, dtype=np.int32)
+    if n == 0:
+        return out.astype(bool)
+    if har is not None:
+        hb = np.asfortranarray(har, dtype=np.float64)
+        lag = hb.shape[1] // dim
+        hp, ldh = hb.ctypes.data_as(c_dp), hb.shape[0]
+    else:
+        lag = nrow // dim
+        hp, ldh = None, 0
+    check(load_library().bvhar_cuda_is_stable(int(device), n, dim, nrow, lag, draws.ctypes.data_as(c_dp), draws.shape[1], hp, ldh,
+                                              float(threshold), out.ctypes.data_as(C.POINTER(C.c_int32))))
+    return out.astype(bool)
 
 
 def pack_forecast(units: Sequence[Dict[str, np.ndarray]], last_obs: Sequence[np.ndarray], step: int, var_lag: int,

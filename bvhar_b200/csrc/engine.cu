@@ -1413,6 +1413,67 @@ int bvhar_cuda_outforecast_run(const bvhar_fit_desc* fd, const bvhar_outforecast
   return 0;
 }
 
+// ---- stability filter of the forecasters (subsetStable config.h:884-914, 1003-1034; is_stable draw.h:1265-1295) ----
+int bvhar_cuda_is_stable(int device, int64_t n_draws, int32_t dim, int32_t nrow, int32_t lag, const double* coef, int64_t ld,
+                         const double* har_trans, int64_t ldh, double threshold, int32_t* out) {
+  if (!coef || !out) return fail(BVHAR_ERR_BAD_ARG, "null argument");
+  if (n_draws < 0 || dim < 1 || lag < 1 || nrow < 1 || ld < (int64_t)nrow * dim || !(threshold > 0.0)) return fail(BVHAR_ERR_BAD_ARG, "bad dimensions");
+  if (har_trans ? (nrow != 3 * dim || ldh < 3 * dim) : (nrow != dim * lag)) return fail(BVHAR_ERR_BAD_ARG, "coefficient rows do not match the lag structure");
+  if (n_draws == 0) return 0;
+  API_LOCK;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(BVHAR_ERR_CUDA, "no CUDA device available: no CPU fallback");
+  CU(cudaSetDevice(device));
+  pool_setup(device);
+  const int m = dim * lag, ldm = (m + 1) & ~1;
+  const size_t mat = (size_t)m * ldm;
+  const int64_t batch = std::max<int64_t>(1, std::min<int64_t>({n_draws, (int64_t)65535, (int64_t)((3ull << 30) / (4 * mat * sizeof(double)))}));
+  DevBuf<double> dcoef, dhar, R[2], Rt[2], logacc;
+  DevBuf<int> state, kg, undecided;
+  DevBuf<long long> off;
+  CU(dcoef.alloc((size_t)batch * ld)); CU(logacc.alloc((size_t)batch)); CU(state.alloc((size_t)batch)); CU(kg.alloc((size_t)batch));
+  CU(undecided.alloc(1));
+  for (auto& b : R) CU(b.alloc((size_t)batch * mat));
+  for (auto& b : Rt) CU(b.alloc((size_t)batch * mat));
+  if (har_trans) {
+    std::vector<double> h((size_t)m * 3 * dim);
+    for (int c = 0; c < m; ++c)
+      for (int r = 0; r < 3 * dim; ++r) h[(size_t)c * 3 * dim + r] = har_trans[(size_t)c * ldh + r];
+    CU(dhar.upload(h));
+  }
+  {
+    std::vector<long long> ho((size_t)batch);
+    for (int64_t g = 0; g < batch; ++g) ho[g] = (long long)(g * mat);
+    CU(off.upload(ho));
+  }
+  std::vector<int> hk((size_t)batch, m), hs((size_t)batch);
+  for (int64_t i0 = 0; i0 < n_draws; i0 += batch) {
+    const int64_t nb = std::min(batch, n_draws - i0);
+    CU(cudaMemcpy(dcoef.p, coef + (size_t)i0 * ld, (size_t)nb * ld * sizeof(double), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(kg.p, hk.data(), (size_t)nb * sizeof(int), cudaMemcpyHostToDevice));
+    CU(launch_stab_build(dcoef.p, ld, nb, dim, nrow, lag, dhar.p, 3 * dim, 1.0 / threshold, R[0].p, Rt[0].p, ldm, logacc.p, state.p, 0));
+    int cur = 0;
+    for (int it = 0; it < STAB_MAX_SQUARINGS; ++it) {
+      GemmArgs g{};
+      g.M = m; g.N = m; g.K = m; g.lda = ldm; g.ldb = ldm; g.ldc = ldm; g.groups = (int)nb;
+      g.a_off = off.p; g.b_off = off.p; g.c_off = off.p; g.Kg = kg.p; g.epi = EPI_STORE; g.aligned16 = 1;
+      g.A = Rt[cur].p; g.B = R[cur].p; g.C = R[cur ^ 1].p;   // (B^2)[r][c]   = sum_k B[r][k] B[k][c]
+      CU(launch_dgemm_tn(g, 0));
+      g.A = R[cur].p; g.B = Rt[cur].p; g.C = Rt[cur ^ 1].p;  // (B^2)'[r][c]  = sum_k B[k][r] B[c][k]
+      CU(launch_dgemm_tn(g, 0));
+      cur ^= 1;
+      CU(cudaMemsetAsync(undecided.p, 0, sizeof(int), 0));
+      CU(launch_stab_norm(R[cur].p, Rt[cur].p, nb, m, ldm, logacc.p, state.p, kg.p, undecided.p, 0));
+      int left = 0;
+      CU(cudaMemcpy(&left, undecided.p, sizeof(int), cudaMemcpyDeviceToHost));
+      if (left == 0) break;
+    }
+    CU(cudaMemcpy(hs.data(), state.p, (size_t)nb * sizeof(int), cudaMemcpyDeviceToHost));
+    for (int64_t i = 0; i < nb; ++i) out[i0 + i] = hs[i] == 1 ? 1 : 0;
+  }
+  return 0;
+}
+
 // ---- building blocks ------------------------------------------------------------------------
 int bvhar_cuda_dgemm_tn(int device, int64_t M, int64_t N, int64_t K, const double* A, int64_t lda, const double* B,
                         int64_t ldb, double* C, int64_t ldc) {

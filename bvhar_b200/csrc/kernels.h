@@ -49,6 +49,12 @@ cudaError_t launch_prior(const Dims& D, const DevPtrs& P, const PriorConst& C, i
 cudaError_t launch_scatter_lvol(const double* src, double* dst, int n, int M, int ldM, int nsrc, cudaStream_t st);
 cudaError_t launch_record_mean(const double* rec, int U, int cap, int cols, int rows, int thin, double* out, cudaStream_t st);
 cudaError_t launch_build_xx(const Dims& D, const DevPtrs& P, double* XX, cudaStream_t st);
+// stability filter (kernels_stable.cu)
+constexpr int STAB_MAX_SQUARINGS = 40;
+cudaError_t launch_stab_build(const double* coef, long long ld, long long n_mat, int k, int nrow, int p, const double* har, int ldh,
+                              double inv_thr, double* R, double* Rt, int ldm, double* logacc, int* state, cudaStream_t st);
+cudaError_t launch_stab_norm(double* R, double* Rt, long long n_mat, int m, int ldm, double* logacc, int* state, int* kg, int* undecided,
+                             cudaStream_t st);
 // forecast (kernels_forecast.cu)
 struct RecView {  // element (unit u, draw i, column c) = p[u * us + i * sd + c * sc]
   const double* p;

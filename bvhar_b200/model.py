@@ -248,7 +248,7 @@ class _AutoregBayes:
         """'n_ahead'-step density forecast from the stored draws (forecaster.h:494-568)."""
         recs = self._chain_records()
         seeds = self._seeds(self.chains_)
-        if stable:  # the host-side stability filter may keep a different number of draws per chain: one call per chain
+        if stable:  # the stability filter (bvhar_cuda_is_stable) may keep a different number of draws per chain: one call per chain
             dens = [forecast_density([rec], [self.y_], n_ahead, self.lag_, self.fit_intercept, self._is_sv, [seeds[c]],
                                      har_trans=self._har(), sv=sv, stable=True, sparse=sparse, device=self._device,
                                      unit_id_base=c)[0][0] for c, rec in enumerate(recs)]
@@ -282,7 +282,7 @@ class _AutoregBayes:
         C_ = self.chains_
         def per_unit(units, lasts, seeds_u, base):
             """stable=True: the stability filter (subsetStable, config.h:884-914, 1003-1034: companion-matrix eigenvalues
-            per draw) runs on the host and may keep a different number of draws per unit -> one forecaster call per unit."""
+            per draw, decided on the device by bvhar_cuda_is_stable) may keep a different number of draws per unit -> one forecaster call per unit."""
             outs, lps = [], []
             for i, (rec, lo, sd) in enumerate(zip(units, lasts, seeds_u)):
                 dens, lp = forecast_density([rec], [lo], n_ahead, self.lag_, self.fit_intercept, self._is_sv, [sd],

@@ -308,6 +308,18 @@ typedef struct {
 int bvhar_cuda_outforecast_run(const bvhar_fit_desc* fit, const bvhar_outforecast_params* fc, double* out_forecast,
                                double* out_lpl);
 
+/* ---- stability filter of the forecasters ---------------------------------------------------------
+ * Replaces subsetStable (config.h:884-914, 1003-1034) -> is_stable / build_companion / root_unitcircle (draw.h:1265-1295)
+ * for a batch of draws: out[i] = 1 when every eigenvalue of the VAR(1) companion matrix of draw i has modulus <
+ * `threshold` (the forecasters pass 1, forecaster.h:283, 319).  coef: draw i at coef + i * ld, the first nrow * dim
+ * entries being coef_record.row(i).head(num_alpha) (equation-major: alpha[j * nrow + r] = A(r, j)).  VAR: nrow = dim * lag,
+ * har_trans = NULL.  VHAR: nrow = 3 * dim, lag = month and har_trans = the top-left 3 dim x (month dim) corner of the
+ * HAR transformation, column-major with leading dimension ldh (forecaster.h:319).  The decision is taken on the device by
+ * repeated squaring of companion / threshold (||B^N|| < 1 <=> stable; |trace(B^N)| > m => unstable); see
+ * bvhar_b200/csrc/kernels_stable.cu. */
+int bvhar_cuda_is_stable(int device, int64_t n_draws, int32_t dim, int32_t nrow, int32_t lag, const double* coef, int64_t ld,
+                         const double* har_trans, int64_t ldh, double threshold, int32_t* out);
+
 /* ---- fp64 building blocks exported for stage-level parity tests and the roofline bench ---- */
 /* C[M x N] (row-major, ldc) = alpha * A^T B + beta * C with A stored K x M row-major (lda) and
  * B stored K x N row-major (ldb): the DMMA contraction that builds the SV-weighted Gram
