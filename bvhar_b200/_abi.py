@@ -94,6 +94,16 @@ class ForecastDesc(C.Structure):
     ]
 
 
+class SpilloverDesc(C.Structure):
+    """bvhar_spillover_desc (include/bvhar_cuda.h)."""
+    _fields_ = [
+        ("abi_version", C.c_int32), ("device", C.c_int32), ("dim", C.c_int32), ("nrow", C.c_int32), ("lag", C.c_int32),
+        ("step", C.c_int32), ("sv_kind", C.c_int32), ("n_time", C.c_int32), ("n_draws", C.c_int64),
+        ("coef", c_dp), ("ld_coef", C.c_int64), ("contem", c_dp), ("ld_contem", C.c_int64), ("sv", c_dp), ("ld_sv", C.c_int64),
+        ("har_trans", c_dp), ("ldh", C.c_int64),
+    ]
+
+
 class OutforecastParams(C.Structure):
     _fields_ = [
         ("abi_version", C.c_int32), ("step", C.c_int32), ("var_lag", C.c_int32), ("is_vhar", C.c_int32),
@@ -336,6 +346,7 @@ def load_library():
     L.bvhar_cuda_fit_record.argtypes = [vp, C.c_int, C.c_int, C.c_char_p, c_dp, C.c_int64, C.c_int64]
     L.bvhar_cuda_fit_record_all.argtypes = [vp, C.c_char_p, c_dp, C.c_int64, C.c_int64, C.c_int64]
     L.bvhar_cuda_fit_bind_record_sink.argtypes = [vp, C.c_char_p, c_dp, C.c_int64, C.c_int64, C.c_int64]
+    L.bvhar_cuda_spillover.argtypes = [C.POINTER(SpilloverDesc), c_dp, c_dp, c_dp, c_dp, c_dp]
     L.bvhar_cuda_is_stable.argtypes = [C.c_int, C.c_int64, C.c_int32, C.c_int32, C.c_int32, c_dp, C.c_int64, c_dp, C.c_int64, C.c_double,
                                        C.POINTER(C.c_int32)]
     L.bvhar_cuda_fit_record_names.argtypes = [vp, C.c_char_p, C.c_int64]

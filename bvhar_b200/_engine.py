@@ -237,6 +237,35 @@ def _stable_rows(coef: np.ndarray, dim: int, nrow: int, har: Optional[np.ndarray
     return out.astype(bool)
 
 
+def spillover(coef: np.ndarray, contem: np.ndarray, sv: np.ndarray, dim: int, nrow: int, lag: int, step: int,
+              har_trans: Optional[np.ndarray] = None, sv_kind: int = 0, n_time: int = 0, device: int = 0) -> Dict[str, np.ndarray]:
+    """``McmcSpilloverRun<RecordType>::returnSpillover()`` (spillover.h:246-260) for the draws in the rows of ``coef`` /
+    ``contem`` / ``sv``: the ``connect`` / ``to`` / ``from`` / ``tot`` / ``net`` / ``net_pairwise`` densities, computed on
+    the device (``bvhar_cuda_spillover``).  ``sv_kind``: 0 = ``d_record`` rows, 1 = log-volatilities of one time point,
+    2 = whole ``h_record`` rows (``n_time`` x dim, time average of exp(h / 2), config.h:980-988)."""
+    from ._abi import SpilloverDesc, load_library
+    cf = np.ascontiguousarray(coef, dtype=np.float64)
+    S = cf.shape[0]
+    q = dim * (dim - 1) // 2
+    ac = np.ascontiguousarray(contem, dtype=np.float64).reshape(S, -1) if q > 0 else np.zeros((S, 1))
+    sc = np.ascontiguousarray(sv, dtype=np.float64).reshape(S, -1)
+    D = SpilloverDesc()
+    D.abi_version = _abi.ABI_VERSION; D.device = int(device); D.dim = dim; D.nrow = nrow; D.lag = lag; D.step = int(step)
+    D.sv_kind = int(sv_kind); D.n_time = int(n_time); D.n_draws = S
+    D.coef = cf.ctypes.data_as(c_dp); D.ld_coef = cf.shape[1]
+    D.contem = ac.ctypes.data_as(c_dp); D.ld_contem = ac.shape[1]
+    D.sv = sc.ctypes.data_as(c_dp); D.ld_sv = sc.shape[1]
+    hb = None
+    if har_trans is not None:
+        hb = np.asfortranarray(np.asarray(har_trans, dtype=np.float64)[: 3 * dim, : lag * dim])
+        D.har_trans = hb.ctypes.data_as(c_dp); D.ldh = hb.shape[0]
+    connect = np.empty((dim, S * dim), order="F"); net_pw = np.empty((dim, S * dim), order="F")
+    to = np.empty(S * dim); frm = np.empty(S * dim); tot = np.empty(S)
+    check(load_library().bvhar_cuda_spillover(C.byref(D), connect.ctypes.data_as(c_dp), to.ctypes.data_as(c_dp), frm.ctypes.data_as(c_dp),
+                                              tot.ctypes.data_as(c_dp), net_pw.ctypes.data_as(c_dp)))
+    return {"connect": connect, "to": to, "from": frm, "tot": tot, "net": to - frm, "net_pairwise": net_pw}
+
+
 def pack_forecast(units: Sequence[Dict[str, np.ndarray]], last_obs: Sequence[np.ndarray], step: int, var_lag: int,
                   include_mean: bool, sv_model: bool, seeds, har_trans: Optional[np.ndarray] = None, sv: bool = True,
                   valid_vec: Optional[np.ndarray] = None, stable: bool = False, sparse: bool = False,

@@ -1474,6 +1474,60 @@ int bvhar_cuda_is_stable(int device, int64_t n_draws, int32_t dim, int32_t nrow,
   return 0;
 }
 
+// ---- spillover densities (McmcSpilloverRun::returnSpillover, spillover.h:246-260) ----
+int bvhar_cuda_spillover(const bvhar_spillover_desc* d, double* connect, double* to, double* from, double* tot, double* net_pairwise) {
+  if (!d || !connect || !to || !from || !tot || !net_pairwise) return fail(BVHAR_ERR_BAD_ARG, "null argument");
+  if (d->abi_version != BVHAR_CUDA_ABI_VERSION) return fail(BVHAR_ERR_BAD_ARG, "descriptor ABI version mismatch");
+  const int k = d->dim, p = d->lag, step = d->step, q = k * (k - 1) / 2;
+  if (k < 1 || p < 1 || d->n_draws < 0 || !d->coef || !d->sv || (q > 0 && !d->contem)) return fail(BVHAR_ERR_BAD_ARG, "bad spillover descriptor");
+  if (step < 2) return fail(BVHAR_ERR_BAD_ARG, "'lag_max' must larger than 0");  // lag_max = step - 1 (spillover.h:170); structural.h:10-12
+  if (d->har_trans ? (d->nrow != 3 * k || d->ldh < 3 * k) : (d->nrow != k * p)) return fail(BVHAR_ERR_BAD_ARG, "coefficient rows do not match the lag structure");
+  if (d->sv_kind < 0 || d->sv_kind > 2 || (d->sv_kind == 2 && d->n_time < 1)) return fail(BVHAR_ERR_BAD_ARG, "bad sv_kind / n_time");
+  if (d->n_draws == 0) return 0;
+  API_LOCK;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(BVHAR_ERR_CUDA, "no CUDA device available: no CPU fallback");
+  CU(cudaSetDevice(d->device));
+  pool_setup(d->device);
+  const int64_t S = d->n_draws;
+  const size_t svw = d->sv_kind == 2 ? (size_t)d->n_time * k : (size_t)k;
+  if (d->ld_coef < (int64_t)d->nrow * k || d->ld_contem < q || d->ld_sv < (int64_t)svw) return fail(BVHAR_ERR_BAD_ARG, "leading dimensions too small");
+  DevBuf<double> dc, da, dsv, dh, scratch, oc, ot, of, otot, on;
+  const int64_t batch = std::min<int64_t>(S, std::max<int64_t>(1, (int64_t)((1ull << 30) / (sizeof(double) * (d->ld_coef + d->ld_contem + d->ld_sv + 2 * (size_t)k * k + 3 * k)))));
+  CU(dc.alloc((size_t)batch * d->ld_coef)); CU(da.alloc((size_t)batch * std::max<int64_t>(1, d->ld_contem))); CU(dsv.alloc((size_t)batch * d->ld_sv));
+  CU(oc.alloc((size_t)batch * k * k)); CU(on.alloc((size_t)batch * k * k)); CU(ot.alloc((size_t)batch * k)); CU(of.alloc((size_t)batch * k));
+  CU(otot.alloc((size_t)batch));
+  if (d->har_trans) {
+    std::vector<double> h((size_t)p * k * 3 * k);
+    for (int r = 0; r < p * k; ++r)
+      for (int qq = 0; qq < 3 * k; ++qq) h[(size_t)r * 3 * k + qq] = d->har_trans[(size_t)r * d->ldh + qq];
+    CU(dh.upload(h));
+  }
+  const int n_cta = (int)std::min<int64_t>(batch, 592);
+  SpilloverArgs A{};
+  A.k = k; A.nrow = d->nrow; A.lag = p; A.step = step; A.sv_kind = d->sv_kind; A.n_time = d->n_time; A.ldh = 3 * k;
+  A.ld_coef = d->ld_coef; A.ld_contem = d->ld_contem; A.ld_sv = d->ld_sv;
+  A.coef = dc.p; A.contem = da.p; A.sv = dsv.p; A.har = dh.p;
+  A.slab = spillover_slab_doubles(k, p, step);
+  CU(scratch.alloc((size_t)n_cta * A.slab));
+  A.scratch = scratch.p; A.connect = oc.p; A.to = ot.p; A.from = of.p; A.tot = otot.p; A.net_pairwise = on.p;
+  for (int64_t i0 = 0; i0 < S; i0 += batch) {
+    const int64_t nb = std::min(batch, S - i0);
+    CU(cudaMemcpy(dc.p, d->coef + (size_t)i0 * d->ld_coef, (size_t)nb * d->ld_coef * sizeof(double), cudaMemcpyHostToDevice));
+    if (q > 0) CU(cudaMemcpy(da.p, d->contem + (size_t)i0 * d->ld_contem, (size_t)nb * d->ld_contem * sizeof(double), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(dsv.p, d->sv + (size_t)i0 * d->ld_sv, (size_t)nb * d->ld_sv * sizeof(double), cudaMemcpyHostToDevice));
+    A.n_draws = nb;
+    CU(launch_spillover(A, n_cta, 0));
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpy(connect + (size_t)i0 * k * k, oc.p, (size_t)nb * k * k * sizeof(double), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(net_pairwise + (size_t)i0 * k * k, on.p, (size_t)nb * k * k * sizeof(double), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(to + (size_t)i0 * k, ot.p, (size_t)nb * k * sizeof(double), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(from + (size_t)i0 * k, of.p, (size_t)nb * k * sizeof(double), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(tot + (size_t)i0, otot.p, (size_t)nb * sizeof(double), cudaMemcpyDeviceToHost));
+  }
+  return 0;
+}
+
 // ---- building blocks ------------------------------------------------------------------------
 int bvhar_cuda_dgemm_tn(int device, int64_t M, int64_t N, int64_t K, const double* A, int64_t lda, const double* B,
                         int64_t ldb, double* C, int64_t ldc) {

@@ -55,6 +55,17 @@ cudaError_t launch_stab_build(const double* coef, long long ld, long long n_mat,
                               double inv_thr, double* R, double* Rt, int ldm, double* logacc, int* state, cudaStream_t st);
 cudaError_t launch_stab_norm(double* R, double* Rt, long long n_mat, int m, int ldm, double* logacc, int* state, int* kg, int* undecided,
                              cudaStream_t st);
+// spillover densities (kernels_spillover.cu)
+struct SpilloverArgs {
+  int k, nrow, lag, step, sv_kind, n_time, ldh;
+  long long n_draws, ld_coef, ld_contem, ld_sv;
+  const double *coef, *contem, *sv, *har;  // har: (lag k) rows x ldh: har[r * ldh + q] = har_trans(q, r)
+  double* scratch;
+  size_t slab;
+  double *connect, *to, *from, *tot, *net_pairwise;
+};
+size_t spillover_slab_doubles(int k, int lag, int step);
+cudaError_t launch_spillover(const SpilloverArgs& A, int n_cta, cudaStream_t st);
 // forecast (kernels_forecast.cu)
 struct RecView {  // element (unit u, draw i, column c) = p[u * us + i * sd + c * sc]
   const double* p;

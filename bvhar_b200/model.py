@@ -259,6 +259,42 @@ class _AutoregBayes:
         allchains = np.concatenate([d.reshape(n_ahead, -1, k) for d in dens], axis=1).reshape(n_ahead, -1)
         return self._summarise(allchains, k, level, med)
 
+    def spillover(self, n_ahead: int = 10, level=.05, sparse=True):
+        """Spillover densities from the stored draws of all chains (the reference's ``spillover()``, _bayes.py:611-641 ->
+        ``LdltSpillover`` / ``SvSpillover`` = ``McmcSpilloverRun``, spillover.h:246-260), computed on the device."""
+        if not self.is_fitted_:
+            raise RuntimeError("call fit() first")
+        from ._engine import spillover as _spillover
+        k = self.n_features_in_
+        sfx = "_sparse_record" if sparse else "_record"
+        if sparse and "alpha_sparse_record" not in self.param_:
+            raise ValueError("sparse draws were not recorded")
+        coef = np.concatenate(list(self.param_["alpha" + sfx]), axis=0)   # concat_params(..., chain=False): every chain's draws
+        contem = np.concatenate(list(self.param_["a" + sfx]), axis=0) if k > 1 else np.zeros((coef.shape[0], 1))
+        nrow = coef.shape[1] // k
+        if self._is_sv:
+            if "h_record" not in self.param_:
+                raise ValueError("spillover() of an SV fit needs the full 'h_record'")
+            sv = np.concatenate(list(self.param_["h_record"]), axis=0)
+            kind, n_time = 2, sv.shape[1] // k
+        else:
+            sv = np.concatenate(list(self.param_["d_record"]), axis=0)
+            kind, n_time = 0, 0
+        out = _spillover(coef, contem, sv, k, nrow, self.lag_, n_ahead, har_trans=self._har(), sv_kind=kind, n_time=n_time, device=self._device)
+
+        def tab(m, lv=None):  # process_dens_spillover, _misc.py:172-181
+            st = np.stack(np.array_split(m, m.shape[1] // k, axis=1), axis=0)
+            return {"mean": st.mean(axis=0), "se": st.std(axis=0), "lower": np.quantile(st, level / 2, axis=0),
+                    "upper": np.quantile(st, 1 - level / 2, axis=0)}
+
+        def vec(v):  # process_dens_vector_spillover, _misc.py:183-190
+            r = v.reshape(-1, k)
+            return {"mean": r.mean(axis=0), "se": r.std(axis=0), "lower": np.quantile(r, level / 2, axis=0),
+                    "upper": np.quantile(r, 1 - level / 2, axis=0)}
+
+        return {"connect": tab(out["connect"]), "net_pairwise": tab(out["net_pairwise"]), "tot": vec(out["tot"]),
+                "to": vec(out["to"]), "from": vec(out["from"]), "net": vec(out["net"])}
+
     def _outforecast(self, n_ahead: int, test, expanding: bool, level, stable, sparse, med, sv):
         """forecast_roll / forecast_expand: window 0 reuses the fit, windows >= 1 are refitted, every
         (window, chain) in one GPU batch (forecaster.h:575-807, 851-875, 920-956)."""

@@ -320,6 +320,38 @@ int bvhar_cuda_outforecast_run(const bvhar_fit_desc* fit, const bvhar_outforecas
 int bvhar_cuda_is_stable(int device, int64_t n_draws, int32_t dim, int32_t nrow, int32_t lag, const double* coef, int64_t ld,
                          const double* har_trans, int64_t ldh, double threshold, int32_t* out);
 
+/* ---- spillover densities from stored draws ------------------------------------------------------
+ * Replaces McmcSpilloverRun<RecordType>::returnSpillover() / McmcSpillover::computeSpillover (spillover.h:48-81, 246-260;
+ * bound by src/triangular.cpp:636-647 and python/src/bvhar/_src/_cta.cpp) and the structural.h helpers it calls
+ * (convert_var_to_vma :8-36, convert_vhar_to_vma :54-78, compute_vma_fevd :100-127, compute_sp_index / _to / _from /
+ * _tot / _net :129-152) for a batch of draws.  Per draw i: coef + i * ld_coef holds alpha (equation-major, constants not
+ * used), contem + i * ld_contem the q contemporaneous coefficients, sv + i * ld_sv the record the innovation scale D^(1/2)
+ * comes from (updateDiag, config.h:876-881, 980-996): sv_kind 0 = d_record row (sqrt), 1 = log-volatilities at one time
+ * point (exp(h / 2)), 2 = the whole h_record row, n_time x dim time-major (time average of exp(h / 2)).
+ * VHAR: nrow = 3 dim, lag = month, har_trans = HAR transformation without constant, 3 dim x (month dim) column-major. */
+typedef struct {
+  int32_t abi_version;
+  int32_t device;
+  int32_t dim;
+  int32_t nrow;   /* dim * lag (VAR) or 3 * dim (VHAR) */
+  int32_t lag;    /* p, or month */
+  int32_t step;   /* lag_max of McmcSpillover: horizon of the FEVD */
+  int32_t sv_kind;
+  int32_t n_time; /* sv_kind 2 */
+  int64_t n_draws;
+  const double* coef;
+  int64_t ld_coef;
+  const double* contem;
+  int64_t ld_contem;
+  const double* sv;
+  int64_t ld_sv;
+  const double* har_trans; /* NULL for VAR */
+  int64_t ldh;
+} bvhar_spillover_desc;
+/* connect, net_pairwise: dim x (n_draws * dim) column-major; to, from: n_draws * dim; tot: n_draws
+ * (returnSpilloverDensity, spillover.h:72-81; "net" = to - from). */
+int bvhar_cuda_spillover(const bvhar_spillover_desc* desc, double* connect, double* to, double* from, double* tot, double* net_pairwise);
+
 /* ---- fp64 building blocks exported for stage-level parity tests and the roofline bench ---- */
 /* C[M x N] (row-major, ldc) = alpha * A^T B + beta * C with A stored K x M row-major (lda) and
  * B stored K x N row-major (ldb): the DMMA contraction that builds the SV-weighted Gram

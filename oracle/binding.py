@@ -58,6 +58,8 @@ def lib():
         L.oracle_draw_coef_packed.restype = None
         L.oracle_dgemm_tn.argtypes = [C.c_int, C.c_int, C.c_int, c_dp, c_dp, c_dp]
         L.oracle_dgemm_tn.restype = None
+        L.oracle_spillover.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp]
+        L.oracle_spillover.restype = None
         L.oracle_philox4x32_10.argtypes = [C.POINTER(C.c_uint32)] * 3
         L.oracle_philox4x32_10.restype = None
         L.oracle_sample.argtypes = [C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_double, C.c_double, C.c_double, C.c_int, c_dp]

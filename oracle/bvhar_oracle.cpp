@@ -1345,6 +1345,119 @@ void oracle_dgemm_tn(int M, int N, int K, const double* A, const double* B, doub
       C[(size_t)i * N + j] = s;
     }
 }
+// ---- spillover of one draw: McmcSpillover::computeSpillover (spillover.h:48-66), written as the reference writes it ----
+// convert_var_to_vma / convert_vhar_to_vma (math/structural.h:8-36, 54-78)
+static Mat oracle_var_to_vma(const Mat& var_coef, int var_lag, int lag_max) {
+  const int dim = var_coef.c;
+  const int ma_rows = dim * (lag_max + 1);
+  int num_full_arows = ma_rows;
+  if (lag_max < var_lag) num_full_arows = dim * var_lag;
+  Mat FullA(num_full_arows, dim);
+  for (int j = 0; j < dim; ++j)
+    for (int i = 0; i < dim * var_lag; ++i) FullA(i, j) = var_coef(i, j);
+  Mat ma(ma_rows, dim);
+  for (int i = 0; i < dim; ++i) ma(i, i) = 1.0;  // W0 = Im
+  if (lag_max >= 1)
+    for (int r = 0; r < dim; ++r)
+      for (int c = 0; c < dim; ++c) {
+        double sacc = 0;
+        for (int m = 0; m < dim; ++m) sacc += FullA(r, m) * ma(m, c);
+        ma(dim + r, c) = sacc;
+      }
+  for (int i = 2; i < lag_max + 1; ++i)
+    for (int kq = 0; kq < i; ++kq)
+      for (int r = 0; r < dim; ++r)
+        for (int c = 0; c < dim; ++c) {
+          double sacc = 0;
+          for (int m = 0; m < dim; ++m) sacc += FullA(kq * dim + r, m) * ma((i - kq - 1) * dim + m, c);
+          ma(i * dim + r, c) += sacc;
+        }
+  return ma;
+}
+// compute_vma_fevd (math/structural.h:100-127)
+static Mat oracle_vma_fevd(const Mat& vma, const Mat& cov, bool normalize) {
+  const int dim = cov.c, step = vma.r / dim;
+  Mat innov(dim, dim), numer(dim, dim), res(dim * step, dim), ma_prod(dim, dim);
+  for (int i = 0; i < step; ++i) {
+    for (int r = 0; r < dim; ++r)
+      for (int c = 0; c < dim; ++c) {
+        double sacc = 0;
+        for (int m = 0; m < dim; ++m) sacc += vma(i * dim + m, r) * cov(m, c);  // block' * Sigma
+        ma_prod(r, c) = sacc;
+      }
+    for (int r = 0; r < dim; ++r)
+      for (int c = 0; c < dim; ++c) {
+        double sacc = 0;
+        for (int m = 0; m < dim; ++m) sacc += ma_prod(r, m) * vma(i * dim + m, c);
+        innov(r, c) += sacc;
+        const double v = ma_prod(r, c) * (1.0 / std::sqrt(cov(c, c)));
+        numer(r, c) += v * v;
+      }
+    for (int r = 0; r < dim; ++r)
+      for (int c = 0; c < dim; ++c) res(i * dim + r, c) = (1.0 / innov(r, r)) * numer(r, c);
+  }
+  if (normalize)
+    for (int r = 0; r < dim * step; ++r) {
+      double rs = 0;
+      for (int c = 0; c < dim; ++c) rs += res(r, c);
+      for (int c = 0; c < dim; ++c) res(r, c) /= rs;
+    }
+  return res;
+}
+// alpha: equation-major coefficients of one draw; a: q contemporaneous coefficients; sv: D^(1/2) (dim); har: 3 dim x
+// (lag dim) column-major or NULL.  Outputs: connect / net_pairwise dim x dim column-major, to / from dim, tot 1.
+void oracle_spillover(int dim, int nrow, int lag, int step, const double* alpha, const double* a, const double* sv, const double* har,
+                      double* connect, double* to, double* from, double* tot, double* net_pairwise) {
+  Mat L(dim, dim);  // build_inv_lower (draw.h:124-132)
+  for (int i = 0; i < dim; ++i) {
+    L(i, i) = 1.0;
+    for (int j = 0; j < i; ++j) L(i, j) = a[i * (i - 1) / 2 + j];
+  }
+  Mat sq(dim, dim);  // L^-1 diag(sv): unit-lower solve, column by column
+  for (int c = 0; c < dim; ++c)
+    for (int r = 0; r < dim; ++r) {
+      double sacc = (r == c) ? sv[c] : 0.0;
+      for (int m = 0; m < r; ++m) sacc -= L(r, m) * sq(m, c);
+      sq(r, c) = sacc;
+    }
+  Mat cov(dim, dim);
+  for (int r = 0; r < dim; ++r)
+    for (int c = 0; c < dim; ++c) {
+      double sacc = 0;
+      for (int m = 0; m < dim; ++m) sacc += sq(r, m) * sq(c, m);
+      cov(r, c) = sacc;
+    }
+  Mat coef(nrow, dim);  // unvectorize
+  for (int j = 0; j < dim; ++j)
+    for (int i = 0; i < nrow; ++i) coef(i, j) = alpha[(size_t)j * nrow + i];
+  Mat var_coef = coef;
+  if (har) {  // HARtrans' * Phi (structural.h:56)
+    var_coef = Mat(lag * dim, dim);
+    for (int r = 0; r < lag * dim; ++r)
+      for (int j = 0; j < dim; ++j) {
+        double sacc = 0;
+        for (int qq = 0; qq < nrow; ++qq) sacc += har[(size_t)r * nrow + qq] * coef(qq, j);
+        var_coef(r, j) = sacc;
+      }
+  }
+  const Mat vma = oracle_var_to_vma(var_coef, lag, step - 1);
+  const Mat fevd = oracle_vma_fevd(vma, cov, true);
+  Mat sp(dim, dim);  // compute_sp_index: bottom rows * 100
+  for (int r = 0; r < dim; ++r)
+    for (int c = 0; c < dim; ++c) sp(r, c) = fevd((step - 1) * dim + r, c) * 100;
+  double off = 0;
+  for (int c = 0; c < dim; ++c) {
+    double tsum = 0, fsum = 0;
+    for (int r = 0; r < dim; ++r) {
+      connect[(size_t)c * dim + r] = sp(r, c);
+      net_pairwise[(size_t)c * dim + r] = (sp(c, r) - sp(r, c)) / dim;
+      if (r != c) { tsum += sp(r, c); fsum += sp(c, r); off += sp(r, c); }
+    }
+    to[c] = tsum;
+    from[c] = fsum;
+  }
+  *tot = off / dim;
+}
 void oracle_philox4x32_10(const uint32_t* ctr, const uint32_t* key, uint32_t* out) { philox4x32_10(ctr, key, out); }
 
 // Sampler access for distribution tests. kind: 0 normal, 1 uniform, 2 gamma(p0,p1), 3 beta(p0,p1),

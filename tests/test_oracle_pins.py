@@ -214,3 +214,41 @@ def test_window_table_matches_explicit_slices():
         for c in range(2):
             assert_allclose(f.record("alpha_record", w, c), g.record("alpha_record", 0, c), rtol=1e-12, atol=1e-14)
             assert_allclose(f.record("h_record", w, c), g.record("h_record", 0, c), rtol=1e-12, atol=1e-14)
+
+
+@pytest.mark.parametrize("dim,lag,step", [(2, 1, 3), (3, 2, 10), (5, 4, 6)])
+def test_oracle_spillover_against_companion_form(dim, lag, step):
+    """oracle_spillover (literal restatement of spillover.h:48-66 + math/structural.h) against an independent derivation:
+    Phi_h = top-left block of the h-th power of the companion matrix, Sigma = L^-1 D L^-T, generalised FEVD
+    theta_ij = sigma_jj^-1 sum_h (Phi_h Sigma)_ij^2 / sum_h (Phi_h Sigma Phi_h')_ii (Diebold-Yilmaz), rows normalised."""
+    rng = np.random.default_rng(dim + 10 * lag)
+    nrow = dim * lag
+    A = rng.normal(size=(nrow, dim)) * 0.25
+    a = rng.normal(size=max(1, dim * (dim - 1) // 2)) * 0.3
+    d = rng.uniform(0.3, 2.0, size=dim)
+    L = np.eye(dim)
+    for i in range(dim):
+        for j in range(i):
+            L[i, j] = a[i * (i - 1) // 2 + j]
+    Li = np.linalg.inv(L)
+    Sigma = Li @ np.diag(d) @ Li.T
+    F = np.zeros((nrow, nrow)); F[:dim, :] = A.T; F[dim:, :nrow - dim] = np.eye(nrow - dim)
+    num = np.zeros((dim, dim)); den = np.zeros(dim)
+    P = np.eye(nrow)
+    for h in range(step):
+        Phi = P[:dim, :dim]
+        PS = Phi @ Sigma
+        num += PS ** 2 / np.diag(Sigma)[None, :]
+        den += np.diag(PS @ Phi.T)
+        P = F @ P
+    theta = num / den[:, None]
+    sp = 100 * theta / theta.sum(axis=1, keepdims=True)
+    off = sp - np.diag(np.diag(sp))
+    c = np.empty(dim * dim); n = np.empty(dim * dim); t = np.empty(dim); f = np.empty(dim); tt = np.empty(1)
+    ob.lib().oracle_spillover(dim, nrow, lag, step, ob.dp(np.ascontiguousarray(A.reshape(-1, order="F"))), ob.dp(a), ob.dp(np.sqrt(d)),
+                              ob.c_dp(), ob.dp(c), ob.dp(t), ob.dp(f), ob.dp(tt), ob.dp(n))
+    assert_allclose(c.reshape(dim, dim, order="F"), sp, rtol=1e-10)
+    assert_allclose(t, off.sum(axis=0), rtol=1e-10, atol=1e-12)
+    assert_allclose(f, off.sum(axis=1), rtol=1e-10, atol=1e-12)
+    assert_allclose(tt[0], off.sum() / dim, rtol=1e-10)
+    assert_allclose(n.reshape(dim, dim, order="F"), (sp.T - sp) / dim, rtol=1e-9, atol=1e-11)
