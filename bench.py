@@ -259,23 +259,27 @@ def main():
         m_warm.fit()
         del m_warm
         gc.collect()
-        m2 = build_model(args.chains, W + K, W, seed=2000 + rank, device=local, prior=args.prior, record_mask=REC_ALL)
-        h2d = m2.design_.nbytes + m2.response_.nbytes + sum(sum(np.asarray(v).nbytes for v in ini.values()) for ini in m2.init_)
-        barrier()
-        t0 = time.perf_counter()
-        m2.fit()
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        d2h = sum(a.nbytes for a in m2.param_.values())
-        te = torch.tensor([dt], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        dt = float(te.item())
+        dts = []
+        for rep in range(3):  # three timed fits, each a fresh model and fresh outputs; the median is reported
+            m2 = build_model(args.chains, W + K, W, seed=2000 + 10 * rep + rank, device=local, prior=args.prior, record_mask=REC_ALL)
+            h2d = m2.design_.nbytes + m2.response_.nbytes + sum(sum(np.asarray(v).nbytes for v in ini.values()) for ini in m2.init_)
+            barrier()
+            t0 = time.perf_counter()
+            m2.fit()
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            d2h = sum(a.nbytes for a in m2.param_.values())
+            te = torch.tensor([dt], dtype=torch.float64, device="cuda")
+            if world > 1:
+                dist.all_reduce(te, op=dist.ReduceOp.MAX)
+            dts.append(float(te.item()))
+            del m2
+            gc.collect()
+        dt = sorted(dts)[1]
         e2e = {"value": world * args.chains * (W + K) / dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d / (W + K)),
-               "d2h_bytes_per_step": int(d2h / K), "sweeps": W + K, "recorded_draws": K, "seconds": dt,
+               "d2h_bytes_per_step": int(d2h / K), "sweeps": W + K, "recorded_draws": K, "seconds": dt, "seconds_all": dts,
                "note": "VharBayes.fit(): pack + H2D + (warm-up + K) sweeps + D2H of every record incl. h_record into pooled page-locked "
-                       "host memory (pool warmed by one untimed fit)"}
-        del m2
+                       "host memory, streamed out while later sweeps sample (pool warmed by one untimed fit; median of 3 timed fits)"}
 
     if rank != 0:
         if world > 1:
