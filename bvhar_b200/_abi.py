@@ -104,6 +104,12 @@ class SpilloverDesc(C.Structure):
     ]
 
 
+class DynspillParams(C.Structure):
+    """bvhar_dynspill_params (include/bvhar_cuda.h)."""
+    _fields_ = [("abi_version", C.c_int32), ("step", C.c_int32), ("var_lag", C.c_int32), ("sparse", C.c_int32),
+                ("har_trans", c_dp), ("ldh", C.c_int64)]
+
+
 class OutforecastParams(C.Structure):
     _fields_ = [
         ("abi_version", C.c_int32), ("step", C.c_int32), ("var_lag", C.c_int32), ("is_vhar", C.c_int32),
@@ -347,6 +353,7 @@ def load_library():
     L.bvhar_cuda_fit_record_all.argtypes = [vp, C.c_char_p, c_dp, C.c_int64, C.c_int64, C.c_int64]
     L.bvhar_cuda_fit_bind_record_sink.argtypes = [vp, C.c_char_p, c_dp, C.c_int64, C.c_int64, C.c_int64]
     L.bvhar_cuda_spillover.argtypes = [C.POINTER(SpilloverDesc), c_dp, c_dp, c_dp, c_dp, c_dp]
+    L.bvhar_cuda_dynamic_spillover.argtypes = [C.POINTER(FitDesc), C.POINTER(DynspillParams), c_dp, c_dp, c_dp]
     L.bvhar_cuda_is_stable.argtypes = [C.c_int, C.c_int64, C.c_int32, C.c_int32, C.c_int32, c_dp, C.c_int64, c_dp, C.c_int64, C.c_double,
                                        C.POINTER(C.c_int32)]
     L.bvhar_cuda_fit_record_names.argtypes = [vp, C.c_char_p, C.c_int64]

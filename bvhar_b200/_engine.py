@@ -259,11 +259,33 @@ def spillover(coef: np.ndarray, contem: np.ndarray, sv: np.ndarray, dim: int, nr
     if har_trans is not None:
         hb = np.asfortranarray(np.asarray(har_trans, dtype=np.float64)[: 3 * dim, : lag * dim])
         D.har_trans = hb.ctypes.data_as(c_dp); D.ldh = hb.shape[0]
-    connect = np.empty((dim, S * dim), order="F"); net_pw = np.empty((dim, S * dim), order="F")
-    to = np.empty(S * dim); frm = np.empty(S * dim); tot = np.empty(S)
+    So = S * int(n_time) if int(sv_kind) == 3 else S  # sv_kind 3: one spillover per time point, ordered [time][draw]
+    connect = np.empty((dim, So * dim), order="F"); net_pw = np.empty((dim, So * dim), order="F")
+    to = np.empty(So * dim); frm = np.empty(So * dim); tot = np.empty(So)
     check(load_library().bvhar_cuda_spillover(C.byref(D), connect.ctypes.data_as(c_dp), to.ctypes.data_as(c_dp), frm.ctypes.data_as(c_dp),
                                               tot.ctypes.data_as(c_dp), net_pw.ctypes.data_as(c_dp)))
     return {"connect": connect, "to": to, "from": frm, "tot": tot, "net": to - frm, "net_pairwise": net_pw}
+
+
+def dynamic_spillover(packed: PackedFit, step: int, var_lag: int, har_trans: Optional[np.ndarray] = None, sparse: bool = False):
+    """``DynamicLdltSpillover::returnSpillover()`` (spillover.h:272-443): every (window, chain) of ``packed``'s window table
+    is refitted and its spillover computed from the device-resident draws (``bvhar_cuda_dynamic_spillover``).
+    Returns ``to, from [window, chain, draw, variable]`` and ``tot [window, chain, draw]``."""
+    from ._abi import DynspillParams, load_library
+    P = DynspillParams()
+    P.abi_version = _abi.ABI_VERSION; P.step = int(step); P.var_lag = int(var_lag); P.sparse = int(bool(sparse))
+    hb = None
+    if har_trans is not None:
+        hb = np.asfortranarray(np.asarray(har_trans, dtype=np.float64)[: 3 * packed.dim, : var_lag * packed.dim])
+        P.har_trans = hb.ctypes.data_as(c_dp); P.ldh = hb.shape[0]
+    d = packed.desc
+    thin = max(1, int(d.thin))
+    S = (max(0, int(d.num_iter) - int(d.num_burn)) + thin - 1) // thin
+    W, Cn, k = packed.n_windows, packed.n_chains, packed.dim
+    to = np.empty((W, Cn, S, k)); frm = np.empty((W, Cn, S, k)); tot = np.empty((W, Cn, S))
+    check(load_library().bvhar_cuda_dynamic_spillover(C.byref(d), C.byref(P), to.ctypes.data_as(c_dp), frm.ctypes.data_as(c_dp),
+                                                      tot.ctypes.data_as(c_dp)))
+    return to, frm, tot
 
 
 def pack_forecast(units: Sequence[Dict[str, np.ndarray]], last_obs: Sequence[np.ndarray], step: int, var_lag: int,

@@ -1482,7 +1482,7 @@ int bvhar_cuda_spillover(const bvhar_spillover_desc* d, double* connect, double*
   if (k < 1 || p < 1 || d->n_draws < 0 || !d->coef || !d->sv || (q > 0 && !d->contem)) return fail(BVHAR_ERR_BAD_ARG, "bad spillover descriptor");
   if (step < 2) return fail(BVHAR_ERR_BAD_ARG, "'lag_max' must larger than 0");  // lag_max = step - 1 (spillover.h:170); structural.h:10-12
   if (d->har_trans ? (d->nrow != 3 * k || d->ldh < 3 * k) : (d->nrow != k * p)) return fail(BVHAR_ERR_BAD_ARG, "coefficient rows do not match the lag structure");
-  if (d->sv_kind < 0 || d->sv_kind > 2 || (d->sv_kind == 2 && d->n_time < 1)) return fail(BVHAR_ERR_BAD_ARG, "bad sv_kind / n_time");
+  if (d->sv_kind < 0 || d->sv_kind > 3 || (d->sv_kind >= 2 && d->n_time < 1)) return fail(BVHAR_ERR_BAD_ARG, "bad sv_kind / n_time");
   if (d->n_draws == 0) return 0;
   API_LOCK;
   int ndev = 0;
@@ -1490,7 +1490,47 @@ int bvhar_cuda_spillover(const bvhar_spillover_desc* d, double* connect, double*
   CU(cudaSetDevice(d->device));
   pool_setup(d->device);
   const int64_t S = d->n_draws;
-  const size_t svw = d->sv_kind == 2 ? (size_t)d->n_time * k : (size_t)k;
+  const size_t svw = d->sv_kind >= 2 ? (size_t)d->n_time * k : (size_t)k;
+  if (d->sv_kind == 3) {  // one spillover per time point: unit = time point, the same coefficient rows for every unit
+    DevBuf<double> dc, da, dsv, dh, scratch, oc, ot, of, otot, on;
+    if (d->ld_coef < (int64_t)d->nrow * k || d->ld_contem < q || d->ld_sv < (int64_t)svw) return fail(BVHAR_ERR_BAD_ARG, "leading dimensions too small");
+    const int64_t T = d->n_time, tb = std::max<int64_t>(1, std::min<int64_t>(T, (int64_t)((1ull << 30) / (sizeof(double) * S * (2 * (size_t)k * k + 3 * k)))));
+    CU(dc.alloc((size_t)S * d->ld_coef)); CU(da.alloc((size_t)S * std::max<int64_t>(1, d->ld_contem))); CU(dsv.alloc((size_t)S * d->ld_sv));
+    CU(cudaMemcpy(dc.p, d->coef, (size_t)S * d->ld_coef * sizeof(double), cudaMemcpyHostToDevice));
+    if (q > 0) CU(cudaMemcpy(da.p, d->contem, (size_t)S * d->ld_contem * sizeof(double), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(dsv.p, d->sv, (size_t)S * d->ld_sv * sizeof(double), cudaMemcpyHostToDevice));
+    CU(oc.alloc((size_t)tb * S * k * k)); CU(on.alloc((size_t)tb * S * k * k)); CU(ot.alloc((size_t)tb * S * k)); CU(of.alloc((size_t)tb * S * k));
+    CU(otot.alloc((size_t)tb * S));
+    if (d->har_trans) {
+      std::vector<double> h((size_t)p * k * 3 * k);
+      for (int r = 0; r < p * k; ++r)
+        for (int qq = 0; qq < 3 * k; ++qq) h[(size_t)r * 3 * k + qq] = d->har_trans[(size_t)r * d->ldh + qq];
+      CU(dh.upload(h));
+    }
+    const int n_cta = (int)std::min<int64_t>(tb * S, 592);
+    SpilloverArgs A{};
+    A.k = k; A.nrow = d->nrow; A.lag = p; A.step = step; A.sv_kind = 1; A.n_time = 1; A.ldh = 3 * k;
+    A.ld_coef = d->ld_coef; A.ld_contem = d->ld_contem; A.ld_sv = d->ld_sv;
+    A.per_unit = S; A.us_coef = 0; A.us_contem = 0; A.us_sv = k;
+    A.coef = dc.p; A.contem = da.p; A.har = dh.p;
+    A.slab = spillover_slab_doubles(k, p, step);
+    CU(scratch.alloc((size_t)n_cta * A.slab));
+    A.scratch = scratch.p; A.connect = oc.p; A.to = ot.p; A.from = of.p; A.tot = otot.p; A.net_pairwise = on.p;
+    for (int64_t t0 = 0; t0 < T; t0 += tb) {
+      const int64_t nt = std::min(tb, T - t0);
+      A.sv = dsv.p + (size_t)t0 * k;
+      A.n_draws = nt * S;
+      CU(launch_spillover(A, n_cta, 0));
+      CU(cudaDeviceSynchronize());
+      const size_t o = (size_t)t0 * S;
+      CU(cudaMemcpy(connect + o * k * k, oc.p, (size_t)nt * S * k * k * sizeof(double), cudaMemcpyDeviceToHost));
+      CU(cudaMemcpy(net_pairwise + o * k * k, on.p, (size_t)nt * S * k * k * sizeof(double), cudaMemcpyDeviceToHost));
+      CU(cudaMemcpy(to + o * k, ot.p, (size_t)nt * S * k * sizeof(double), cudaMemcpyDeviceToHost));
+      CU(cudaMemcpy(from + o * k, of.p, (size_t)nt * S * k * sizeof(double), cudaMemcpyDeviceToHost));
+      CU(cudaMemcpy(tot + o, otot.p, (size_t)nt * S * sizeof(double), cudaMemcpyDeviceToHost));
+    }
+    return 0;
+  }
   if (d->ld_coef < (int64_t)d->nrow * k || d->ld_contem < q || d->ld_sv < (int64_t)svw) return fail(BVHAR_ERR_BAD_ARG, "leading dimensions too small");
   DevBuf<double> dc, da, dsv, dh, scratch, oc, ot, of, otot, on;
   const int64_t batch = std::min<int64_t>(S, std::max<int64_t>(1, (int64_t)((1ull << 30) / (sizeof(double) * (d->ld_coef + d->ld_contem + d->ld_sv + 2 * (size_t)k * k + 3 * k)))));
@@ -1507,6 +1547,7 @@ int bvhar_cuda_spillover(const bvhar_spillover_desc* d, double* connect, double*
   SpilloverArgs A{};
   A.k = k; A.nrow = d->nrow; A.lag = p; A.step = step; A.sv_kind = d->sv_kind; A.n_time = d->n_time; A.ldh = 3 * k;
   A.ld_coef = d->ld_coef; A.ld_contem = d->ld_contem; A.ld_sv = d->ld_sv;
+  A.per_unit = batch; A.us_coef = 0; A.us_contem = 0; A.us_sv = 0;
   A.coef = dc.p; A.contem = da.p; A.sv = dsv.p; A.har = dh.p;
   A.slab = spillover_slab_doubles(k, p, step);
   CU(scratch.alloc((size_t)n_cta * A.slab));
@@ -1524,6 +1565,108 @@ int bvhar_cuda_spillover(const bvhar_spillover_desc* d, double* connect, double*
     CU(cudaMemcpy(to + (size_t)i0 * k, ot.p, (size_t)nb * k * sizeof(double), cudaMemcpyDeviceToHost));
     CU(cudaMemcpy(from + (size_t)i0 * k, of.p, (size_t)nb * k * sizeof(double), cudaMemcpyDeviceToHost));
     CU(cudaMemcpy(tot + (size_t)i0, otot.p, (size_t)nb * sizeof(double), cudaMemcpyDeviceToHost));
+  }
+  return 0;
+}
+
+// ---- rolling-window spillover with a refit per window (DynamicLdltSpillover::returnSpillover, spillover.h:272-443) ----
+static int dynspill_batch(const bvhar_fit_desc* fd, const bvhar_dynspill_params* fp, double* to, double* from, double* tot) {
+  bvhar_fit_desc d2 = *fd;
+  const bool sv = fd->cov_type == BVHAR_COV_SV;
+  d2.record_mask = BVHAR_REC_COEF | (sv ? BVHAR_REC_LVOL : 0u) | (fp->sparse ? BVHAR_REC_SPARSE : 0u);
+  bvhar_fit* fit = nullptr;
+  int rc = build(&d2, &fit);
+  if (rc) return rc;
+  std::unique_ptr<bvhar_fit> guard(fit);
+  rc = bvhar_cuda_fit_run(fit, nullptr, nullptr);
+  if (rc && rc != BVHAR_ERR_NUMERICAL) return rc;
+  API_LOCK;
+  const Dims& D = fit->D;
+  const int k = D.k, U = D.U, q = D.q, p = fp->var_lag;
+  const long long S = (fit->rec_filled + fit->thin - 1) / fit->thin, cap = fit->R.cap, th = fit->thin;
+  if (S < 1) return fail(BVHAR_ERR_BAD_ARG, "no draws recorded");
+  if (fp->har_trans ? (D.nrow != 3 * k) : (D.nrow != p * k)) return fail(BVHAR_ERR_BAD_ARG, "var_lag does not match the coefficient matrix");
+  const RecPtrs& R = fit->R;
+  DevBuf<double> dh, scratch, oc, ot, of, otot, on;
+  if (fp->har_trans) {
+    std::vector<double> h((size_t)p * k * 3 * k);
+    for (int r = 0; r < p * k; ++r)
+      for (int qq = 0; qq < 3 * k; ++qq) h[(size_t)r * 3 * k + qq] = fp->har_trans[(size_t)r * fp->ldh + qq];
+    CU(dh.upload(h));
+  }
+  const long long nd = (long long)U * S;
+  CU(oc.alloc((size_t)nd * k * k)); CU(on.alloc((size_t)nd * k * k)); CU(ot.alloc((size_t)nd * k)); CU(of.alloc((size_t)nd * k)); CU(otot.alloc((size_t)nd));
+  const int n_cta = (int)std::min<long long>(nd, 592);
+  SpilloverArgs A{};
+  A.k = k; A.nrow = D.nrow; A.lag = p; A.step = fp->step; A.ldh = 3 * k; A.n_draws = nd; A.per_unit = S;
+  A.coef = fp->sparse ? R.alpha_sparse : R.alpha; A.ld_coef = th * D.N; A.us_coef = cap * D.N;
+  A.contem = fp->sparse ? R.a_sparse : R.a; A.ld_contem = th * q; A.us_contem = cap * q;
+  if (sv) { A.sv = R.h; A.sv_kind = 2; A.n_time = D.nmax; A.ld_sv = th * (long long)D.nmax * k; A.us_sv = cap * (long long)D.nmax * k; }
+  else { A.sv = R.d; A.sv_kind = 0; A.n_time = 0; A.ld_sv = th * k; A.us_sv = cap * k; }
+  if (!A.coef || (q > 0 && !A.contem) || !A.sv) return fail(BVHAR_ERR_BAD_ARG, "records needed by the spillover were not kept");
+  A.har = dh.p;
+  A.slab = spillover_slab_doubles(k, p, fp->step);
+  CU(scratch.alloc((size_t)n_cta * A.slab));
+  A.scratch = scratch.p; A.connect = oc.p; A.to = ot.p; A.from = of.p; A.tot = otot.p; A.net_pairwise = on.p;
+  CU(cudaStreamSynchronize(fit->st));
+  CU(launch_spillover(A, n_cta, 0));
+  CU(cudaDeviceSynchronize());
+  CU(cudaMemcpy(to, ot.p, (size_t)nd * k * sizeof(double), cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(from, of.p, (size_t)nd * k * sizeof(double), cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(tot, otot.p, (size_t)nd * sizeof(double), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int bvhar_cuda_dynamic_spillover(const bvhar_fit_desc* fd, const bvhar_dynspill_params* fp, double* to, double* from, double* tot) {
+  if (!fd || !fp || !to || !from || !tot) return fail(BVHAR_ERR_BAD_ARG, "null argument");
+  if (fp->abi_version != BVHAR_CUDA_ABI_VERSION) return fail(BVHAR_ERR_BAD_ARG, "descriptor ABI version mismatch");
+  if (fp->step < 2) return fail(BVHAR_ERR_BAD_ARG, "'lag_max' must larger than 0");
+  if (fd->n_windows < 1 || fd->n_chains < 1 || !fd->win_row0 || !fd->win_nrow || !fd->seed_chain) return fail(BVHAR_ERR_BAD_ARG, "empty window table");
+  if (fp->har_trans && fp->ldh < 3 * fd->dim) return fail(BVHAR_ERR_BAD_ARG, "har_trans leading dimension too small");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(BVHAR_ERR_CUDA, "no CUDA device available: no CPU fallback");
+  CU(cudaSetDevice(fd->device));
+  const int W = fd->n_windows, C = fd->n_chains, k = fd->dim;
+  const int thin = fd->thin < 1 ? 1 : fd->thin;
+  const long long S = ((long long)std::max(0, fd->num_iter - fd->num_burn) + thin - 1) / thin;
+  size_t free_b = 0, total_b = 0;
+  CU(cudaMemGetInfo(&free_b, &total_b));
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, fd->device) == cudaSuccess) {
+    unsigned long long reserved = 0, used = 0;
+    if (cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved) == cudaSuccess &&
+        cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used) == cudaSuccess && reserved > used)
+      free_b += (size_t)(reserved - used);
+  }
+  size_t nmax = 1;
+  for (int w = 0; w < W; ++w) nmax = std::max(nmax, (size_t)fd->win_nrow[w]);
+  const size_t d_ = fd->dim_design;
+  const size_t shared_b = (size_t)fd->n_rows_total * (d_ * (d_ + 1) / 2 + 2 * d_ + 2 * k + 8) * sizeof(double);
+  size_t unit_b = outforecast_unit_bytes(fd, 1) + (size_t)S * (2 * (size_t)k * k + 3 * k) * sizeof(double);
+  if (fd->cov_type == BVHAR_COV_SV) unit_b += (size_t)std::max(1, fd->num_iter - fd->num_burn) * nmax * k * sizeof(double);
+  const size_t budget = free_b > shared_b ? (size_t)(0.85 * (double)(free_b - shared_b)) : 0;
+  long long batch = std::max<long long>(1, (long long)(budget / ((size_t)C * unit_b)));
+  if (const char* env = getenv("BVHAR_MAX_WINDOWS_PER_BATCH")) batch = std::max(1, atoi(env));
+  batch = std::min<long long>(batch, W);
+  for (int w0 = 0; w0 < W;) {
+    const int nw = (int)std::min<long long>(batch, W - w0);
+    bvhar_fit_desc sub = *fd;
+    sub.n_windows = nw;
+    sub.win_row0 = fd->win_row0 + w0;
+    sub.win_nrow = fd->win_nrow + w0;
+    sub.seed_chain = fd->seed_chain + (size_t)w0 * C;
+    sub.unit_id_base = fd->unit_id_base + w0 * C;
+    const size_t o = (size_t)w0 * C * S;
+    const int rc = dynspill_batch(&sub, fp, to + o * k, from + o * k, tot + o);
+    if (rc == BVHAR_ERR_CUDA && nw > 1 && g_err.find("out of memory") != std::string::npos) {
+      cudaGetLastError();
+      cudaDeviceSynchronize();
+      if (cudaDeviceGetDefaultMemPool(&pool, fd->device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
+      batch = (nw + 1) / 2;
+      continue;
+    }
+    if (rc) return rc;
+    w0 += nw;
   }
   return 0;
 }

@@ -59,6 +59,7 @@ cudaError_t launch_stab_norm(double* R, double* Rt, long long n_mat, int m, int 
 struct SpilloverArgs {
   int k, nrow, lag, step, sv_kind, n_time, ldh;
   long long n_draws, ld_coef, ld_contem, ld_sv;
+  long long per_unit, us_coef, us_contem, us_sv;  // draw i -> unit i / per_unit (stride us_*), row i % per_unit (stride ld_*)
   const double *coef, *contem, *sv, *har;  // har: (lag k) rows x ldh: har[r * ldh + q] = har_trans(q, r)
   double* scratch;
   size_t slab;

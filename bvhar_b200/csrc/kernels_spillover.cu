@@ -24,9 +24,12 @@ __global__ void __launch_bounds__(256) spillover_kernel(const SpilloverArgs A) {
   double* Av = mp + kk;                   // [p k][k] VAR coefficients (row block l = lag l + 1)
   double* W = Av + (size_t)p * kk;        // [step][k][k] VMA blocks
   for (long long i = blockIdx.x; i < A.n_draws; i += gridDim.x) {
-    const double* alpha = A.coef + i * A.ld_coef;
-    const double* a = A.contem + i * A.ld_contem;
-    const double* dv = A.sv + i * A.ld_sv;
+    // draw i = (unit, s): units are e.g. the (window, chain) pairs of device-resident records, or the time points of a
+    // dynamic SV spillover (the same coefficient rows, log-volatilities advancing by dim per unit)
+    const long long un = i / A.per_unit, sd = i - un * A.per_unit;
+    const double* alpha = A.coef + un * A.us_coef + sd * A.ld_coef;
+    const double* a = A.contem + un * A.us_contem + sd * A.ld_contem;
+    const double* dv = A.sv + un * A.us_sv + sd * A.ld_sv;
     __syncthreads();
     // D^(1/2): updateDiag (config.h:876-881 LDLT, 980-996 SV)
     for (int c = tid; c < k; c += nt) {

@@ -295,6 +295,42 @@ class _AutoregBayes:
         return {"connect": tab(out["connect"]), "net_pairwise": tab(out["net_pairwise"]), "tot": vec(out["tot"]),
                 "to": vec(out["to"]), "from": vec(out["from"]), "net": vec(out["net"])}
 
+    def dynamic_spillover(self, window: int, n_ahead: int = 10, level=.05, sparse=True):
+        """Dynamic spillover (the reference's ``dynamic_spillover()``, _bayes.py:643-666).  LDLT models: rolling windows of
+        ``window`` observations, every window refitted with ``chains_`` chains (``DynamicLdltSpillover``, spillover.h:272-443).
+        SV models: one spillover per time point from the stored draws and their log-volatilities (``DynamicSvSpillover``,
+        spillover.h:445-507).  Returns, per horizon, mean / se / lower / upper of tot, to, from and net."""
+        if not self.is_fitted_:
+            raise RuntimeError("call fit() first")
+        from ._engine import dynamic_spillover as _dyn, spillover as _spillover
+        k = self.n_features_in_
+        if self._is_sv:
+            sfx = "_sparse_record" if sparse else "_record"
+            if "h_record" not in self.param_:
+                raise ValueError("dynamic_spillover() of an SV fit needs the full 'h_record'")
+            coef = np.concatenate(list(self.param_["alpha" + sfx]), axis=0)
+            contem = np.concatenate(list(self.param_["a" + sfx]), axis=0) if k > 1 else np.zeros((coef.shape[0], 1))
+            h = np.concatenate(list(self.param_["h_record"]), axis=0)
+            n_time, S = h.shape[1] // k, coef.shape[0]
+            out = _spillover(coef, contem, h, k, coef.shape[1] // k, self.lag_, n_ahead, har_trans=self._har(), sv_kind=3, n_time=n_time,
+                             device=self._device)
+            to = out["to"].reshape(n_time, S, k); frm = out["from"].reshape(n_time, S, k); tot = out["tot"].reshape(n_time, S, 1)
+        else:
+            H = self.y_.shape[0] - window + 1
+            if H <= 0:
+                raise ValueError("Window size is too large")  # spillover.h:316-318
+            x_tot, y_tot = self._design_of(self.y_)
+            n_w = window - self.lag_
+            packed = self._pack(x_tot, y_tot, self._seeds(H, self.chains_), win_row0=list(range(H)), win_nrow=[n_w] * H, record_mask=0)
+            to, frm, tot = _dyn(packed, n_ahead, self.lag_, har_trans=self._har(), sparse=sparse)
+            to = to.reshape(H, -1, k); frm = frm.reshape(H, -1, k); tot = tot.reshape(H, -1, 1)
+
+        def dens(a):  # process_dens_list_spillover, _misc.py:195-209
+            r = {"mean": a.mean(axis=1), "se": a.std(axis=1), "lower": np.quantile(a, level / 2, axis=1), "upper": np.quantile(a, 1 - level / 2, axis=1)}
+            return {nm: (v[:, 0] if v.shape[1] == 1 else v) for nm, v in r.items()}
+
+        return {"tot": dens(tot), "to": dens(to), "from": dens(frm), "net": dens(to - frm)}
+
     def _outforecast(self, n_ahead: int, test, expanding: bool, level, stable, sparse, med, sv):
         """forecast_roll / forecast_expand: window 0 reuses the fit, windows >= 1 are refitted, every
         (window, chain) in one GPU batch (forecaster.h:575-807, 851-875, 920-956)."""

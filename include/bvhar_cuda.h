@@ -327,7 +327,9 @@ int bvhar_cuda_is_stable(int device, int64_t n_draws, int32_t dim, int32_t nrow,
  * _tot / _net :129-152) for a batch of draws.  Per draw i: coef + i * ld_coef holds alpha (equation-major, constants not
  * used), contem + i * ld_contem the q contemporaneous coefficients, sv + i * ld_sv the record the innovation scale D^(1/2)
  * comes from (updateDiag, config.h:876-881, 980-996): sv_kind 0 = d_record row (sqrt), 1 = log-volatilities at one time
- * point (exp(h / 2)), 2 = the whole h_record row, n_time x dim time-major (time average of exp(h / 2)).
+ * point (exp(h / 2)), 2 = the whole h_record row, n_time x dim time-major (time average of exp(h / 2)), 3 = the whole
+ * h_record row, one spillover PER TIME POINT (DynamicSvSpillover, spillover.h:445-507): the outputs then hold
+ * n_time * n_draws draws ordered [time][draw].
  * VHAR: nrow = 3 dim, lag = month, har_trans = HAR transformation without constant, 3 dim x (month dim) column-major. */
 typedef struct {
   int32_t abi_version;
@@ -351,6 +353,23 @@ typedef struct {
 /* connect, net_pairwise: dim x (n_draws * dim) column-major; to, from: n_draws * dim; tot: n_draws
  * (returnSpilloverDensity, spillover.h:72-81; "net" = to - from). */
 int bvhar_cuda_spillover(const bvhar_spillover_desc* desc, double* connect, double* to, double* from, double* tot, double* net_pairwise);
+
+/* Rolling-window spillover with a refit per window: replaces DynamicLdltSpillover::returnSpillover() (spillover.h:272-443;
+ * bound by src/triangular.cpp:649-709 dynamic_bvarldlt_spillover / dynamic_bvharldlt_spillover) for the window table of
+ * `fit` (window i = rows [i, i + window) of y, design built once on the whole series as for the rolling forecasts).  Every
+ * (window, chain) is refitted and its spillover computed from the device-resident draws; the window table is processed in
+ * batches sized to the free device memory.  Works for both covariance models (SV fits use the time average of exp(h / 2),
+ * which needs BVHAR_REC_LVOL records and is memory-hungry; LDLT is the reference's use).
+ * to, from: [window][chain][draw * dim + variable]; tot: [window][chain][draw]; net = to - from. */
+typedef struct {
+  int32_t abi_version;
+  int32_t step;    /* FEVD horizon */
+  int32_t var_lag; /* p, or month */
+  int32_t sparse;  /* use the SAVS draws */
+  const double* har_trans; /* VHAR: 3 dim x (month dim) column-major without constant, else NULL */
+  int64_t ldh;
+} bvhar_dynspill_params;
+int bvhar_cuda_dynamic_spillover(const bvhar_fit_desc* fit, const bvhar_dynspill_params* p, double* to, double* from, double* tot);
 
 /* ---- fp64 building blocks exported for stage-level parity tests and the roofline bench ---- */
 /* C[M x N] (row-major, ldc) = alpha * A^T B + beta * C with A stored K x M row-major (lda) and

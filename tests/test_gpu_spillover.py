@@ -78,3 +78,62 @@ def test_model_spillover_api():
         assert np.all(np.isfinite(sp["tot"]["mean"]))
     with pytest.raises(Exception):
         m.spillover(1)
+
+
+def test_time_sweep_equals_one_call_per_time_point():
+    """sv_kind = 3 (DynamicSvSpillover, spillover.h:445-507: one spillover per time point from one set of draws)."""
+    rng = np.random.default_rng(9)
+    dim, lag, step, S, n_time = 3, 2, 5, 4, 6
+    coef, contem = _inputs(rng, S, dim, dim * lag)
+    h = rng.normal(size=(S, n_time * dim))
+    sweep = spillover(coef, contem, h, dim, dim * lag, lag, step, sv_kind=3, n_time=n_time)
+    for t in range(n_time):
+        one = spillover(coef, contem, np.ascontiguousarray(h[:, t * dim:(t + 1) * dim]), dim, dim * lag, lag, step, sv_kind=1)
+        assert np.array_equal(sweep["tot"][t * S:(t + 1) * S], one["tot"])
+        assert np.array_equal(sweep["to"][t * S * dim:(t + 1) * S * dim], one["to"])
+        assert np.array_equal(sweep["connect"][:, t * S * dim:(t + 1) * S * dim], one["connect"])
+
+
+@pytest.mark.parametrize("batch", [None, 1])
+@pytest.mark.parametrize("vhar,sv_model", [(False, False), (True, False), (False, True)])
+def test_native_dynamic_spillover_matches_fit_plus_spillover(monkeypatch, vhar, sv_model, batch):
+    """bvhar_cuda_dynamic_spillover (refit + spillover of every (window, chain), draws kept on the device, windows in
+    memory-sized batches) equals fit_run -> records -> bvhar_cuda_spillover on the same window table, bit for bit."""
+    import problems as pr
+    from bvhar_b200._abi import PackedFit
+    from bvhar_b200._engine import CudaFit, dynamic_spillover
+    if batch:
+        monkeypatch.setenv("BVHAR_MAX_WINDOWS_PER_BATCH", str(batch))
+    wins = [(0, 40), (1, 40), (2, 40)]
+    kw, meta = pr.make_problem(prior="Horseshoe", sv=sv_model, dim=3, T=60, vhar=vhar, week=2, month=4, chains=2, iters=9, burn=3,
+                               thin=2, windows=wins)
+    if sv_model:
+        kw["lvol_from_init"] = True
+    lag = 4 if vhar else 2
+    har = build_vhar(3, 2, 4, False) if vhar else None
+    to, frm, tot = dynamic_spillover(PackedFit(**kw), 6, lag, har_trans=har)
+    assert to.shape == (3, 2, 3, 3) and tot.shape == (3, 2, 3)
+    g = CudaFit(PackedFit(**kw)); g.run()
+    for w in range(3):
+        for c in range(2):
+            rec = g.records(w, c)
+            if sv_model:
+                ref = spillover(rec["alpha_record"], rec["a_record"], rec["h_record"], 3, rec["alpha_record"].shape[1] // 3, lag, 6,
+                                har_trans=har, sv_kind=2, n_time=rec["h_record"].shape[1] // 3)
+            else:
+                ref = spillover(rec["alpha_record"], rec["a_record"], rec["d_record"], 3, rec["alpha_record"].shape[1] // 3, lag, 6, har_trans=har)
+            assert np.array_equal(to[w, c].reshape(-1), ref["to"]) and np.array_equal(frm[w, c].reshape(-1), ref["from"])
+            assert np.array_equal(tot[w, c], ref["tot"])
+
+
+def test_model_dynamic_spillover_api():
+    from bvhar_b200 import datasets
+    from bvhar_b200._spec import HorseshoeConfig, LdltConfig, SvConfig
+    from bvhar_b200.model import VarBayes
+    y = datasets.load_vix()[:60, :3]
+    m = VarBayes(y, 2, 2, 20, 8, 1, HorseshoeConfig(), LdltConfig(), seed=3).fit()
+    out = m.dynamic_spillover(55, 4, sparse=False)   # 6 rolling windows
+    assert out["tot"]["mean"].shape == (6,) and out["to"]["mean"].shape == (6, 3) and np.all(np.isfinite(out["net"]["upper"]))
+    s = VarBayes(y, 2, 2, 20, 8, 1, HorseshoeConfig(), SvConfig(), seed=3).fit()
+    out = s.dynamic_spillover(55, 4, sparse=False)   # SV: one spillover per time point of the design
+    assert out["tot"]["mean"].shape == (58,) and out["from"]["lower"].shape == (58, 3)
