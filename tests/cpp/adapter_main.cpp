@@ -3,7 +3,7 @@
 // File format (both ways): repeated { int32 name_len, name bytes, int64 rows, int64 cols, rows*cols doubles }.
 #include <cstdio>
 #include <cstring>
-#include <bvhar_b200/mcmc_run.hpp>
+#include <bvhar_b200/forecast_run.hpp>
 
 using namespace bvhar_b200;
 
@@ -34,6 +34,7 @@ static std::vector<int32_t> ints(const Matrix& m) { return std::vector<int32_t>(
 
 int main(int argc, char** argv) {
   if (argc != 3) { std::fprintf(stderr, "usage: adapter_main problem.bin records.bin\n"); return 2; }
+  // optional "forecast" entry of the problem file: lag | (week, month), step, stable -> McmcForecastRun on the fit's records
   try {
     auto all = read_all(argv[1]);
     const Matrix& meta = all.at("meta");  // chains, iter, burn, thin, prior_type, include_mean, sv, ggl
@@ -56,6 +57,23 @@ int main(int argc, char** argv) {
         std::fwrite(&kv.second.rows, sizeof(int64_t), 1, f); std::fwrite(&kv.second.cols, sizeof(int64_t), 1, f);
         std::fwrite(kv.second.data.data(), sizeof(double), kv.second.data.size(), f);
       }
+    if (all.count("forecast")) {  // VAR: (lag, 0, step, stable); VHAR: (week, month, step, stable)
+      const Matrix& fc = all.at("forecast");
+      const int a0 = (int)fc.data[0], a1 = (int)fc.data[1], step = (int)fc.data[2];
+      const bool stable = fc.data[3] != 0;
+      std::vector<Matrix> dens;
+      if (sv) dens = a1 > 0 ? SvForecast(chains, a0, a1, step, all.at("y"), false, 0.0, rec, seeds, mean, stable, 1).returnForecast()
+                            : SvForecast(chains, a0, step, all.at("y"), false, 0.0, rec, seeds, mean, stable, 1).returnForecast();
+      else dens = a1 > 0 ? LdltForecast(chains, a0, a1, step, all.at("y"), false, 0.0, rec, seeds, mean, stable, 1).returnForecast()
+                         : LdltForecast(chains, a0, step, all.at("y"), false, 0.0, rec, seeds, mean, stable, 1).returnForecast();
+      for (int c = 0; c < chains; ++c) {
+        const std::string name = "f" + std::to_string(c);
+        const int32_t nl = (int32_t)name.size();
+        std::fwrite(&nl, sizeof nl, 1, f); std::fwrite(name.data(), 1, nl, f);
+        std::fwrite(&dens[c].rows, sizeof(int64_t), 1, f); std::fwrite(&dens[c].cols, sizeof(int64_t), 1, f);
+        std::fwrite(dens[c].data.data(), sizeof(double), dens[c].data.size(), f);
+      }
+    }
     std::fclose(f);
     return 0;
   } catch (const std::exception& e) {
