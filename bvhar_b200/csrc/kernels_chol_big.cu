@@ -18,6 +18,8 @@
 //   coef_seq_big_kernel    the part that is sequential in j (one CTA per unit) with the factor read from
 //                          global / L2 by a blocked two-sided triangular solve that uses all warps, and the
 //                          k x d work vectors h_i = C_i - S_i v_i in a global scratch.
+#include <algorithm>
+
 #include "block_linalg.cuh"
 #include "engine.cuh"
 #include "gemm_tn.cuh"
@@ -48,6 +50,7 @@ __global__ void __launch_bounds__(CB_THREADS) coef_chol_cta_kernel(const Dims D,
   double* pan = sm;                       // [d][33] current panel, rows c0 .. d-1
   double* bt = pan + (size_t)d * 33;      // [32][CB_PB] rows of the diagonal block, 32 previous columns at a time
   double* red = bt + 32 * CB_PB;          // [64] scratch
+  double* pan2 = red + 64;                // [d - 32][33] the next panel, prefetched
   __shared__ int bad;
   if (tid == 0) bad = 0;
   double* Lg = Pfac + ((size_t)u * k + j) * D.ldS;  // in/out (SV: holds P_j on entry)
@@ -68,16 +71,22 @@ __global__ void __launch_bounds__(CB_THREADS) coef_chol_cta_kernel(const Dims D,
     const int m = d - c0;            // rows of the panel
     const int nc = min(32, m);       // columns of the panel
     __syncthreads();
-    // 1. load the panel (rows r = c0 + rr, columns c0 .. min(c0 + 31, r)), add the prior precision on the diagonal
-    for (int e = tid; e < m * 32; e += CB_THREADS) {
-      const int rr = e >> 5, cc = e & 31;
-      const int r = c0 + rr, c = c0 + cc;
-      double v = 0.0;
-      if (c <= r && cc < nc) {
-        v = scale * src[rowoff(r) + c];
-        if (c == r) v += pr[r];
+    // 1. the panel (rows r = c0 + rr, columns c0 .. min(c0 + 31, r)) with the prior precision on the diagonal: read from
+    //    global memory for the first panel, afterwards taken from the copy that warps 1..7 prefetched into pan2 while
+    //    warp 0 factored the previous diagonal block (step 3)
+    if (c0 == 0) {
+      for (int e = tid; e < m * 32; e += CB_THREADS) {
+        const int rr = e >> 5, cc = e & 31;
+        const int r = c0 + rr, c = c0 + cc;
+        double v = 0.0;
+        if (c <= r && cc < nc) {
+          v = scale * src[rowoff(r) + c];
+          if (c == r) v += pr[r];
+        }
+        pan[rr * 33 + cc] = v;
       }
-      pan[rr * 33 + cc] = v;
+    } else {
+      for (int e = tid; e < m * 33; e += CB_THREADS) pan[e] = pan2[e];
     }
     // 2. panel -= L[rows, 0:c0] * L[c0:c0+32, 0:c0]'   (DMMA; K = c0 in chunks of 32)
     if (c0 > 0) {
@@ -134,6 +143,19 @@ __global__ void __launch_bounds__(CB_THREADS) coef_chol_cta_kernel(const Dims D,
       for (int c = 0; c < 32; ++c)
         if (lane < nc && c <= lane) pan[lane * 33 + c] = dg[c];
       red[lane] = dinv;  // 1 / L_cc for the row solves
+    } else if (c0 + 32 < d) {  // the other warps: fetch the next panel's source values (not yet overwritten: step 5 only
+                               // stores columns < c0 + 32) so that their global-memory latency hides behind the factorisation
+      const int c1 = c0 + 32, m2 = d - c1, nc2 = min(32, m2);
+      for (int e = tid - 32; e < m2 * 32; e += CB_THREADS - 32) {
+        const int rr = e >> 5, cc = e & 31;
+        const int r = c1 + rr, c = c1 + cc;
+        double v = 0.0;
+        if (c <= r && cc < nc2) {
+          v = scale * src[rowoff(r) + c];
+          if (c == r) v += pr[r];
+        }
+        pan2[rr * 33 + cc] = v;
+      }
     }
     __syncthreads();
     // 4. rows below the block: x = a L_diag^-T, one thread per row (forward substitution against the 32 x 32 block)
@@ -196,7 +218,7 @@ __global__ void __launch_bounds__(32 * ID_WARPS) invert_diag_kernel(const Dims D
 
 }  // namespace
 
-size_t chol_cta_smem(const Dims& D) { return ((size_t)D.d * 33 + 32 * CB_PB + 64) * sizeof(double); }
+size_t chol_cta_smem(const Dims& D) { return ((size_t)D.d * 33 + 32 * CB_PB + 64 + (size_t)std::max(0, D.d - 32) * 33) * sizeof(double); }
 size_t seq_big_smem(const Dims& D) {
   return ((size_t)D.k * D.k + 3 * (size_t)D.d + 32 * 33 + (size_t)(CB_THREADS / 32) * D.d + D.k + 8) * sizeof(double);
 }
