@@ -28,6 +28,7 @@ __global__ void __launch_bounds__(128) BV_CAT(coef_chol_kernel_nc, BV_NC)(const 
   double* Pk = sm + (size_t)warp * ((Pp + 1) & ~1);
   double* Pg = Pfac + ((size_t)u * k + j) * D.ldS;
   __shared__ int bad[8];
+  __shared__ double colbuf[8][64];  // column broadcast buffers of the warp Cholesky (warp_linalg.cuh)
   if (lane == 0) bad[warp] = 0;
   if (SV) {
     for (int p = lane; p < Pp; p += 32) Pk[p] = Pg[p];
@@ -44,7 +45,7 @@ __global__ void __launch_bounds__(128) BV_CAT(coef_chol_kernel_nc, BV_NC)(const 
   const double* pr = P.prec + (size_t)u * k * d + (size_t)j * d;
   for (int a = lane; a < d; a += 32) Pk[a * (a + 1) / 2 + a] += pr[a];
   __syncwarp();
-  chol_blocked_warp<NC>(Pk, d, &bad[warp]);
+  chol_blocked_warp<NC>(Pk, d, &bad[warp], colbuf[warp]);
   for (int p = lane; p < Pp; p += 32) Pg[p] = Pk[p];
   __syncwarp();
   if (lane == 0 && bad[warp]) atomicOr(&P.flags[u], 1);

@@ -39,7 +39,7 @@ __device__ __forceinline__ size_t rowoff(int a) { return (size_t)a * (a + 1) / 2
 // ---- A2 (large d): one CTA per matrix --------------------------------------------------------------------
 // MTW = m-tiles (8 rows) per warp: ceil(ceil(d / 8) / 8).
 template <int MTW>
-__global__ void __launch_bounds__(CB_THREADS) coef_chol_cta_kernel(const Dims D, const DevPtrs P, double* Pfac) {
+__global__ void __launch_bounds__(CB_THREADS, (MTW <= 4 ? 2 : 1)) coef_chol_cta_kernel(const Dims D, const DevPtrs P, double* Pfac) {
   extern __shared__ __align__(16) double sm[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int fr = lane >> 2, fc = lane & 3;
@@ -52,6 +52,7 @@ __global__ void __launch_bounds__(CB_THREADS) coef_chol_cta_kernel(const Dims D,
   double* red = bt + 32 * CB_PB;          // [64] scratch
   double* pan2 = red + 64;                // [d - 32][33] the next panel, prefetched
   __shared__ int bad;
+  __shared__ double colbuf[64];  // column broadcast buffer of the diagonal-block factorisation (warp_linalg.cuh)
   if (tid == 0) bad = 0;
   double* Lg = Pfac + ((size_t)u * k + j) * D.ldS;  // in/out (SV: holds P_j on entry)
   const double* src = Lg;
@@ -138,7 +139,7 @@ __global__ void __launch_bounds__(CB_THREADS) coef_chol_cta_kernel(const Dims D,
       double dg[32];
 #pragma unroll
       for (int c = 0; c < 32; ++c) dg[c] = (lane < nc && c <= lane) ? pan[lane * 33 + c] : (c == lane ? 1.0 : 0.0);
-      const double dinv = chol32_registers(dg, &bad);
+      const double dinv = chol32_smem(dg, colbuf, &bad);
 #pragma unroll
       for (int c = 0; c < 32; ++c)
         if (lane < nc && c <= lane) pan[lane * 33 + c] = dg[c];

@@ -44,6 +44,34 @@ __device__ __forceinline__ double chol32_registers(double (&dg)[32], int* bad) {
   return dinv;
 }
 
+// The same factorisation with the column broadcasts through SHARED MEMORY instead of warp shuffles: after the pivot
+// step every lane drops its entry of column c into a 32-double buffer (double-buffered by the parity of c, one
+// __syncwarp per step) and the rank-1 update reads L[b][c], b > c, from there - one broadcast 8-byte load with an
+// immediate offset per value instead of two 32-bit shuffles.  The shuffle version issues 2 x 496 SHFL per block and is
+// bound by the shuffle pipe; this one is bound by the pivot chain.  colbuf: 64 doubles of shared memory owned by the
+// warp.  On exit dg holds L; returns 1 / L[lane][lane].
+__device__ __forceinline__ double chol32_smem(double (&dg)[32], double* colbuf, int* bad) {
+  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  double dinv = 1.0;
+#pragma unroll
+  for (int c = 0; c < 32; ++c) {
+    const double pc = __shfl_sync(FULL, dg[c], c);
+    const double inv = rsqrt(pc), piv = pc * inv;
+    if (lane == c && !(pc > 0.0)) *bad = 1;
+    const double lc = lane > c ? dg[c] * inv : 0.0;
+    if (lane == c) { dg[c] = piv; dinv = inv; }
+    else dg[c] = lc;
+    double* cb = colbuf + 32 * (c & 1);
+    cb[lane] = lc;
+    __syncwarp();
+#pragma unroll
+    for (int b = c + 1; b < 32; ++b) dg[b] = fma(-lc, cb[b], dg[b]);
+  }
+  __syncwarp();
+  return dinv;
+}
+
 // Column `c` (one thread per column) of the inverse of a 32 x 32 lower-triangular block whose rows are read through
 // `Lrow(r)` (pointer to L[r][0], the same address for every thread => shared-memory broadcasts) and whose reciprocal
 // diagonal is dinv[r]: forward substitution L x = e_c, 496 predicated FMAs per thread with two partial sums.  Rows >= nv
@@ -65,7 +93,7 @@ __device__ __forceinline__ void inv32_column(RowFn Lrow, const double* dinv, int
 }
 
 template <int NB>
-__device__ __forceinline__ void chol_blocked_warp(double* Pk, int d, int* bad) {
+__device__ __forceinline__ void chol_blocked_warp(double* Pk, int d, int* bad, double* colbuf /* 64 doubles of shared memory per warp */) {
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   double dg[32], wk[32];
@@ -77,25 +105,12 @@ __device__ __forceinline__ void chol_blocked_warp(double* Pk, int d, int* bad) {
     // ---- diagonal block: load, factor in registers, store
 #pragma unroll
     for (int c = 0; c < 32; ++c) dg[c] = (va && c <= lane) ? Pk[ra + c] : (c == lane ? 1.0 : 0.0);
-    double dinv = 1.0;
-#pragma unroll
-    for (int c = 0; c < 32; ++c) {
-      const double pc = __shfl_sync(FULL, dg[c], c);
-      const double inv = rsqrt(pc), piv = pc * inv;  // one MUFU + Newton instead of sqrt followed by a division
-      if (lane == c && !(pc > 0.0)) *bad = 1;
-      const double lc = lane > c ? dg[c] * inv : 0.0;
-      if (lane == c) { dg[c] = piv; dinv = inv; }
-      else dg[c] = lc;
-#pragma unroll
-      for (int b = c + 1; b < 32; ++b) {
-        const double lbc = __shfl_sync(FULL, lc, b);
-        dg[b] = fma(-lc, lbc, dg[b]);
-      }
-    }
+    const double dinv = chol32_smem(dg, colbuf, bad);
 #pragma unroll
     for (int c = 0; c < 32; ++c)
       if (va && c <= lane) Pk[ra + c] = dg[c];
-    // ---- panel: L[ib][jb] = A[ib][jb] L[jb][jb]^-T, one block row at a time
+    // ---- panel: L[ib][jb] = A[ib][jb] L[jb][jb]^-T, one block row at a time; column c of the diagonal block (lane b
+    // holds L[jb][jb](b, c) in dg[c]) is broadcast through colbuf
     for (int ib = jb + 1; ib < NB; ++ib) {
       if (32 * ib >= d) break;
       const int a2 = 32 * ib + lane;
@@ -107,12 +122,13 @@ __device__ __forceinline__ void chol_blocked_warp(double* Pk, int d, int* bad) {
       for (int c = 0; c < 32; ++c) {
         const double xc = wk[c] * __shfl_sync(FULL, dinv, c);
         wk[c] = xc;
+        double* cbf = colbuf + 32 * (c & 1);
+        cbf[lane] = dg[c];
+        __syncwarp();
 #pragma unroll
-        for (int b = c + 1; b < 32; ++b) {
-          const double lbc = __shfl_sync(FULL, dg[c], b);  // L[jb][jb](b, c): lane b, register c
-          wk[b] = fma(-xc, lbc, wk[b]);
-        }
+        for (int b = c + 1; b < 32; ++b) wk[b] = fma(-xc, cbf[b], wk[b]);
       }
+      __syncwarp();
 #pragma unroll
       for (int c = 0; c < 32; ++c)
         if (v2) Pk[r2 + c] = wk[c];
