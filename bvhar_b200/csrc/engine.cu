@@ -97,7 +97,7 @@ struct bvhar_fit {
   int num_iter = 0, num_burn = 0, thin = 1;
   uint32_t rec_mask = 0;
   cudaStream_t st = nullptr, s2 = nullptr, s3 = nullptr;
-  cudaEvent_t evf[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t evf[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   cudaGraphExec_t graph[2] = {nullptr, nullptr};
   double last_ms = 0.0;
@@ -114,7 +114,7 @@ struct bvhar_fit {
   DevBuf<long long> d_off, g1_b, g1_c, g2_b, g2_c, g3_a, g3_b, g3_y;
   DevBuf<uint32_t> seeds, iter;
   DevBuf<double> H, Z, Dinv, YLD, S, Cm, Acoef, alpha, cvec, prec, contem, L, chol_prec, sparse_coef, sparse_contem;
-  DevBuf<double> lvol_init, lvol_sig, diag, znorm, hN[4], hG[3], hq[4], hs, vscratch, pscratch, gscratch, Pfac, hscr, Qn;
+  DevBuf<double> Zn, lvol_init, lvol_sig, diag, znorm, hN[4], hG[3], hq[4], hs, vscratch, pscratch, gscratch, Pfac, hscr, Qn;
   bool coef_v2 = false, coef_big = false;
   std::map<std::string, std::unique_ptr<DevBuf<double>>> rec;
   std::vector<RecordSpec> rec_order;
@@ -225,6 +225,9 @@ struct bvhar_fit {
     }
     if (fork) CU(cudaEventRecord(evf[1], s2));
     if (D.sv) {
+      // the normals of the log-volatility draw depend only on the sweep counter: drawn on the side branch, consumed by sv_solve
+      LAUNCH("sv_normals", launch_sv_state(3, D, P, sp));
+      if (fork) CU(cudaEventRecord(evf[6], s2));
       // (updateSv, stage 3, was already done at the end of the previous sweep - see below - or at create time)
       if (fork) { CU(cudaEventRecord(evf[2], st)); CU(cudaStreamWaitEvent(s3, evf[2], 0)); }
       LAUNCH("gram_C_dmma", launch_dgemm_tn(g2, sg));
@@ -249,6 +252,7 @@ struct bvhar_fit {
     if (D.k > 1) LAUNCH("impact_draw", launch_impact(D, P, gscratch.p, st));
     if (D.sv) {
       LAUNCH("sv_mix", launch_sv_state(0, D, P, st));
+      if (fork) CU(cudaStreamWaitEvent(st, evf[6], 0));
       LAUNCH("sv_solve", launch_sv_state(1, D, P, st));
       // updateSv of the NEXT sweep (Dinv = exp(-h), YLD) depends only on h and L, both final here: it runs beside
       // sv_finish / the record copy instead of at the head of the next sweep's critical path
@@ -609,7 +613,7 @@ int build(const bvhar_fit_desc* d, bvhar_fit** out) {
       }
       CU(cudaDeviceSynchronize());
     }
-    CU(F->Dinv.alloc((size_t)tm_total)); CU(F->YLD.alloc((size_t)tm_total));
+    CU(F->Dinv.alloc((size_t)tm_total)); CU(F->YLD.alloc((size_t)tm_total)); CU(F->Zn.alloc((size_t)tm_total));
     CU(F->S.alloc((size_t)U * k * D.ldS)); CU(F->Cm.alloc((size_t)U * k * D.ldX));
     CU(F->XX.alloc((size_t)D.T * D.ldXX));
   } else {
@@ -627,7 +631,7 @@ int build(const bvhar_fit_desc* d, bvhar_fit** out) {
   P.grp_idx = F->grp_idx.p; P.grp_cnt = F->grp_cnt.p; P.own_flag = F->own_flag.p; P.prior_mean = F->prior_mean.p;
   P.sig_shp = F->sig_shp.p; P.sig_scl = F->sig_scl.p; P.sv_mean = F->sv_mean.p; P.sv_prec = F->sv_prec.p;
   P.ssvs_s1 = F->ssvs_s1.p; P.ssvs_s2 = F->ssvs_s2.p; P.seeds = F->seeds.p;
-  P.H = F->H.p; P.Z = F->Z.p; P.Dinv = F->Dinv.p; P.YLD = F->YLD.p;
+  P.H = F->H.p; P.Z = F->Z.p; P.Dinv = F->Dinv.p; P.YLD = F->YLD.p; P.Zn = F->Zn.p;
   P.S = F->S.p; P.Cm = F->Cm.p; P.Acoef = F->Acoef.p; P.alpha = F->alpha.p; P.cvec = F->cvec.p; P.prec = F->prec.p;
   P.contem = F->contem.p; P.L = F->L.p; P.chol_prec = F->chol_prec.p; P.sparse_coef = F->sparse_coef.p;
   P.sparse_contem = F->sparse_contem.p; P.lvol_init = F->lvol_init.p; P.lvol_sig = F->lvol_sig.p; P.diag = F->diag.p;
@@ -1212,7 +1216,7 @@ int bvhar_cuda_fit_run_stage(bvhar_fit* fit, int stage, int iter) {
     case 7: if (D.k > 1) CU(launch_impact(D, fit->P, fit->gscratch.p, fit->st)); break;
     case 8: break;  // chol_lower is rebuilt inside the contemporaneous draw
     case 9:
-      if (D.sv) { CU(launch_sv_state(0, D, fit->P, fit->st)); CU(launch_sv_state(1, D, fit->P, fit->st)); CU(launch_sv_state(2, D, fit->P, fit->st)); }
+      if (D.sv) { CU(launch_sv_state(3, D, fit->P, fit->st)); CU(launch_sv_state(0, D, fit->P, fit->st)); CU(launch_sv_state(1, D, fit->P, fit->st)); CU(launch_sv_state(2, D, fit->P, fit->st)); }
       else CU(launch_ldlt_state(D, fit->P, fit->st));
       break;
     default: return fail(BVHAR_ERR_BAD_ARG, "stage must be 1..9");

@@ -66,6 +66,7 @@ struct DevPtrs {
   double* Z;     // latent_innov
   double* Dinv;  // 1 / sqrt_sv^2 ; reused as the tridiagonal pivots in updateState
   double* YLD;   // (Y L')_ti / sqrt_sv_ti^2 ; reused as the tridiagonal right-hand side
+  double* Zn;    // standard normals of the log-volatility draw, pre-drawn per sweep (sv_normals_kernel)
   // ---- per unit ----
   double* S;      // [U*k][ldS]  S_i = X' D_i X packed
   double* Cm;     // [U*k][ldX]  C_i = X' D_i (Y L_i')

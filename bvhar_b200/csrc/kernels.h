@@ -39,7 +39,7 @@ int impact_gsize(const Dims& D);
 size_t impact_smem(const Dims& D);
 bool impact_supported(const Dims& D, size_t smem_limit);
 cudaError_t launch_impact(const Dims& D, const DevPtrs& P, double* gscratch, cudaStream_t st);
-cudaError_t launch_sv_state(int part, const Dims& D, const DevPtrs& P, cudaStream_t st);  // 0 mix, 1 solve, 2 finish
+cudaError_t launch_sv_state(int part, const Dims& D, const DevPtrs& P, cudaStream_t st);  // 0 mix, 1 solve, 2 finish, 3 normals of the solve
 cudaError_t launch_ldlt_state(const Dims& D, const DevPtrs& P, cudaStream_t st);
 cudaError_t launch_record(const Dims& D, const DevPtrs& P, const RecPtrs& R, cudaStream_t st);
 cudaError_t launch_bump(const DevPtrs& P, int bump_iter, int bump_rec, cudaStream_t st);

@@ -326,6 +326,27 @@ __global__ void __launch_bounds__(256, (KMAX <= 32 ? 2 : 1)) sv_mix_kernel(const
   }
 }
 
+// The n standard normals per series of the log-volatility draw (draw.h:479-481; Philox stage ST_SV_H_Z, pair p of
+// series i = normals 2p and 2p + 1), drawn by one thread per (series, pair) into the [t][m] buffer Zn.  They depend on
+// nothing but the sweep counter, so the kernel runs on a side branch of the graph beside the Gram contraction instead of
+// inside the one-thread-per-series recurrence of sv_solve_kernel, whose serial loop then only loads them.
+__global__ void __launch_bounds__(256) sv_normals_kernel(const Dims D, const DevPtrs P) {
+  const int w = blockIdx.z;
+  const int n = P.win_n[w];
+  const int pr = blockIdx.y, t = 2 * pr;
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n || m >= D.M) return;
+  const int c = m / D.k, i = m - c * D.k;
+  const int u = w * D.C + c;
+  const Philox rng(P.seeds[u], (uint32_t)(D.ubase + u), *P.iter);
+  const uint32_t nh = (uint32_t)((n + 1) / 2);
+  double z0, z1;
+  rng.normal_pair(ST_SV_H_Z, (uint32_t)i * nh + (uint32_t)pr, 0, z0, z1);
+  const long long at = P.win_off[w] + (long long)t * D.ldM + m;
+  P.Zn[at] = z0;
+  if (t + 1 < n) P.Zn[at + D.ldM] = z1;
+}
+
 // h_i ~ N(K^-1 b, K^-1) with the tridiagonal K = H'H / sig + diag(1/v_s) (draw.h:469-487): one thread per
 // series runs the bidiagonal Cholesky forward, then the combined mean + noise back substitution; accesses are
 // [t][m], coalesced.  The three recurrences are rewritten so that each step of the dependent chain is ONE FMA:
@@ -403,21 +424,23 @@ __global__ void __launch_bounds__(128) sv_solve_kernel(const Dims D, const DevPt
   }
   double next = 0.0, ssq = 0.0;
   const int nb = (n + SVS_B - 1) / SVS_B;
-  double wvn[SVS_B], yvn[SVS_B];
+  double wvn[SVS_B], yvn[SVS_B], zvn[SVS_B];  // z: the standard normals of this sweep, pre-drawn by sv_normals_kernel
 #pragma unroll
   for (int r = 0; r < SVS_B; ++r) {
     const int t = (nb - 1) * SVS_B + r;
     const long long at = off + (long long)t * D.ldM;
     wvn[r] = t < n ? P.Dinv[at] : 0.0;
     yvn[r] = t < n ? P.YLD[at] : 0.0;
+    zvn[r] = t < n ? P.Zn[at] : 0.0;
   }
   for (int blk = nb - 1; blk >= 0; --blk) {
     const int t0 = blk * SVS_B;  // SVS_B is even, so Philox pairs (t even, t odd) never straddle blocks
-    double wv[SVS_B], yv[SVS_B], zv[SVS_B] = {};
+    double wv[SVS_B], yv[SVS_B], zv[SVS_B];
 #pragma unroll
     for (int r = 0; r < SVS_B; ++r) {
       wv[r] = wvn[r];
       yv[r] = yvn[r];
+      zv[r] = zvn[r];
     }
     if (blk > 0) {
 #pragma unroll
@@ -425,11 +448,8 @@ __global__ void __launch_bounds__(128) sv_solve_kernel(const Dims D, const DevPt
         const long long at = off + (long long)(t0 - SVS_B + r) * D.ldM;
         wvn[r] = P.Dinv[at];
         yvn[r] = P.YLD[at];
+        zvn[r] = P.Zn[at];
       }
-    }
-#pragma unroll
-    for (int r = 0; r < SVS_B; r += 2) {
-      if (t0 + r < n) rng.normal_pair(ST_SV_H_Z, (uint32_t)i * nh + ((uint32_t)(t0 + r) >> 1), 0, zv[r], zv[r + 1]);
     }
     double gam[SVS_B], del[SVS_B];
 #pragma unroll
@@ -616,6 +636,10 @@ cudaError_t launch_sv_prep(const Dims& D, const DevPtrs& P, cudaStream_t st) {
   return cudaGetLastError();
 }
 cudaError_t launch_sv_state(int part, const Dims& D, const DevPtrs& P, cudaStream_t st) {
+  if (part == 3) {  // the pre-drawn normals of sv_solve
+    sv_normals_kernel<<<dim3((D.M + 255) / 256, (D.nmax + 1) / 2, D.W), 256, 0, st>>>(D, P);
+    return cudaGetLastError();
+  }
   if (part == 0) {
     const dim3 grid((D.M + 255) / 256, (D.nmax + SVP_TT - 1) / SVP_TT, D.W);
     const size_t smem = (size_t)SVP_TT * (256 + 2 * D.k) * sizeof(double);

@@ -21,30 +21,8 @@ __device__ __forceinline__ double wl_wsum(double v) {
 }
 #define wsum wl_wsum
 
-// Cholesky of one 32 x 32 block held in registers, one row per lane (dg[c] = A[lane][c], c <= lane; rows >= nv
-// must be passed as identity rows).  On exit dg holds L, and the return value is 1 / L[lane][lane].
-__device__ __forceinline__ double chol32_registers(double (&dg)[32], int* bad) {
-  const unsigned FULL = 0xffffffffu;
-  const int lane = threadIdx.x & 31;
-  double dinv = 1.0;
-#pragma unroll
-  for (int c = 0; c < 32; ++c) {
-    const double pc = __shfl_sync(FULL, dg[c], c);
-    const double inv = rsqrt(pc), piv = pc * inv;  // one MUFU + Newton instead of sqrt followed by a division
-    if (lane == c && !(pc > 0.0)) *bad = 1;
-    const double lc = lane > c ? dg[c] * inv : 0.0;
-    if (lane == c) { dg[c] = piv; dinv = inv; }
-    else dg[c] = lc;
-#pragma unroll
-    for (int b = c + 1; b < 32; ++b) {
-      const double lbc = __shfl_sync(FULL, lc, b);
-      dg[b] = fma(-lc, lbc, dg[b]);
-    }
-  }
-  return dinv;
-}
-
-// The same factorisation with the column broadcasts through SHARED MEMORY instead of warp shuffles: after the pivot
+// Cholesky of one 32 x 32 block held in registers, one row per lane (dg[c] = A[lane][c], c <= lane; rows >= nv must be
+// passed as identity rows), with the column broadcasts through SHARED MEMORY instead of warp shuffles: after the pivot
 // step every lane drops its entry of column c into a 32-double buffer (double-buffered by the parity of c, one
 // __syncwarp per step) and the rank-1 update reads L[b][c], b > c, from there - one broadcast 8-byte load with an
 // immediate offset per value instead of two 32-bit shuffles.  The shuffle version issues 2 x 496 SHFL per block and is
