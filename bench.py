@@ -226,17 +226,26 @@ def main():
     k, d, n = model.n_features_in_, model.design_.shape[1], model.response_.shape[0]
     packed = model._pack(model.design_, model.response_, model._seeds(1, args.chains), record_mask=0)
     fit = CudaFit(packed)
-    fit.step(W, False)  # warm-up: first sweep eager, then the captured graph
     sampler = ClockSampler(local)
+    sampler.start()     # nvidia-smi is looping before the timed region starts (its start-up can exceed a 150 ms region)
+    fit.step(W, False)  # warm-up: first sweep eager, then the captured graph
     barrier()
-    sampler.start()
+    n0 = len(sampler.rows)
     l0 = fit.launch_count()
     fit.step(K, False, sync=False)
     fit.sync()
     barrier()
     ms = fit.last_ms()
     launches = fit.launch_count() - l0
+    n1 = len(sampler.rows)
+    # the timed region may be shorter than the 100 ms sampling period: the same load (untimed sweeps) is kept up until at
+    # least three samples have been taken under it
+    t_lim = time.perf_counter() + 3.0
+    while len(sampler.rows) - n0 < 3 and time.perf_counter() < t_lim:
+        fit.step(K, False)
+    sampler.rows = sampler.rows[n0:]
     clocks = sampler.stop()
+    clocks["samples_in_timed_region"] = n1 - n0
     # same K steps again with a CUDA-event pair around every kernel (eager launches) for the roofline
     fit.set_profiling(True)
     fit.step(K, False)
