@@ -122,6 +122,8 @@ PROGRESS_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_int)
 
 
 def _f64(a, order="F") -> np.ndarray:
+    if type(a) is np.ndarray and a.dtype == np.float64 and a.flags.aligned and (a.flags.f_contiguous if order == "F" else a.flags.c_contiguous):
+        return a  # already in the layout the C-ABI reads (thousands of per-chain init vectors take this path)
     return np.require(np.asarray(a, dtype=np.float64), dtype=np.float64, requirements=["F" if order == "F" else "C", "A"])
 
 
@@ -130,7 +132,7 @@ def _i32(a) -> np.ndarray:
 
 
 def _dp(a: Optional[np.ndarray]):
-    return a.ctypes.data_as(c_dp) if a is not None else c_dp()
+    return C.cast(a.__array_interface__["data"][0], c_dp) if a is not None else c_dp()
 
 
 def _ip(a: Optional[np.ndarray]):
