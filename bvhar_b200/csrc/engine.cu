@@ -59,6 +59,19 @@ inline void pool_setup(int device) {
   }
   done[device] = true;
 }
+// Grow-only page-locked staging buffer for the chains' log-volatility inits (nullptr if it cannot be allocated).
+inline double* lvol_stage_buffer(size_t count) {
+  static double* buf = nullptr;
+  static size_t cap = 0;
+  if (count > cap) {
+    if (buf) cudaFreeHost(buf);
+    buf = nullptr; cap = 0;
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, count * sizeof(double), cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    buf = static_cast<double*>(p); cap = count;
+  }
+  return buf;
+}
 template <typename T>
 struct DevBuf {
   T* p = nullptr;
@@ -494,12 +507,14 @@ int build(const bvhar_fit_desc* d, bvhar_fit** out) {
   std::vector<double> hH, hli, hls, hdiag;
   // SV: the n x k `lvol` blocks of the chains are staged series-major ([chain][series][t], a plain memcpy per
   // chain) and transposed into the time-major layout on the device; replicated inits are k values per unit.
-  std::vector<double> hlv;     // [C][k][n0] when explicit lvol inits are given
+  std::vector<double> hlv;     // [C][k][n0] when explicit lvol inits are given (fallback storage)
+  double* hlv_stage = nullptr; // the same, page-locked
   bool lvol_explicit = false;
   if (D.sv) { hli.resize((size_t)U * k); hls.resize((size_t)U * k); }
   else hdiag.resize((size_t)U * k);
   std::vector<double> hhN[4], hhG[3], hhq[4], hhs((size_t)U * HS_SLOTS, 0.0);
-  for (auto& v : hhN) v.assign((size_t)U * N, 0.0);
+  // (the N-long prior vectors are materialised on the host only for the slots a prior actually initialises: a fresh
+  // 10 MB vector costs more in page faults than its upload; untouched slots are zero-filled on the device)
   for (auto& v : hhG) v.assign((size_t)U * G, 0.0);
   for (auto& v : hhq) v.assign((size_t)U * q, 0.0);
   for (int w = 0; w < D.W; ++w)
@@ -536,7 +551,11 @@ int build(const bvhar_fit_desc* d, bvhar_fit** out) {
         for (int i = 0; i < k; ++i) hdiag[(size_t)u * k + i] = in.init_diag[i];
       }
       double* s = &hhs[(size_t)u * HS_SLOTS];
-      auto cpN = [&](int slot, const double* src) { if (src) std::copy(src, src + N, hhN[slot].begin() + (size_t)u * N); };
+      auto cpN = [&](int slot, const double* src) {
+        if (!src) return;
+        if (hhN[slot].empty()) hhN[slot].assign((size_t)U * N, 0.0);
+        std::copy(src, src + N, hhN[slot].begin() + (size_t)u * N);
+      };
       auto cpG = [&](int slot, const double* src) { if (src) std::copy(src, src + G, hhG[slot].begin() + (size_t)u * G); };
       auto cpq = [&](int slot, const double* src) { if (src) std::copy(src, src + q, hhq[slot].begin() + (size_t)u * q); };
       auto need = [&](const void* p, const char* nm) { return p ? 0 : fail(BVHAR_ERR_BAD_ARG, std::string("param_init lacks ") + nm); };
@@ -585,15 +604,19 @@ int build(const bvhar_fit_desc* d, bvhar_fit** out) {
   lap("host init loops");
   if (D.sv && lvol_explicit) {  // gather the chains' n x k lvol blocks into one staging buffer, a few host threads
     const size_t blk = (size_t)k * F->win_n[0];
-    hlv.resize((size_t)D.C * blk);
+    // staged in a page-locked buffer that lives as long as the process (grow-only, engine construction is serialised):
+    // a fresh pageable vector of this size costs more in page faults than the copy itself (66 ms for 164 MB at C3)
+    hlv_stage = lvol_stage_buffer((size_t)D.C * blk);
+    if (!hlv_stage) { hlv.resize((size_t)D.C * blk); hlv_stage = hlv.data(); }
     const int nthr = std::max(1, std::min(8, D.C / 32));
     std::vector<std::thread> pool;
     for (int th = 0; th < nthr; ++th)
       pool.emplace_back([&, th] {
-        for (int c = th; c < D.C; c += nthr) std::memcpy(hlv.data() + (size_t)c * blk, d->init[c].lvol, sizeof(double) * blk);
+        for (int c = th; c < D.C; c += nthr) std::memcpy(hlv_stage + (size_t)c * blk, d->init[c].lvol, sizeof(double) * blk);
       });
     for (auto& t : pool) t.join();
   }
+  lap("lvol gather");
   CU(F->Acoef.upload(hA)); CU(F->alpha.upload(halpha)); CU(F->cvec.upload(hc)); CU(F->prec.upload(hprec));
   CU(F->contem.upload(hcontem)); CU(F->L.upload(hL)); CU(F->chol_prec.upload(hcp));
   CU(F->sparse_coef.alloc((size_t)U * dd * k)); CU(F->sparse_contem.alloc((size_t)U * q)); CU(F->znorm.alloc((size_t)2 * U * k));  // [U][k] column norms of Z, then [U][k] per-series sums of squared lvol increments
@@ -603,7 +626,11 @@ int build(const bvhar_fit_desc* d, bvhar_fit** out) {
     {
       DevBuf<double> stage;
       const int n0 = F->win_n[0];
-      if (lvol_explicit) CU(stage.upload(hlv));
+      if (lvol_explicit) {
+        const size_t cnt = (size_t)D.C * k * n0;
+        CU(stage.alloc(cnt));
+        CU(cudaMemcpyAsync(stage.p, hlv_stage, cnt * sizeof(double), cudaMemcpyHostToDevice, 0));  // completes before the sync below
+      }
       for (int w = 0; w < D.W; ++w) {
         if (lvol_explicit) {  // every window starts from the chains' lvol blocks (forecaster.h:867-872)
           CU(launch_scatter_lvol(stage.p, F->H.p + F->win_off[w], F->win_n[w], D.M, D.ldM, n0, 0));
@@ -613,13 +640,18 @@ int build(const bvhar_fit_desc* d, bvhar_fit** out) {
       }
       CU(cudaDeviceSynchronize());
     }
+    lap("coef uploads + lvol upload / scatter");
     CU(F->Dinv.alloc((size_t)tm_total)); CU(F->YLD.alloc((size_t)tm_total)); CU(F->Zn.alloc((size_t)tm_total));
     CU(F->S.alloc((size_t)U * k * D.ldS)); CU(F->Cm.alloc((size_t)U * k * D.ldX));
     CU(F->XX.alloc((size_t)D.T * D.ldXX));
   } else {
     CU(F->diag.upload(hdiag));
   }
-  for (int i = 0; i < 4; ++i) CU(F->hN[i].upload(hhN[i]));
+  lap("big allocs");
+  for (int i = 0; i < 4; ++i) {
+    if (hhN[i].empty()) CU(F->hN[i].alloc((size_t)U * N));
+    else CU(F->hN[i].upload(hhN[i]));
+  }
   for (int i = 0; i < 3; ++i) CU(F->hG[i].upload(hhG[i]));
   for (int i = 0; i < 4; ++i) CU(F->hq[i].upload(hhq[i]));
   CU(F->hs.upload(hhs));
