@@ -35,6 +35,8 @@ class CudaFit:
         if getattr(self, "_h", None) is not None and self._h.value:
             self.L.bvhar_cuda_fit_destroy(self._h)
             self._h = C.c_void_p()
+        self._sink_keep = []  # the engine no longer holds the sink pointers
+        self._sinks = {}
 
     def __del__(self):
         try:
@@ -141,10 +143,17 @@ class CudaFit:
         check(self.L.bvhar_cuda_fit_record_dims(self._h, name.encode(), C.byref(r), C.byref(c)))
         U = self.packed.n_windows * self.packed.n_chains
         shape = (U, r.value, c.value)
-        sink = (getattr(self, "_sinks", None) or {}).pop(name, None)  # handed out once: the caller owns it from here on
+        sinks = getattr(self, "_sinks", None) or {}
+        sink = sinks.get(name)
         if sink is not None and sink.shape == shape:  # streamed during run(): only waits for the tail of the copy stream
             check(self.L.bvhar_cuda_fit_record_all(self._h, name.encode(), sink.ctypes.data_as(c_dp), U, r.value, c.value))
+            # handed out once; the engine keeps the pointer bound until it is destroyed, so the block must not go back
+            # to the pool before close(): a reference stays in _sink_keep
+            self._sink_keep = getattr(self, "_sink_keep", [])
+            self._sink_keep.append(sinks.pop(name))
             return sink
+        # (a sink whose shape does not match - a run cut short by the progress callback keeps fewer rows - stays bound
+        # and alive: a resumed run() still streams into it; the rows kept so far are fetched from the device below)
         if pinned and U * r.value * c.value * 8 >= (8 << 20):
             from . import _hostpool
             out = _hostpool.empty(shape)

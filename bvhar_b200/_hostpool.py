@@ -72,7 +72,9 @@ class _Keep(np.ndarray):
         return obj
 
     def __array_finalize__(self, obj):
-        self._blk = getattr(obj, "_blk", None)
+        blk = getattr(obj, "_blk", None)
+        # only arrays that really live in the block keep it pinned (arr * 2 owns fresh pageable memory)
+        self._blk = blk if blk is not None and np.may_share_memory(self, obj) else None
 
 
 def trim():

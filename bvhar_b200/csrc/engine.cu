@@ -111,7 +111,7 @@ struct bvhar_fit {
   uint32_t rec_mask = 0;
   cudaStream_t st = nullptr, s2 = nullptr, s3 = nullptr;
   cudaEvent_t evf[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, evs0 = nullptr;
   cudaGraphExec_t graph[2] = {nullptr, nullptr};
   double last_ms = 0.0;
   int64_t launches = 0;
@@ -175,6 +175,7 @@ struct bvhar_fit {
     if (evc) cudaEventDestroy(evc);
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
+    if (evs0) cudaEventDestroy(evs0);
     if (st) cudaStreamDestroy(st);
   }
 
@@ -675,6 +676,7 @@ int build(const bvhar_fit_desc* d, bvhar_fit** out) {
 
   CU(cudaStreamCreateWithFlags(&F->st, cudaStreamNonBlocking));
   CU(cudaEventCreate(&F->ev0)); CU(cudaEventCreate(&F->ev1));
+  CU(cudaEventCreateWithFlags(&F->evs0, cudaEventDisableTiming));
   if (getenv("BVHAR_NO_FORK") == nullptr) {
     CU(cudaStreamCreateWithFlags(&F->s2, cudaStreamNonBlocking)); CU(cudaStreamCreateWithFlags(&F->s3, cudaStreamNonBlocking));
     for (auto& e : F->evf) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -723,6 +725,14 @@ int build(const bvhar_fit_desc* d, bvhar_fit** out) {
   CU(F->gscratch.alloc((size_t)U * impact_gsize(D)));
   if (!impact_supported(D, F->smem_limit))
     return fail(BVHAR_ERR_UNSUPPORTED, "dim too large for the shared-memory contemporaneous draw of this build");
+  // every allocation, memset and upload above was issued on stream 0, and F->st is a non-blocking stream: order
+  // stream 0 before the first kernel on F->st (a staged pageable upload or a pending memset may not have landed yet)
+  auto order_after_stream0 = [&]() -> int {
+    CU(cudaEventRecord(F->evs0, 0));
+    CU(cudaStreamWaitEvent(F->st, F->evs0, 0));
+    return 0;
+  };
+  if (int rc = order_after_stream0()) return rc;
   if (D.sv) { CU(launch_build_xx(D, P, F->XX.p, F->st)); CU(launch_sv_prep(D, P, F->st)); }  // updateSv for the first sweep
   else {
     // X'X (packed) and X'Y per window through the same contraction kernel
@@ -733,6 +743,7 @@ int build(const bvhar_fit_desc* d, bvhar_fit** out) {
     for (int w = 0; w < D.W; ++w) { bo[w] = (long long)F->win_row0[w] * D.ldX; co[w] = (long long)w * dd * dd; yo[w] = (long long)F->win_row0[w] * k; cy[w] = (long long)w * dd * k; }
     DevBuf<long long> dbo, dco, dyo, dcy;
     CU(dbo.upload(bo)); CU(dco.upload(co)); CU(dyo.upload(yo)); CU(dcy.upload(cy));
+    if (int rc = order_after_stream0()) return rc;  // XtX / XtY / full / the offset tables live on stream 0
     GemmArgs g{};
     g.A = P.X; g.B = P.X; g.C = full.p; g.M = dd; g.N = dd; g.lda = D.ldX; g.ldb = D.ldX; g.ldc = dd; g.groups = D.W;
     g.a_off = dbo.p; g.b_off = dbo.p; g.c_off = dco.p; g.Kg = F->gKg.p; g.epi = EPI_STORE; g.aligned16 = 1;
@@ -1046,9 +1057,11 @@ int bvhar_cuda_fit_run(bvhar_fit* fit, bvhar_progress_fn progress, void* ctx) {
     if (rec && (rc = fit->stream_out())) return rc;
     done += chunk;
     if (progress) {
+      // a non-PD flag is sticky and per unit: it is reported once, by the final sync, exactly as on the path without a
+      // callback (the reference would carry NaNs in that chain and keep sampling) - only CUDA errors and the callback abort
       rc = fit->sync();
       ms_total += (float)fit->last_ms;
-      if (rc) return rc;
+      if (rc && rc != BVHAR_ERR_NUMERICAL) return rc;
       if (progress(ctx, done, total)) return fail(BVHAR_ERR_INTERRUPTED, "interrupted by the progress callback");
     }
   }

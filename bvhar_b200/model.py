@@ -163,11 +163,13 @@ class _AutoregBayes:
         if devices is not None and len(devices) > 1:
             names, recs = self._fit_sharded(list(devices))
             k = self.n_features_in_
-            self.coef_ = recs["alpha_record"].mean(axis=(0, 1)).reshape(k, -1).T
+            # NaN-skipping means, as the device reduction of the single-engine path (record_mean): a chain with a
+            # numerical flag carries NaNs and must not poison the posterior mean on one path only
+            self.coef_ = np.nanmean(recs["alpha_record"], axis=(0, 1)).reshape(k, -1).T
             if "alpha_sparse_record" in recs:
                 self.sparse_coef_ = np.nanmean(recs["alpha_sparse_record"], axis=(0, 1)).reshape(k, -1).T
             if self.fit_intercept:
-                self.intercept_ = recs["c_record"].mean(axis=(0, 1)).reshape(k)
+                self.intercept_ = np.nanmean(recs["c_record"], axis=(0, 1)).reshape(k)
                 self.coef_ = np.concatenate([self.coef_, self.intercept_[None, :]], axis=0)
                 if self.sparse_coef_ is not None:
                     self.sparse_coef_ = np.concatenate([self.sparse_coef_, np.nanmean(recs["c_sparse_record"], axis=(0, 1))[None, :]], axis=0)

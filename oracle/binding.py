@@ -64,6 +64,8 @@ def lib():
         L.oracle_philox4x32_10.restype = None
         L.oracle_sample.argtypes = [C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_double, C.c_double, C.c_double, C.c_int, c_dp]
         L.oracle_sample.restype = None
+        L.oracle_draw_at.argtypes = [C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_double, C.c_double, C.c_double]
+        L.oracle_draw_at.restype = C.c_double
         L.oracle_minnesota_moments.argtypes = [C.c_int, C.c_int, c_dp, C.c_double, C.c_double, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp]
         L.oracle_minnesota_moments.restype = None
         L.oracle_max_threads.restype = C.c_int

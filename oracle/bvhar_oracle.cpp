@@ -1478,6 +1478,28 @@ void oracle_sample(int kind, int rng_mode, uint32_t seed, uint32_t iter, double 
   }
 }
 
+// One variate of the addressed Philox stream (DESIGN.md "Random streams"): sampler `kind` at (seed, unit | iter, stage,
+// idx).  kind: 0 normal element idx of a vector site, 1 uniform element idx of a vector site, 2 gamma(p0 shape, p1 scale),
+// 3 beta(p0, p1), 4 invgauss(p0 mean, p1 shape), 5 gig(p0, p1, p2), 6 scalar-site uniform (Bernoulli / categorical
+// sites compare it themselves).  Lets an independent restatement of the sweep (tests/numpy_mirror.py) be fed the very
+// same random variates as the oracle, so that only the algebra is under test.
+double oracle_draw_at(int kind, uint32_t seed, uint32_t unit, uint32_t iter, uint32_t stage, uint32_t idx, double p0, double p1, double p2) {
+  Rng rng;
+  rng.seed(seed, unit, true);
+  rng.iter = iter;
+  double out = 0.0;
+  switch (kind) {
+    case 0: rng.normal_vec(stage, idx, 1, &out); return out;
+    case 1: rng.uniform_vec(stage, idx, 1, &out); return out;
+    case 2: return rng.gamma(stage, idx, p0, p1);
+    case 3: return rng.beta(stage, idx, p0, p1);
+    case 4: return rng.invgauss(stage, idx, p0, p1);
+    case 5: return rng.gig(stage, idx, p0, p1, p2);
+    case 6: return rng.uniform(stage, idx, 0);
+  }
+  return std::numeric_limits<double>::quiet_NaN();
+}
+
 // Minnesota prior moments: build_ydummy / build_xdummy design.h:60-98 and cfg.h:144-151,
 // prior_alpha_prec = diag(kron(diag(1/sigma), Xd'Xd)) tri.h:438-439.  `lag` = p (3 for VHAR).
 void oracle_minnesota_moments(int k, int lag, const double* sigma, double lambda, double eps, const double* daily,
