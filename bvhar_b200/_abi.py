@@ -16,7 +16,7 @@ from typing import Any, Dict, List, Optional, Sequence
 
 import numpy as np
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 COV_LDLT, COV_SV = 0, 1
 PRIOR_MINNESOTA, PRIOR_SSVS, PRIOR_HORSESHOE, PRIOR_HIERMINN, PRIOR_NG, PRIOR_DL, PRIOR_GDP = 1, 2, 3, 4, 5, 6, 7
@@ -90,7 +90,7 @@ class ForecastDesc(C.Structure):
         ("var_lag", C.c_int32), ("is_vhar", C.c_int32), ("sv", C.c_int32), ("get_lpl", C.c_int32),
         ("n_draws", C.c_int32), ("unit_id_base", C.c_int32),
         ("har_trans", c_dp), ("coef_record", c_dp), ("contem_record", c_dp), ("diag_record", c_dp),
-        ("sigh_record", c_dp), ("last_obs", c_dp), ("valid_vec", c_dp), ("seed", c_up),
+        ("sigh_record", c_dp), ("last_obs", c_dp), ("valid_vec", c_dp), ("seed", c_up), ("level", C.c_double),
     ]
 
 
@@ -115,6 +115,7 @@ class OutforecastParams(C.Structure):
         ("abi_version", C.c_int32), ("step", C.c_int32), ("var_lag", C.c_int32), ("is_vhar", C.c_int32),
         ("sv", C.c_int32), ("get_lpl", C.c_int32), ("sparse", C.c_int32), ("reserved", C.c_int32),
         ("har_trans", c_dp), ("y_full", c_dp), ("y_rows", C.c_int64), ("valid_vec", c_dp), ("seed_forecast", c_up),
+        ("level", C.c_double),
     ]
 
 
@@ -312,7 +313,7 @@ class PackedFit:
         self.desc = D
         self.n_windows, self.n_chains, self.dim, self.dim_design = n_win, num_chains, dim, d
         self.n_alpha, self.q, self.sv = n_alpha, q, sv
-        self.win_nrow = wn
+        self.win_nrow, self.win_row0, self.include_mean = wn, w0, bool(include_mean)
 
 
 _LIB = None

@@ -300,10 +300,12 @@ def dynamic_spillover(packed: PackedFit, step: int, var_lag: int, har_trans: Opt
 def pack_forecast(units: Sequence[Dict[str, np.ndarray]], last_obs: Sequence[np.ndarray], step: int, var_lag: int,
                   include_mean: bool, sv_model: bool, seeds, har_trans: Optional[np.ndarray] = None, sv: bool = True,
                   valid_vec: Optional[np.ndarray] = None, stable: bool = False, sparse: bool = False,
-                  coef_name: str = "alpha", device: int = 0, unit_id_base: int = 0):
+                  coef_name: str = "alpha", device: int = 0, unit_id_base: int = 0, level: float = 0.0):
     """Build the ``bvhar_forecast_desc`` of a batch of forecasters from their record dicts
     (``initialize_record`` config.h:1316-1363 + the forecaster ctors forecaster.h:27-52, 229-240).
     Returns (descriptor, keep-alive list)."""
+    if sparse and level > 0:
+        raise ValueError("If 'level > 0', 'spare' should be false.")  # forecaster.h:445-447 (sic)
     dim = last_obs[0].shape[1]
     sfx = "_sparse_record" if sparse else "_record"
     coefs, contems, diags, sighs = [], [], [], []
@@ -336,7 +338,7 @@ def pack_forecast(units: Sequence[Dict[str, np.ndarray]], last_obs: Sequence[np.
     D.abi_version = _abi.ABI_VERSION; D.device = device; D.n_units = U; D.dim = dim; D.nrow_coef = nrow
     D.include_mean = int(include_mean); D.cov_type = _abi.COV_SV if sv_model else _abi.COV_LDLT; D.step = int(step)
     D.var_lag = int(var_lag); D.is_vhar = int(har_trans is not None); D.sv = int(sv); D.get_lpl = int(valid_vec is not None)
-    D.n_draws = S; D.unit_id_base = int(unit_id_base)
+    D.n_draws = S; D.unit_id_base = int(unit_id_base); D.level = float(level)
     keep = [coef_b, contem_b, diag_b, last_b]
     D.coef_record = coef_b.ctypes.data_as(c_dp); D.contem_record = contem_b.ctypes.data_as(c_dp)
     D.diag_record = diag_b.ctypes.data_as(c_dp); D.last_obs = last_b.ctypes.data_as(c_dp)
@@ -354,12 +356,13 @@ def pack_forecast(units: Sequence[Dict[str, np.ndarray]], last_obs: Sequence[np.
 def forecast_density(units: Sequence[Dict[str, np.ndarray]], last_obs: Sequence[np.ndarray], step: int, var_lag: int,
                      include_mean: bool, sv_model: bool, seeds, har_trans: Optional[np.ndarray] = None, sv: bool = True,
                      valid_vec: Optional[np.ndarray] = None, stable: bool = False, sparse: bool = False,
-                     coef_name: str = "alpha", device: int = 0, unit_id_base: int = 0):
+                     coef_name: str = "alpha", device: int = 0, unit_id_base: int = 0, level: float = 0.0):
     """Density forecasts of independent units on the GPU (``McmcForecaster::forecastDensity``,
-    forecaster.h:55-85).  Returns (list of step x (S*k) matrices, step-wise ALPL per unit or None)."""
+    forecaster.h:55-85).  ``level > 0``: the Select forecasters (forecaster.h:348-416), coefficients masked by each unit's
+    credible-interval activity graph.  Returns (list of step x (S*k) matrices, step-wise ALPL per unit or None)."""
     L = load_library()
     D, keep = pack_forecast(units, last_obs, step, var_lag, include_mean, sv_model, seeds, har_trans, sv, valid_vec, stable,
-                            sparse, coef_name, device, unit_id_base)
+                            sparse, coef_name, device, unit_id_base, level)
     U, S, dim = D.n_units, D.n_draws, D.dim
     out = np.empty(U * step * S * dim)
     lpl = np.zeros(U * step) if valid_vec is not None else None
@@ -369,14 +372,14 @@ def forecast_density(units: Sequence[Dict[str, np.ndarray]], last_obs: Sequence[
 
 
 def outforecast(packed: PackedFit, y_full: np.ndarray, step: int, var_lag: int, seed_forecast, har_trans=None, sv: bool = True,
-                valid_vec=None, sparse: bool = False):
+                valid_vec=None, sparse: bool = False, level: float = 0.0):
     """``McmcOutforecastRun::returnForecast`` for the windows of ``packed`` in ONE native call
     (``bvhar_cuda_outforecast_run``): refit every (window, chain), forecast from the device-resident draws.
     Returns (forecast[window, chain, draw, variable] of the last step, lpl[window, chain] or None)."""
     L = load_library()
     P = _abi.OutforecastParams()
     P.abi_version = _abi.ABI_VERSION; P.step = int(step); P.var_lag = int(var_lag); P.is_vhar = int(har_trans is not None)
-    P.sv = int(sv); P.get_lpl = int(valid_vec is not None); P.sparse = int(sparse)
+    P.sv = int(sv); P.get_lpl = int(valid_vec is not None); P.sparse = int(sparse); P.level = float(level)
     yf = np.asfortranarray(y_full, dtype=np.float64)
     P.y_full = yf.ctypes.data_as(c_dp); P.y_rows = yf.shape[0]
     keep = [yf]

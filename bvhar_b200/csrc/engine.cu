@@ -1275,6 +1275,24 @@ void bvhar_cuda_fit_destroy(bvhar_fit* fit) {
   delete fit;
 }
 
+// Order statistics behind RegRecords::computeActivity (config.h:747-758): boost::accumulators::tail_quantile evaluates
+// n = ceil(count * prob) for the left tail and n = ceil(count * (1. - prob)) for the right tail, in double precision, with
+// prob = level / 2 and 1 - level / 2 (so the two counts can differ by one, e.g. count = 1000, level = .05: 25 and 26).
+static void activity_order_stats(int S, double level, int* n_lo, int* n_hi) {
+  const double p_lo = level / 2, p_hi = 1 - level / 2;
+  *n_lo = (int)std::ceil((double)S * p_lo);
+  *n_hi = (int)std::ceil((double)S * (1. - p_hi));
+}
+static int activity_graph(const ForecastArgs& A, double level, DevBuf<double>& act, DevBuf<double>& scratch, cudaStream_t st) {
+  int n_lo = 0, n_hi = 0;
+  activity_order_stats(A.S, level, &n_lo, &n_hi);
+  const int N = A.nrow * A.k, kc = A.mean ? A.k : 0;
+  CU(act.alloc((size_t)A.n_units * (N + kc)));
+  CU(scratch.alloc(activity_scratch_doubles(A.n_units, N + kc, A.S)));
+  CU(launch_activity(A.coef, A.cst, A.n_units, N, kc, A.S, n_lo, n_hi, act.p, scratch.p, st));
+  return 0;
+}
+
 // ---- density forecast -------------------------------------------------------------------
 int bvhar_cuda_forecast_density(const bvhar_forecast_desc* d, double* out_density, double* out_lpl) {
   if (!d || !out_density) return fail(BVHAR_ERR_BAD_ARG, "null argument");
@@ -1317,6 +1335,12 @@ int bvhar_cuda_forecast_density(const bvhar_forecast_desc* d, double* out_densit
   A.sigh = {sigh.p, (long long)S * k, 1, S};
   A.last_obs = last.p;
   A.valid = valid.p; A.seed = seed.p; A.out = out.p; A.lpl = lpl.p;
+  DevBuf<double> act, act_scratch;
+  A.ncoef = ncoef;
+  if (d->level > 0) {  // Select forecasters (the caller's `sparse` draws are refused upstream: forecaster.h:445-447)
+    if (int rc = activity_graph(A, d->level, act, act_scratch, 0)) return rc;
+    A.act = act.p;
+  }
   CU(launch_forecast(A, 0));
   CU(cudaDeviceSynchronize());
   CU(cudaMemcpy(out_density, out.p, out.n * sizeof(double), cudaMemcpyDeviceToHost));
@@ -1378,6 +1402,13 @@ static int outforecast_batch(const bvhar_fit_desc* fd, const bvhar_outforecast_p
   CU(out.alloc((size_t)U * S * k * step));
   if (A.get_lpl) CU(lpl.alloc((size_t)U * step));
   A.har = har.p; A.last_obs = last.p; A.valid = valid.p; A.seed = seed.p; A.out = out.p; A.lpl = lpl.p;
+  DevBuf<double> act, act_scratch;
+  A.ncoef = D.N + (D.mean ? k : 0);
+  if (fp->level > 0) {  // McmcVarSelectForecaster / McmcVharSelectForecaster per refitted window (forecaster.h:1024-1030)
+    CU(cudaStreamSynchronize(fit->st));
+    if (int rc2 = activity_graph(A, fp->level, act, act_scratch, 0)) return rc2;
+    A.act = act.p;
+  }
   CU(launch_forecast(A, 0));
   CU(cudaDeviceSynchronize());
   std::vector<double> hout(out.n);
@@ -1414,6 +1445,7 @@ int bvhar_cuda_outforecast_run(const bvhar_fit_desc* fd, const bvhar_outforecast
   if (fp->step < 1 || fp->step > 64) return fail(BVHAR_ERR_UNSUPPORTED, "forecast step must be in 1..64");
   if (!fp->y_full || !fp->seed_forecast) return fail(BVHAR_ERR_BAD_ARG, "y_full / seed_forecast missing");
   if (fp->is_vhar && !fp->har_trans) return fail(BVHAR_ERR_BAD_ARG, "har_trans missing");
+  if (fp->sparse && fp->level > 0) return fail(BVHAR_ERR_BAD_ARG, "If 'level > 0', 'spare' should be false.");  // forecaster.h:445-447 (sic)
   if (fd->n_windows < 1 || fd->n_chains < 1 || !fd->win_row0 || !fd->win_nrow || !fd->seed_chain) return fail(BVHAR_ERR_BAD_ARG, "empty window table");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(BVHAR_ERR_CUDA, "no CUDA device available: no CPU fallback");

@@ -80,7 +80,14 @@ struct ForecastArgs {
   const double *last_obs, *valid;
   const uint32_t* seed;
   double *out, *lpl;
+  const double* act;  // [n_units][ncoef] activity graph of the Select forecasters (0 or 1.1), nullptr for the plain ones
+  int ncoef;          // nrow * k + k * mean
 };
 cudaError_t launch_forecast(const ForecastArgs& A, cudaStream_t st);
+// RegRecords::computeActivity (config.h:747-758) of every unit: act[u][i] for the ncoef = N + kc record columns
+// (alpha, then the constants); S draws per unit; n_lo / n_hi = the 1-based order statistics of the two tail quantiles
+size_t activity_scratch_doubles(int n_units, int ncoef, int S);
+cudaError_t launch_activity(const RecView& coef, const RecView& cst, int n_units, int N, int kc, int S, int n_lo, int n_hi, double* act,
+                            double* scratch, cudaStream_t st);
 
 }  // namespace bvhar

@@ -2,6 +2,7 @@
 #include "engine.cuh"
 #include "kernels.h"
 #include "rng.cuh"
+#include <math_constants.h>
 
 namespace bvhar {
 
@@ -126,11 +127,24 @@ __global__ void __launch_bounds__(128) forecast_kernel(const ForecastArgs A) {
         }
       }
       const double* xin = A.is_vhar ? hx : last_pvec;
-      for (int j = 0; j < k; ++j) {
-        double s = 0.0;
-        for (int r = 0; r < nrow; ++r) s += at(A.coef, j * nrow + r) * xin[r];
-        if (A.mean) s += at(A.cst, j) * xin[nrow];
-        pm[j] = s;
+      if (A.act) {
+        // Select forecasters (fc.h:372-374, 409-411): mean = x' (activity_graph o coef_mat); the graph is the activity
+        // VECTOR reshaped column-major to (nrow + mean) x k (fc.h:356), i.e. graph(r, j) = act[j * (nrow + mean) + r]
+        const double* act = A.act + (size_t)u * A.ncoef;
+        const int df = nrow + (A.mean ? 1 : 0);
+        for (int j = 0; j < k; ++j) {
+          double s = 0.0;
+          for (int r = 0; r < nrow; ++r) s += act[j * df + r] * at(A.coef, j * nrow + r) * xin[r];
+          if (A.mean) s += act[j * df + nrow] * at(A.cst, j) * xin[nrow];
+          pm[j] = s;
+        }
+      } else {
+        for (int j = 0; j < k; ++j) {
+          double s = 0.0;
+          for (int r = 0; r < nrow; ++r) s += at(A.coef, j * nrow + r) * xin[r];
+          if (A.mean) s += at(A.cst, j) * xin[nrow];
+          pm[j] = s;
+        }
       }
       if (A.sv_model) {
         if (A.sv)
@@ -170,6 +184,79 @@ __global__ void __launch_bounds__(128) forecast_kernel(const ForecastArgs A) {
   if (A.lpl)
     for (int h = threadIdx.x; h < step && h < 64; h += blockDim.x) atomicAdd(&A.lpl[(size_t)u * step + h], lpl_acc[h] / S);
 }
+// RegRecords::computeActivity (config.h:747-758): per record column, the two order statistics that
+// boost::accumulators::tail_quantile<left / right> return with the whole sample cached (BH >= 1.87, un-vendored:
+// "the largest of the ceil(n a) smallest" / "the smallest of the ceil(n (1 - a)) largest" samples, NaN when that count
+// is not below the cache size), then 0 when they have opposite signs, else 1.1.  One CTA per (column, unit): the S
+// draws of the column are sorted ascending by a bitonic network in shared memory (S <= ACT_SMEM_MAX), or - for longer
+// chains - ranked by counting in a global scratch row.
+constexpr int ACT_SMEM_MAX = 16384;
+__global__ void __launch_bounds__(256) activity_kernel(const RecView coef, const RecView cst, int N, int S, int n_lo, int n_hi, int ncoef,
+                                                       double* __restrict__ act, double* __restrict__ scratch) {
+  extern __shared__ __align__(16) double sm[];
+  const int col = blockIdx.x, u = blockIdx.y;
+  const RecView& v = col < N ? coef : cst;
+  const int c = col < N ? col : col - N;
+  const double* base = v.p + (long long)u * v.us + (long long)c * v.sc;
+  const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+  double lo = qnan, hi = qnan;
+  if (S <= ACT_SMEM_MAX) {
+    int P2 = 1;
+    while (P2 < S) P2 <<= 1;
+    for (int i = threadIdx.x; i < P2; i += blockDim.x) {
+      double x = i < S ? base[(long long)i * v.sd] : CUDART_INF;
+      sm[i] = x == x ? x : CUDART_INF;  // (NaN draws - a flagged chain - sort last)
+    }
+    __syncthreads();
+    for (int kk = 2; kk <= P2; kk <<= 1)
+      for (int j = kk >> 1; j > 0; j >>= 1) {
+        for (int i = threadIdx.x; i < P2; i += blockDim.x) {
+          const int l = i ^ j;
+          if (l > i) {
+            const double a = sm[i], b = sm[l];
+            const bool up = (i & kk) == 0;
+            if ((a > b) == up) { sm[i] = b; sm[l] = a; }
+          }
+        }
+        __syncthreads();
+      }
+    if (n_lo >= 1 && n_lo < S) lo = sm[n_lo - 1];
+    if (n_hi >= 1 && n_hi < S) hi = sm[S - n_hi];
+  } else {
+    double* row = scratch + ((size_t)u * ncoef + col) * S;
+    for (int i = threadIdx.x; i < S; i += blockDim.x) {
+      const double x = base[(long long)i * v.sd];
+      row[i] = x == x ? x : CUDART_INF;
+    }
+    __syncthreads();
+    __shared__ double pick[2];
+    for (int i = threadIdx.x; i < S; i += blockDim.x) {
+      const double x = row[i];
+      int rank = 0;  // position of element i in the stable ascending order
+      for (int m = 0; m < S; ++m) {
+        const double y = row[m];
+        rank += (y < x) || (y == x && m < i);
+      }
+      if (rank == n_lo - 1) pick[0] = x;
+      if (rank == S - n_hi) pick[1] = x;
+    }
+    __syncthreads();
+    if (n_lo >= 1 && n_lo < S) lo = pick[0];
+    if (n_hi >= 1 && n_hi < S) hi = pick[1];
+  }
+  if (threadIdx.x == 0) act[(size_t)u * ncoef + col] = (lo * hi < 0.0) ? 0.0 : 1.1;
+}
+size_t activity_scratch_doubles(int n_units, int ncoef, int S) { return S <= ACT_SMEM_MAX ? 0 : (size_t)n_units * ncoef * S; }
+cudaError_t launch_activity(const RecView& coef, const RecView& cst, int n_units, int N, int kc, int S, int n_lo, int n_hi, double* act,
+                            double* scratch, cudaStream_t st) {
+  int P2 = 1;
+  while (P2 < S) P2 <<= 1;
+  const size_t smem = S <= ACT_SMEM_MAX ? (size_t)P2 * sizeof(double) : 0;
+  cudaFuncSetAttribute(activity_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(ACT_SMEM_MAX * sizeof(double)));
+  activity_kernel<<<dim3(N + kc, n_units), 256, smem, st>>>(coef, cst, N, S, n_lo, n_hi, N + kc, act, scratch);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_forecast(const ForecastArgs& A, cudaStream_t st) {
   const int dd = A.p * A.k + (A.mean ? 1 : 0);
   const int per = dd + (A.p - 1) * A.k + 3 * A.k + (A.is_vhar ? A.har_r : 0);

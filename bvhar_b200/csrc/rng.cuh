@@ -118,6 +118,8 @@ struct Philox {
     const double z = normal(stage, idx, 0);
     const double c = mean / (2.0 * shape);
     const double w = mean * z * z;
+    // literal evaluation of common.h:104-106 on purpose: the catastrophic cancellation for w >> shape is part of the
+    // reference's behaviour (it keeps the Dirichlet-Laplace chains out of their absorbing state), see oracle_rng.h
     const double cand = mean + c * (w - sqrt(w * (4.0 * shape + w)));
     const double u = uniform(stage, idx, 1);
     if (u < mean / (mean + cand)) return cand;

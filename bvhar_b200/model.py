@@ -246,17 +246,30 @@ class _AutoregBayes:
     def _har(self):
         return None
 
+    @staticmethod
+    def _ci_level(sparse):
+        """``sparse`` given as a number = credible-interval level of the Select forecasters (R/forecast.R:423-428:
+        ``ci_lev <- sparse; sparse <- FALSE``); returns (sparse flag, level)."""
+        if isinstance(sparse, (bool, np.bool_)):
+            return bool(sparse), 0.0
+        if isinstance(sparse, (int, float, np.integer, np.floating)):
+            return False, float(sparse)
+        raise ValueError("'sparse' must be a bool or a credible-interval level")
+
     def predict(self, n_ahead: int, level=.05, stable=False, sparse=False, med=False, sv=True):
-        """'n_ahead'-step density forecast from the stored draws (forecaster.h:494-568)."""
+        """'n_ahead'-step density forecast from the stored draws (forecaster.h:494-568).  ``sparse``: ``True`` uses the
+        SAVS draws; a number uses the full draws restricted by the activity graph of that credible level
+        (``McmcVarSelectForecaster`` / ``McmcVharSelectForecaster``, forecaster.h:348-416)."""
+        sparse, ci_lev = self._ci_level(sparse)
         recs = self._chain_records()
         seeds = self._seeds(self.chains_)
         if stable:  # the stability filter (bvhar_cuda_is_stable) may keep a different number of draws per chain: one call per chain
             dens = [forecast_density([rec], [self.y_], n_ahead, self.lag_, self.fit_intercept, self._is_sv, [seeds[c]],
                                      har_trans=self._har(), sv=sv, stable=True, sparse=sparse, device=self._device,
-                                     unit_id_base=c)[0][0] for c, rec in enumerate(recs)]
+                                     unit_id_base=c, level=ci_lev)[0][0] for c, rec in enumerate(recs)]
         else:
             dens, _ = forecast_density(recs, [self.y_] * self.chains_, n_ahead, self.lag_, self.fit_intercept, self._is_sv, seeds,
-                                       har_trans=self._har(), sv=sv, sparse=sparse, device=self._device)
+                                       har_trans=self._har(), sv=sv, sparse=sparse, device=self._device, level=ci_lev)
         k = self.n_features_in_
         allchains = np.concatenate([d.reshape(n_ahead, -1, k) for d in dens], axis=1).reshape(n_ahead, -1)
         return self._summarise(allchains, k, level, med)
@@ -337,6 +350,7 @@ class _AutoregBayes:
         """forecast_roll / forecast_expand: window 0 reuses the fit, windows >= 1 are refitted, every
         (window, chain) in one GPU batch (forecaster.h:575-807, 851-875, 920-956)."""
         test = _check_np(test)
+        sparse, ci_lev = self._ci_level(sparse)
         k = self.n_features_in_
         n_hor = test.shape[0] - n_ahead + 1
         if n_hor < 1:
@@ -361,7 +375,7 @@ class _AutoregBayes:
             for i, (rec, lo, sd) in enumerate(zip(units, lasts, seeds_u)):
                 dens, lp = forecast_density([rec], [lo], n_ahead, self.lag_, self.fit_intercept, self._is_sv, [sd],
                                             har_trans=self._har(), sv=sv, valid_vec=valid, stable=True, sparse=sparse,
-                                            device=self._device, unit_id_base=base + i)
+                                            device=self._device, unit_id_base=base + i, level=ci_lev)
                 outs.append(dens[0][-1].reshape(-1, k))
                 lps.append(float(lp.mean()) if lp is not None else None)
             return outs, lps
@@ -376,7 +390,7 @@ class _AutoregBayes:
         else:
             dens0, lpl0 = forecast_density(list(self._chain_records()), [tot[: self.lag_ + nrow[0]]] * C_, n_ahead, self.lag_,
                                            self.fit_intercept, self._is_sv, seed_fc, har_trans=self._har(), sv=sv,
-                                           valid_vec=valid, sparse=sparse, device=self._device)
+                                           valid_vec=valid, sparse=sparse, device=self._device, level=ci_lev)
             per_window = [np.concatenate([d[-1].reshape(-1, k) for d in dens0], axis=0)]  # last step only (forecaster.h:803)
             if lpls is not None:
                 lpls.append(lpl0.mean(axis=1))
@@ -405,7 +419,7 @@ class _AutoregBayes:
             packed = self._pack(x_tot, y_tot, seeds[1:], win_row0=row0[1:], win_nrow=nrow[1:], record_mask=0,
                                 lvol_from_init=self._is_sv and expanding, unit_id_base=C_)
             fc, lp = outforecast(packed, tot, n_ahead, self.lag_, seed_fc, har_trans=self._har(), sv=sv, valid_vec=valid,
-                                 sparse=sparse)
+                                 sparse=sparse, level=ci_lev)
             per_window += [fc[w].reshape(-1, k) for w in range(n_hor - 1)]
             if lpls is not None:
                 lpls += [lp[w] for w in range(n_hor - 1)]

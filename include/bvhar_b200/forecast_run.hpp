@@ -5,7 +5,8 @@
 //       the same three constructors (VAR: lag; VHAR: week + month, or month + har_trans) with the reference's argument
 //       order, and `returnForecast()` -> one step x (draws * dim) matrix per chain (predictive_distn, forecaster.h:39).
 //       `fit_record` is what McmcRun::returnRecords() returned (one record map per chain); `stable = true` is the
-//       subsetStable filter (config.h:884-914, 1003-1034), decided on the device by bvhar_cuda_is_stable.
+//       subsetStable filter (config.h:884-914, 1003-1034), decided on the device by bvhar_cuda_is_stable; `level > 0`
+//       selects the Select forecasters (forecaster.h:348-416): activity graph on the device, mask in the forecast kernel.
 //
 // As in mcmc_run.hpp, `Matrix` stands for Eigen::MatrixXd and `Records` for the per-chain LIST.  Errors are
 // std::runtime_error with the reference's messages (forecaster.h:286, 322, 446).  No CPU fallback.
@@ -59,6 +60,7 @@ class McmcForecastRun {
     D.har_trans = har_.data.empty() ? nullptr : har_.data.data();
     D.coef_record = coef_.data(); D.contem_record = contem_.data(); D.diag_record = diag_.data();
     D.sigh_record = isSv ? sigh_.data() : nullptr; D.last_obs = last_.data(); D.seed = seeds_.data();
+    D.level = level_;  // activity graph of every chain computed on the device (config.h:747-758)
     std::vector<double> out((size_t)chains_ * step_ * draws_ * dim_);
     detail::check(bvhar_cuda_forecast_density(&D, out.data(), nullptr));
     std::vector<Matrix> res;
@@ -81,7 +83,7 @@ class McmcForecastRun {
             const std::vector<Records>& fit_record, const std::vector<uint32_t>& seed_chain, bool include_mean, bool stable, bool sv,
             int device) {
     if (sparse && level > 0) throw std::runtime_error("If 'level > 0', 'spare' should be false.");  // forecaster.h:445-447
-    if (level > 0) throw std::runtime_error("selection forecasters (level > 0, forecaster.h:348-416) are not part of this adapter");
+    level_ = level > 0 ? level : 0.0;  // level > 0: McmcVarSelectForecaster / McmcVharSelectForecaster (forecaster.h:348-416, 437-487)
     if ((int)fit_record.size() != num_chains || (int)seed_chain.size() != num_chains) throw std::runtime_error("fit_record / seed_chain need one entry per chain");
     if (response_mat.rows < ord) throw std::runtime_error("response_mat has fewer rows than the lag");
     chains_ = num_chains; lag_ = ord; step_ = step; dim_ = (int)response_mat.cols; mean_ = include_mean; sv_ = sv; device_ = device;
@@ -145,6 +147,7 @@ class McmcForecastRun {
 
   int chains_ = 0, lag_ = 0, step_ = 0, dim_ = 0, nrow_ = 0, draws_ = 0, device_ = 0;
   bool mean_ = true, sv_ = true;
+  double level_ = 0.0;
   Matrix har_;
   std::vector<uint32_t> seeds_;
   std::vector<double> coef_, contem_, diag_, sigh_, last_;

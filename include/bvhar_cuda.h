@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define BVHAR_CUDA_ABI_VERSION 1
+#define BVHAR_CUDA_ABI_VERSION 2
 
 typedef enum {
   BVHAR_OK = 0,
@@ -275,6 +275,12 @@ typedef struct {
   const double* last_obs;      /* per unit: var_lag x k column-major, the last var_lag rows of the response */
   const double* valid_vec;     /* k (forecaster.h:802) or NULL */
   const uint32_t* seed;        /* n_units (seed_forecast, forecaster.h:1028) */
+  /* level > 0 selects McmcVarSelectForecaster / McmcVharSelectForecaster (forecaster.h:348-416, factory :437-487): each
+   * unit's coefficient draws are masked by its activity graph, RegRecords::computeActivity(level) (config.h:747-758):
+   * entry i of coef_record is inactive (0) when the credible interval [tail_quantile<left>(level / 2),
+   * tail_quantile<right>(1 - level / 2)] of its draws has end points of opposite sign, otherwise 1.1 (sic); the vector
+   * is reshaped column-major to (num_coef / dim) x dim (forecaster.h:356).  0 = plain forecasters. */
+  double level;
 } bvhar_forecast_desc;
 
 /* out_density: per unit, step x (n_draws*k) column-major (McmcForecaster::predictive_distn,
@@ -302,6 +308,7 @@ typedef struct {
   int64_t y_rows;
   const double* valid_vec;      /* k (y_test.row(step), forecaster.h:802) or NULL */
   const uint32_t* seed_forecast;/* n_chains (forecaster.h:1028) */
+  double level;                 /* > 0: Select forecasters for every refitted window (forecaster.h:1024-1030, 1109-1115) */
 } bvhar_outforecast_params;
 /* out_forecast: [window][chain][draw * k + variable] (n_windows * n_chains * S * k doubles, S = kept draws);
  * out_lpl: [window][chain] average log-predictive likelihood over the steps, or NULL. */

@@ -1153,6 +1153,28 @@ static void forecast_unit(const bvhar_forecast_desc* D, int u, bool philox, doub
   const int har_r = 3 * k + (mean ? 1 : 0), har_c = p * k + (mean ? 1 : 0);
   Vec lpl(step, 0.0), last_pvec, post_mean(k), tmp((p - 1) * k), svu(k), svs(k), zn(k), hx(D->is_vhar ? har_r : 0);
   Mat coef(nrow + (mean ? 1 : 0), k);
+  // Select forecasters (fc.h:348-416): activity_graph = unvectorize(reg_record->computeActivity(level), dim), cfg.h:747-758.
+  // quantile_lower / quantile_upper (common.h:585-606) are boost::accumulators::tail_quantile<left / right> with the whole
+  // sample cached (Boost.Accumulators, BH >= 1.87, not vendored): n = ceil(count * prob) resp. ceil(count * (1. - prob)),
+  // result = the n-th smallest resp. n-th largest sample, NaN unless n < count.
+  Mat graph;
+  if (D->level > 0) {
+    const int df = nrow + (mean ? 1 : 0);
+    graph = Mat(df, k);
+    const double p_lo = D->level / 2, p_hi = 1 - D->level / 2;
+    const size_t n_lo = (size_t)std::ceil((double)S * p_lo), n_hi = (size_t)std::ceil((double)S * (1. - p_hi));
+    Vec col(S), sel(ncoef);
+    for (int e = 0; e < ncoef; ++e) {
+      for (int i = 0; i < S; ++i) col[i] = coef_rec[(size_t)e * S + i];
+      std::sort(col.begin(), col.end());
+      const double nan = std::numeric_limits<double>::quiet_NaN();
+      const double lo = (n_lo >= 1 && n_lo < (size_t)S) ? col[n_lo - 1] : nan;
+      const double hi = (n_hi >= 1 && n_hi < (size_t)S) ? col[S - n_hi] : nan;
+      sel[e] = lo * hi < 0 ? 0.0 : 1.1;
+    }
+    for (int j = 0; j < k; ++j)
+      for (int r = 0; r < df; ++r) graph(r, j) = sel[(size_t)j * df + r];  // column-major reshape of the VECTOR (fc.h:356)
+  }
   for (int i = 0; i < S; ++i) {
     rng.iter = (uint32_t)i;
     last_pvec = obs;
@@ -1163,6 +1185,9 @@ static void forecast_unit(const bvhar_forecast_desc* D, int u, bool philox, doub
       for (int r = 0; r < nrow; ++r) coef(r, j) = coef_rec[(size_t)(j * nrow + r) * S + i];
       if (mean) coef(nrow, j) = coef_rec[(size_t)(nrow * k + j) * S + i];
     }
+    if (D->level > 0)  // computeMean of the Select variants: (activity_graph o coef_mat), fc.h:372-374, 409-411
+      for (int j = 0; j < k; ++j)
+        for (int r = 0; r < nrow + (mean ? 1 : 0); ++r) coef(r, j) *= graph(r, j);
     Vec a(q);
     for (int e = 0; e < q; ++e) a[e] = a_rec[(size_t)e * S + i];
     Mat L = build_inv_lower(k, a.data());

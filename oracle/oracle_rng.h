@@ -195,6 +195,11 @@ struct Rng {
     double z = normal(stage, idx, 0);
     double c = mean / (2.0 * shape);
     double w = mean * z * z;  // alpha * chi2(1)
+    // The smaller root, evaluated LITERALLY as common.h:104-106 writes it.  The expression cancels catastrophically when
+    // w >> shape (relative error ~ 2^-53 w / shape, it can even come out <= 0), and that rounding noise is load-bearing:
+    // with the cancellation-free form mean * 4 shape w / (w + r)^2 the Dirichlet-Laplace contemporaneous block (q = 3)
+    // collapses into its absorbing state (global -> DBL_MIN -> NaN within ~400 sweeps), whereas the literal form keeps
+    // kicking collapsed chains out again, which is what the reference's posterior reflects.  Do not "fix".
     double cand = mean + c * (w - std::sqrt(w * (4.0 * shape + w)));
     double u = uniform(stage, idx, 1);
     if (u < mean / (mean + cand)) return cand;

@@ -254,3 +254,52 @@ def test_forecast_density(sv_model, vhar, lpl):
         assert relerr(dens[u], dens2[u]) == 0.0
     if lpl:
         assert relerr(lp.reshape(2, step), l) < 1e-9
+
+
+@pytest.mark.parametrize("sv_model,vhar", [(True, False), (False, False), (True, True), (False, True)])
+@pytest.mark.parametrize("level", [0.05, 0.5])
+def test_select_forecasters(sv_model, vhar, level):
+    """McmcVarSelectForecaster / McmcVharSelectForecaster (forecaster.h:348-416): the activity graph
+    (RegRecords::computeActivity, config.h:747-758, entries 0 or 1.1) is computed on the device from the draws and
+    applied in the forecast mean; VAR + VHAR x LDLT + SV against the oracle, and the graph itself against NumPy."""
+    pk, meta = pr.pack(prior="Horseshoe", sv=sv_model, dim=3, T=60, vhar=vhar, week=2, month=4, chains=2, iters=44, burn=4)
+    g = CudaFit(pk); g.run()
+    units = [g.records(0, c) for c in range(2)]
+    from bvhar_b200._design import build_vhar
+    from bvhar_b200._engine import pack_forecast
+    har = build_vhar(3, 2, 4, True) if vhar else None
+    lag = 4 if vhar else 2
+    step = 3
+    valid = meta["y"][-1] * 1.1
+    dens, lp = forecast_density(units, [meta["y"]] * 2, step, lag, True, sv_model, [21, 22], har_trans=har, valid_vec=valid, level=level)
+    plain, _ = forecast_density(units, [meta["y"]] * 2, step, lag, True, sv_model, [21, 22], har_trans=har, valid_vec=valid)
+    D, keep = pack_forecast(units, [meta["y"]] * 2, step, lag, True, sv_model, [21, 22], har_trans=har, valid_vec=valid, level=level)
+    S = D.n_draws
+    out = np.empty(2 * step * S * 3); lpo = np.zeros(2 * step)
+    ob.lib().oracle_forecast_density(C.byref(D), 0, ob.dp(out), ob.dp(lpo))
+    for u in range(2):
+        ref = out[u * step * S * 3:(u + 1) * step * S * 3].reshape(step, S * 3, order="F")
+        assert relerr(ref, dens[u]) < 1e-9
+        # the mask changes the forecast (1.1-scaled or zeroed coefficients), i.e. the Select path really ran
+        assert relerr(plain[u], dens[u]) > 1e-3
+    assert relerr(lpo.reshape(2, step), lp) < 1e-9
+
+
+def test_select_outforecast_matches_fit_plus_forecast():
+    """`level` through the native out-of-sample runner (forecaster.h:1024-1030): bvhar_cuda_outforecast_run with level > 0
+    equals refit -> records -> forecast_density(level) unit by unit."""
+    from bvhar_b200._engine import outforecast
+    wins = [(1, 30), (2, 30)]
+    kw, meta = pr.make_problem(prior="NG", sv=True, dim=2, T=46, lag=2, chains=2, iters=40, burn=8, windows=wins,
+                               record_mask=_abi.REC_COEF | _abi.REC_LVOL_LAST)
+    kw["unit_id_base"] = 2
+    y = meta["y"]
+    fc, lp = outforecast(_abi.PackedFit(**kw), y, 2, 2, [5, 6], valid_vec=y[-1], level=0.2)
+    g = CudaFit(_abi.PackedFit(**kw)); g.run()
+    for w, (r0, n) in enumerate(wins):
+        units = [g.records(w, c) for c in range(2)]
+        dens, l2 = forecast_density(units, [y[: 2 + r0 + n]] * 2, 2, 2, True, True, [5, 6], valid_vec=y[-1], level=0.2,
+                                    unit_id_base=2 + w * 2)
+        for c in range(2):
+            assert np.array_equal(fc[w, c].reshape(-1), dens[c][-1]), (w, c)
+            assert abs(lp[w, c] - l2[c].mean()) < 1e-12

@@ -1,6 +1,7 @@
-"""Properties at BASELINE.json's full sizes, where the oracle is too slow to be the checker:
-determinism, invariance of every unit's draws to how the batch is split (= to the GPU count), stage
-identities that hold at any size (Z = Y - XA, L unit lower, SV weights positive), finite posteriors."""
+"""Size-independent properties at BASELINE.json's full batch sizes (1 024 chains of C3): determinism, invariance
+of every unit's draws to how the batch is split (= to the GPU count), stage identities that hold at any size
+(Z = Y - XA, L unit lower, SV weights positive), finite posteriors.  The oracle comparison at the same shapes
+(a few units of each configuration, stage by stage) is tests/test_gpu_baseline_parity.py."""
 import numpy as np
 import pytest
 
