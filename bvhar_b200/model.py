@@ -19,7 +19,7 @@ from typing import Dict, List, Optional
 import numpy as np
 
 from . import _abi
-from ._abi import REC_ALL, REC_COEF, REC_LVOL_LAST, REC_SPARSE, PackedFit
+from ._abi import REC_ALL, REC_COEF, REC_LVOL, REC_LVOL_LAST, REC_SPARSE, PackedFit
 from ._design import build_design, build_grpmat, build_response, build_vhar, build_vhar_design
 from ._engine import CudaFit, forecast_density, outforecast
 from ._spec import (PRIOR_TYPE, DlConfig, GdpConfig, HorseshoeConfig, InterceptConfig, LdltConfig, MinnesotaConfig,
@@ -38,7 +38,7 @@ def _check_np(data) -> np.ndarray:
 class _AutoregBayes:
     def __init__(self, data, lag, p, n_chain=1, n_iter=1000, n_burn=None, n_thin=1, bayes_config=None, cov_config=None,
                  intercept_config=None, fit_intercept=True, minnesota="longrun", ggl=True, verbose=False, seed=None,
-                 device: int = 0, record_mask: int = REC_ALL):
+                 device: int = 0, record_mask: Optional[int] = None):
         self.y_ = _check_np(data)
         self.n_features_in_ = self.y_.shape[1]
         self.p_ = p
@@ -99,12 +99,23 @@ class _AutoregBayes:
     def _seeds(self, *shape):
         return self._rng.integers(1, np.iinfo(np.int32).max, size=shape)
 
+    def _default_record_mask(self) -> int:
+        """Record policy when the caller gives none: everything the reference's ``returnRecords()`` returns - except that
+        batches of >= 64 stochastic-volatility chains keep the log-volatilities of the LAST time point (``h_last_record``,
+        all the forecasters read: config.h:998-1001) instead of the full ``h_record`` (n x k doubles per draw per chain:
+        0.94 TB at BASELINE's C3).  ``record_mask=REC_ALL`` brings the full ``h_record`` back."""
+        if self._record_mask is not None:
+            return int(self._record_mask)
+        if self._is_sv and self.chains_ >= 64:
+            return (REC_ALL & ~REC_LVOL) | REC_LVOL_LAST
+        return REC_ALL
+
     def _pack(self, x, y, seeds, win_row0=None, win_nrow=None, record_mask=None, lvol_from_init=False, unit_id_base=0) -> PackedFit:
         return PackedFit(self.chains_, self.iter_, self.burn_, self.thin_, x, y, self.cov_spec_.to_dict(),
                          self.spec_.to_dict(), self.intercept_spec_.to_dict(), self.init_, int(self._prior_type),
                          self._group_id, self._own_id, self._cross_id, self.group_, self.fit_intercept, seeds,
                          is_group=self._ggl, win_row0=win_row0, win_nrow=win_nrow,
-                         record_mask=self._record_mask if record_mask is None else record_mask, device=self._device,
+                         record_mask=self._default_record_mask() if record_mask is None else record_mask, device=self._device,
                          lvol_from_init=lvol_from_init, unit_id_base=unit_id_base)
 
     def _coef_name(self) -> str:
@@ -121,7 +132,7 @@ class _AutoregBayes:
                   y=self.response_, param_cov=self.cov_spec_.to_dict(), param_prior=self.spec_.to_dict(),
                   param_intercept=self.intercept_spec_.to_dict(), param_init=self.init_, prior_type=int(self._prior_type),
                   grp_id=self._group_id, own_id=self._own_id, cross_id=self._cross_id, grp_mat=self.group_,
-                  include_mean=self.fit_intercept, seed_chain=seeds, is_group=self._ggl, record_mask=self._record_mask)
+                  include_mean=self.fit_intercept, seed_chain=seeds, is_group=self._ggl, record_mask=self._default_record_mask())
         world = len(devices)
         fits, errs = [None] * world, [None] * world
 
@@ -347,8 +358,25 @@ class _AutoregBayes:
         return {"tot": dens(tot), "to": dens(to), "from": dens(frm), "net": dens(to - frm)}
 
     def _outforecast(self, n_ahead: int, test, expanding: bool, level, stable, sparse, med, sv):
-        """forecast_roll / forecast_expand: window 0 reuses the fit, windows >= 1 are refitted, every
-        (window, chain) in one GPU batch (forecaster.h:575-807, 851-875, 920-956)."""
+        """forecast_roll / forecast_expand: the draws of ``_outforecast_draws`` summarised per window
+        (process_forecast_draws, R/misc-r.R:186-268; _bayes.py:500-512)."""
+        k = self.n_features_in_
+        per_window, lpls = self._outforecast_draws(n_ahead, test, expanding, stable, sparse, sv)
+        out = {"forecast": [], "se": [], "lower": [], "upper": []}
+        for pw in per_window:
+            s = self._summarise(pw.reshape(1, -1), k, level, med)  # all chains' draws of the window pooled
+            for key in out:
+                out[key].append(s[key])
+        res = {key: np.concatenate(v, axis=0) for key, v in out.items()}
+        if lpls is not None:
+            l = np.stack(lpls)  # [window, chain]
+            res["lpl"] = np.median(l, axis=1) if med else np.mean(l, axis=1)
+        return res
+
+    def _outforecast_draws(self, n_ahead: int, test, expanding: bool, stable, sparse, sv):
+        """``McmcOutforecastRun::returnForecast`` (forecaster.h:575-807, 851-875, 920-956): window 0 reuses the fit, windows
+        >= 1 are refitted, every (window, chain) in one GPU batch.  Returns (per window: the last-step draws of all chains,
+        [chain * draws, k]; per window: the chains' average log-predictive likelihoods, or None)."""
         test = _check_np(test)
         sparse, ci_lev = self._ci_level(sparse)
         k = self.n_features_in_
@@ -423,16 +451,7 @@ class _AutoregBayes:
             per_window += [fc[w].reshape(-1, k) for w in range(n_hor - 1)]
             if lpls is not None:
                 lpls += [lp[w] for w in range(n_hor - 1)]
-        out = {"forecast": [], "se": [], "lower": [], "upper": []}
-        for w in range(n_hor):
-            s = self._summarise(per_window[w].reshape(1, -1), k, level, med)  # all chains' draws of the window pooled
-            for key in out:
-                out[key].append(s[key])
-        res = {key: np.concatenate(v, axis=0) for key, v in out.items()}
-        if lpls is not None:
-            l = np.stack(lpls)  # [window, chain]
-            res["lpl"] = np.median(l, axis=1) if med else np.mean(l, axis=1)
-        return res
+        return per_window, lpls
 
     def roll_forecast(self, n_ahead: int, test, level=.05, stable=False, sparse=False, med=False, sv=True):
         return self._outforecast(n_ahead, test, False, level, stable, sparse, med, sv)
@@ -446,7 +465,7 @@ class VarBayes(_AutoregBayes):
 
     def __init__(self, data, lag=1, n_chain=1, n_iter=1000, n_burn=None, n_thin=1, bayes_config=None, cov_config=None,
                  intercept_config=None, fit_intercept=True, minnesota=True, ggl=True, verbose=False, n_thread=1, seed=None,
-                 device: int = 0, record_mask: int = REC_ALL):
+                 device: int = 0, record_mask: Optional[int] = None):
         super().__init__(data, lag, lag, n_chain, n_iter, n_burn, n_thin, bayes_config, cov_config, intercept_config,
                          fit_intercept, "short" if minnesota else "no", ggl, verbose, seed, device, record_mask)
         self.design_ = build_design(self.y_, lag, fit_intercept)
@@ -474,7 +493,7 @@ class VharBayes(_AutoregBayes):
 
     def __init__(self, data, week=5, month=22, n_chain=1, n_iter=1000, n_burn=None, n_thin=1, bayes_config=None,
                  cov_config=None, intercept_config=None, fit_intercept=True, minnesota="longrun", ggl=True, verbose=False,
-                 n_thread=1, seed=None, device: int = 0, record_mask: int = REC_ALL):
+                 n_thread=1, seed=None, device: int = 0, record_mask: Optional[int] = None):
         super().__init__(data, month, 3, n_chain, n_iter, n_burn, n_thin, bayes_config, cov_config, intercept_config,
                          fit_intercept, minnesota, ggl, verbose, seed, device, record_mask)
         self.week_ = week

@@ -52,17 +52,25 @@ class McmcForecastRun {
   }
 
   // forecaster.h:557-560
-  std::vector<Matrix> returnForecast() {
+  std::vector<Matrix> returnForecast() { return forecastDensity(nullptr, nullptr, 0); }
+
+  // McmcForecaster::forecastDensity(valid_vec) for every chain (forecaster.h:73-85): `lpl`, when given, receives the
+  // chains x step log-predictive-likelihood averages (forecaster.h:83); `unit_id_base` = Philox key word 1 of chain 0
+  // (the out-of-sample runners number their forecasters by (window, chain) unit).
+  std::vector<Matrix> forecastDensity(const std::vector<double>* valid_vec, std::vector<double>* lpl, int unit_id_base) {
     bvhar_forecast_desc D = {};
     D.abi_version = BVHAR_CUDA_ABI_VERSION; D.device = device_; D.n_units = chains_; D.dim = dim_; D.nrow_coef = nrow_;
     D.include_mean = mean_; D.cov_type = isSv ? BVHAR_COV_SV : BVHAR_COV_LDLT; D.step = step_; D.var_lag = lag_;
-    D.is_vhar = har_.data.empty() ? 0 : 1; D.sv = sv_; D.get_lpl = 0; D.n_draws = draws_; D.unit_id_base = 0;
+    D.is_vhar = har_.data.empty() ? 0 : 1; D.sv = sv_; D.n_draws = draws_; D.unit_id_base = unit_id_base;
+    D.get_lpl = valid_vec && lpl ? 1 : 0; D.valid_vec = D.get_lpl ? valid_vec->data() : nullptr;
+    if (D.get_lpl && (int)valid_vec->size() != dim_) throw std::runtime_error("valid_vec needs one entry per variable");
     D.har_trans = har_.data.empty() ? nullptr : har_.data.data();
     D.coef_record = coef_.data(); D.contem_record = contem_.data(); D.diag_record = diag_.data();
     D.sigh_record = isSv ? sigh_.data() : nullptr; D.last_obs = last_.data(); D.seed = seeds_.data();
     D.level = level_;  // activity graph of every chain computed on the device (config.h:747-758)
     std::vector<double> out((size_t)chains_ * step_ * draws_ * dim_);
-    detail::check(bvhar_cuda_forecast_density(&D, out.data(), nullptr));
+    if (D.get_lpl) lpl->assign((size_t)chains_ * step_, 0.0);
+    detail::check(bvhar_cuda_forecast_density(&D, out.data(), D.get_lpl ? lpl->data() : nullptr));
     std::vector<Matrix> res;
     const size_t per = (size_t)step_ * draws_ * dim_;
     for (int c = 0; c < chains_; ++c) {
@@ -145,6 +153,9 @@ class McmcForecastRun {
         for (int l = 0; l < ord; ++l) last_[((size_t)c * k + j) * ord + l] = response_mat(response_mat.rows - ord + l, j);
   }
 
+  int draws() const { return draws_; }
+
+ private:
   int chains_ = 0, lag_ = 0, step_ = 0, dim_ = 0, nrow_ = 0, draws_ = 0, device_ = 0;
   bool mean_ = true, sv_ = true;
   double level_ = 0.0;

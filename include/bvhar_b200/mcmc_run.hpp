@@ -84,39 +84,55 @@ inline void minnesota_moments(const ParamList& prior, int dim, int nrow, bool hi
       }
 }
 
-template <bool isSv, bool isGroup = true>
-class McmcRun {
- public:
-  McmcRun(int num_chains, int num_iter, int num_burn, int thin, const Matrix& x, const Matrix& y, const ParamList& param_cov,
-          const ParamList& param_prior, const ParamList& param_intercept, const std::vector<ParamList>& param_init,
-          int prior_type, const std::vector<int32_t>& grp_id, const std::vector<int32_t>& own_id,
-          const std::vector<int32_t>& cross_id, const std::vector<int32_t>& grp_mat /* column-major (nrow x dim) */,
-          bool include_mean, const std::vector<uint32_t>& seed_chain, bool display_progress = false, int nthreads = 1,
-          int device = 0, uint32_t record_mask = BVHAR_REC_ALL)
-      : num_chains_(num_chains), display_(display_progress) {
-    (void)nthreads;  // all chains advance together on the GPU
+namespace detail {
+inline std::vector<std::string> record_names(bvhar_fit* fit) {
+  char buf[4096];
+  check(bvhar_cuda_fit_record_names(fit, buf, sizeof buf));
+  std::vector<std::string> names;
+  for (const char* p = buf; *p;) {
+    const char* e = p;
+    while (*e && *e != '\n') ++e;
+    names.emplace_back(p, e);
+    p = *e ? e + 1 : e;
+  }
+  return names;
+}
+}  // namespace detail
+
+// Fills a bvhar_fit_desc from the reference's constructor arguments (the LISTs parsed by config.h:50-575) and owns the
+// temporaries the descriptor points into.  One window covering every row of x by default; the out-of-sample runners
+// overwrite the window table, the seeds and unit_id_base.  `lvol_rows` = rows of the chains' `lvol` init blocks (the first
+// window's length); with lvol_from_init the blocks are not read at all.
+struct FitDescBuilder {
+  bvhar_fit_desc desc{};
+  std::vector<double> mmean, mprec;
+  std::vector<bvhar_chain_init> inits;
+  int32_t row0 = 0, nr = 0;
+
+  FitDescBuilder(const Matrix& x, const Matrix& y, const ParamList& param_cov, const ParamList& param_prior, const ParamList& param_intercept,
+                 const std::vector<ParamList>& param_init, int prior_type, const std::vector<int32_t>& grp_id,
+                 const std::vector<int32_t>& own_id, const std::vector<int32_t>& cross_id, const std::vector<int32_t>& grp_mat,
+                 bool include_mean, bool is_sv, bool is_group, int num_chains, int num_iter, int num_burn, int thin, int device,
+                 uint32_t record_mask = BVHAR_REC_ALL, int64_t lvol_rows = -1) {
     using namespace detail;
-    if ((param_cov.count("initial_mean") != 0) != isSv)
-      throw std::runtime_error("param_cov does not match the sampler type ('initial_mean' selects SV, src/triangular.cpp:33)");
     if (x.rows != y.rows) throw std::runtime_error("x and y need the same number of rows");
-    if ((int)param_init.size() != num_chains || (int)seed_chain.size() != num_chains)
-      throw std::runtime_error("param_init / seed_chain need one entry per chain");
+    if ((int)param_init.size() != num_chains) throw std::runtime_error("param_init needs one entry per chain");
     const int dim = (int)y.cols, d = (int)x.cols, q = dim * (dim - 1) / 2;
     const int n_alpha = dim * d - (include_mean ? dim : 0), nrow = n_alpha / dim, G = (int)grp_id.size();
     if ((int)grp_mat.size() != n_alpha) throw std::runtime_error("grp_mat has the wrong size");
-    bvhar_fit_desc D = {};
+    bvhar_fit_desc& D = desc;
     D.abi_version = BVHAR_CUDA_ABI_VERSION; D.device = device;
     D.n_windows = 1; D.n_chains = num_chains; D.dim = dim; D.dim_design = d; D.include_mean = include_mean;
-    D.cov_type = isSv ? BVHAR_COV_SV : BVHAR_COV_LDLT; D.prior_type = prior_type; D.is_group = isGroup;
+    D.cov_type = is_sv ? BVHAR_COV_SV : BVHAR_COV_LDLT; D.prior_type = prior_type; D.is_group = is_group;
     D.num_iter = num_iter; D.num_burn = num_burn; D.thin = thin; D.record_mask = record_mask;
     D.n_rows_total = x.rows; D.x = x.data.data(); D.y = y.data.data();
-    const int32_t row0 = 0, nr = (int32_t)x.rows;
+    nr = (int32_t)x.rows;
     D.win_row0 = &row0; D.win_nrow = &nr;
     D.grp_mat = grp_mat.data(); D.grp_id = grp_id.data(); D.n_grp = G;
     D.own_id = own_id.data(); D.n_own = (int)own_id.size(); D.cross_id = cross_id.data(); D.n_cross = (int)cross_id.size();
     D.sig_shape = need(param_cov, "shape", dim, "param_cov").data();
     D.sig_scale = need(param_cov, "scale", dim, "param_cov").data();
-    if (isSv) {
+    if (is_sv) {
       D.sv_init_mean = need(param_cov, "initial_mean", dim, "param_cov").data();
       D.sv_init_prec = need(param_cov, "initial_prec", (size_t)dim * dim, "param_cov").data();
     }
@@ -124,7 +140,6 @@ class McmcRun {
       D.mean_non = need(param_intercept, "mean_non", dim, "param_intercept").data();
       D.sd_non = scalar(param_intercept, "sd_non", "param_intercept");
     }
-    std::vector<double> mmean, mprec;
     bvhar_prior_params& P = D.prior;
     switch (prior_type) {
       case BVHAR_PRIOR_MINNESOTA:
@@ -165,16 +180,16 @@ class McmcRun {
         break;
       default: throw std::runtime_error("prior_type must be 1..7");
     }
-    std::vector<bvhar_chain_init> inits(num_chains);
+    inits.resize(num_chains);
     for (int c = 0; c < num_chains; ++c) {
       const ParamList& in = param_init[c];
       bvhar_chain_init& I = inits[c];
       I = bvhar_chain_init{};
       I.init_coef = need(in, "init_coef", (size_t)d * dim, "param_init").data();
       I.init_contem = need(in, "init_contem", q, "param_init").data();
-      if (isSv) {
+      if (is_sv) {
         I.lvol_init = need(in, "lvol_init", dim, "param_init").data();
-        I.lvol = need(in, "lvol", (size_t)x.rows * dim, "param_init").data();
+        I.lvol = lvol_rows == 0 ? opt(in, "lvol") : need(in, "lvol", (size_t)(lvol_rows < 0 ? x.rows : lvol_rows) * dim, "param_init").data();
         I.lvol_sig = need(in, "lvol_sig", dim, "param_init").data();
       } else {
         I.init_diag = need(in, "init_diag", dim, "param_init").data();
@@ -193,8 +208,29 @@ class McmcRun {
       I.contem_gamma_shape = sc("contem_gamma_shape"); I.contem_gamma_rate = sc("contem_gamma_rate");
     }
     D.init = inits.data();
-    D.seed_chain = seed_chain.data();
-    detail::check(bvhar_cuda_fit_create(&D, &fit_));  // copies everything it needs: the locals above may die now
+  }
+  FitDescBuilder(const FitDescBuilder&) = delete;
+  FitDescBuilder& operator=(const FitDescBuilder&) = delete;
+};
+
+template <bool isSv, bool isGroup = true>
+class McmcRun {
+ public:
+  McmcRun(int num_chains, int num_iter, int num_burn, int thin, const Matrix& x, const Matrix& y, const ParamList& param_cov,
+          const ParamList& param_prior, const ParamList& param_intercept, const std::vector<ParamList>& param_init,
+          int prior_type, const std::vector<int32_t>& grp_id, const std::vector<int32_t>& own_id,
+          const std::vector<int32_t>& cross_id, const std::vector<int32_t>& grp_mat /* column-major (nrow x dim) */,
+          bool include_mean, const std::vector<uint32_t>& seed_chain, bool display_progress = false, int nthreads = 1,
+          int device = 0, uint32_t record_mask = BVHAR_REC_ALL)
+      : num_chains_(num_chains), display_(display_progress) {
+    (void)nthreads;  // all chains advance together on the GPU
+    if ((param_cov.count("initial_mean") != 0) != isSv)
+      throw std::runtime_error("param_cov does not match the sampler type ('initial_mean' selects SV, src/triangular.cpp:33)");
+    if ((int)seed_chain.size() != num_chains) throw std::runtime_error("param_init / seed_chain need one entry per chain");
+    FitDescBuilder B(x, y, param_cov, param_prior, param_intercept, param_init, prior_type, grp_id, own_id, cross_id, grp_mat, include_mean,
+                     isSv, isGroup, num_chains, num_iter, num_burn, thin, device, record_mask);
+    B.desc.seed_chain = seed_chain.data();
+    detail::check(bvhar_cuda_fit_create(&B.desc, &fit_));  // copies everything it needs: the builder may die now
   }
   McmcRun(const McmcRun&) = delete;
   McmcRun& operator=(const McmcRun&) = delete;
@@ -203,27 +239,27 @@ class McmcRun {
   }
 
   // McmcRun::returnRecords (triangular.h:1230-1233): runs burn-in + sampling, returns the thinned records per chain.
+  // Every record comes back with ONE bulk device-to-host copy (bvhar_cuda_fit_record_all: [chain][draw][column]) and is
+  // then laid out column-major per chain, as Eigen / R / NumPy(order="F") hold it.
   std::vector<Records> returnRecords() {
     const int rc = bvhar_cuda_fit_run(fit_, display_ ? &McmcRun::log_progress : nullptr, nullptr);
     if (rc != BVHAR_OK && rc != BVHAR_ERR_NUMERICAL && rc != BVHAR_ERR_INTERRUPTED) detail::check(rc);
-    char buf[4096];
-    detail::check(bvhar_cuda_fit_record_names(fit_, buf, sizeof buf));
-    std::vector<std::string> names;
-    for (const char* p = buf; *p;) {
-      const char* e = p;
-      while (*e && *e != '\n') ++e;
-      names.emplace_back(p, e);
-      p = *e ? e + 1 : e;
-    }
+    const std::vector<std::string> names = detail::record_names(fit_);
     std::vector<Records> out(num_chains_);
-    for (int c = 0; c < num_chains_; ++c)
-      for (const auto& nm : names) {
-        int64_t r = 0, k = 0;
-        detail::check(bvhar_cuda_fit_record_dims(fit_, nm.c_str(), &r, &k));
+    std::vector<double> bulk;
+    for (const auto& nm : names) {
+      int64_t r = 0, k = 0;
+      detail::check(bvhar_cuda_fit_record_dims(fit_, nm.c_str(), &r, &k));
+      bulk.resize((size_t)num_chains_ * r * k);
+      if (r * k > 0) detail::check(bvhar_cuda_fit_record_all(fit_, nm.c_str(), bulk.data(), num_chains_, r, k));
+      for (int c = 0; c < num_chains_; ++c) {
         Matrix m(r, k);
-        if (r * k > 0) detail::check(bvhar_cuda_fit_record(fit_, 0, c, nm.c_str(), m.data.data(), r, k));
+        const double* src = bulk.data() + (size_t)c * r * k;
+        for (int64_t i = 0; i < r; ++i)
+          for (int64_t j = 0; j < k; ++j) m(i, j) = src[(size_t)i * k + j];
         out[c].emplace(nm, std::move(m));
       }
+    }
     return out;
   }
 

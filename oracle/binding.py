@@ -69,12 +69,28 @@ def lib():
         L.oracle_minnesota_moments.argtypes = [C.c_int, C.c_int, c_dp, C.c_double, C.c_double, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp]
         L.oracle_minnesota_moments.restype = None
         L.oracle_max_threads.restype = C.c_int
+        L.oracle_use_blas.argtypes = [C.c_char_p, C.c_char_p]
         _lib = L
     return _lib
 
 
 def dp(a):
     return a.ctypes.data_as(c_dp)
+
+
+def use_scipy_openblas(on: bool = True) -> str:
+    """Route the oracle's large dense products / Cholesky factorisations through the OpenBLAS bundled with SciPy
+    (single-threaded per call; bench.py's reference arm only).  Returns a description of the back end in use."""
+    if not on:
+        lib().oracle_use_blas(None, None)
+        return "hand-written loops, no BLAS"
+    import glob
+    import scipy
+    cands = glob.glob(os.path.join(os.path.dirname(os.path.dirname(scipy.__file__)), "scipy.libs", "libscipy_openblas*.so"))
+    for path in cands:
+        if lib().oracle_use_blas(path.encode(), b"scipy_") == 0:
+            return f"OpenBLAS bundled with SciPy {scipy.__version__} ({os.path.basename(path)}: dgemm / dpotrf, 1 thread per call)"
+    return "hand-written loops, no BLAS (no bundled OpenBLAS found)"
 
 
 class OracleFit:

@@ -19,6 +19,7 @@
 //               the arithmetic the CUDA engine implements.
 // tests/ check faithful == efficient to rounding, and the CUDA engine against `efficient`.
 #include <omp.h>
+#include <dlfcn.h>
 
 #include <cstdio>
 #include <cstdlib>
@@ -1557,5 +1558,25 @@ void oracle_minnesota_moments(int k, int lag, const double* sigma, double lambda
 }
 
 int oracle_max_threads() { return omp_get_max_threads(); }
+
+// Route the large dense products / Cholesky factorisations through a BLAS shared library (bench.py's reference arm: the
+// OpenBLAS bundled with SciPy, symbols scipy_cblas_dgemm / scipy_dpotrf_ / scipy_openblas_set_num_threads).  The library is
+// put in single-thread mode: the parallelism stays the reference's (one OpenMP task per chain, tri.h:1222).  Returns 0 on
+// success; path == NULL switches back to the hand-written loops.
+int oracle_use_blas(const char* path, const char* prefix) {
+  if (!path) { blas_dgemm() = nullptr; lapack_dpotrf() = nullptr; return 0; }
+  void* h = dlopen(path, RTLD_NOW | RTLD_LOCAL);
+  if (!h) return 1;
+  const std::string pre = prefix ? prefix : "";
+  auto sym = [&](const char* nm) { return dlsym(h, (pre + nm).c_str()); };
+  void* g = sym("cblas_dgemm");
+  void* c = sym("dpotrf_");
+  void* t = sym("openblas_set_num_threads");
+  if (!g || !c) return 2;
+  if (t) ((void (*)(int))t)(1);
+  blas_dgemm() = (cblas_dgemm_fn)g;
+  lapack_dpotrf() = (dpotrf_fn)c;
+  return 0;
+}
 
 }  // extern "C"

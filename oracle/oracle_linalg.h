@@ -1,7 +1,7 @@
 // TEST INFRASTRUCTURE ONLY (see oracle_rng.h).  Small dense column-major linear algebra for the
 // oracle: stands in for the Eigen 3.4 calls of the reference (LLT, triangularView::solve, GEMM,
 // kroneckerProduct; un-vendored dependency RcppEigen >= 0.3.4, DESCRIPTION:46).  Hand-written
-// loops, no BLAS.
+// loops; an optional BLAS back end for the big faithful-mode products (see blas_dgemm below).
 #ifndef BVHAR_ORACLE_LINALG_H
 #define BVHAR_ORACLE_LINALG_H
 
@@ -28,10 +28,25 @@ struct Mat {
 };
 typedef std::vector<double> Vec;
 
+// Optional BLAS / LAPACK back end for the LARGE dense products and factorisations of the reference-faithful formulation
+// (the 1000 x 1000 H'H product and LLT of varsv_ht, the Kronecker-design Gram): the reference runs them through Eigen's
+// vectorised kernels, so timing the oracle with scalar loops would flatter the GPU.  bench.py's reference arm points these
+// at the OpenBLAS that ships inside SciPy (oracle_use_blas, bvhar_oracle.cpp); the tests never do, so that the golden
+// trajectories do not depend on a third-party library's rounding.
+typedef void (*cblas_dgemm_fn)(int order, int transa, int transb, int m, int n, int k, double alpha, const double* a, int lda,
+                               const double* b, int ldb, double beta, double* c, int ldc);
+typedef void (*dpotrf_fn)(const char* uplo, const int* n, double* a, const int* lda, int* info);
+inline cblas_dgemm_fn& blas_dgemm() { static cblas_dgemm_fn f = nullptr; return f; }
+inline dpotrf_fn& lapack_dpotrf() { static dpotrf_fn f = nullptr; return f; }
+
 // C (m x n) = A^T B, A (k x m), B (k x n); cache-blocked over k, inner loop contiguous in k.
 inline void gemm_tn(const Mat& A, const Mat& B, Mat& C) {
   const int m = A.c, n = B.c, k = A.r;
   C = Mat(m, n);
+  if (blas_dgemm() && (double)m * n * k >= 262144.0) {  // CblasColMajor = 102, CblasTrans = 112, CblasNoTrans = 111
+    blas_dgemm()(102, 112, 111, m, n, k, 1.0, A.data(), k, B.data(), k, 0.0, C.data(), m);
+    return;
+  }
   const int KB = 256;
   for (int k0 = 0; k0 < k; k0 += KB) {
     const int k1 = std::min(k, k0 + KB);
@@ -51,6 +66,10 @@ inline void gemm_tn(const Mat& A, const Mat& B, Mat& C) {
 inline void gemm_nn(const Mat& A, const Mat& B, Mat& C) {
   const int m = A.r, n = B.c, k = A.c;
   C = Mat(m, n);
+  if (blas_dgemm() && (double)m * n * k >= 262144.0) {
+    blas_dgemm()(102, 111, 111, m, n, k, 1.0, A.data(), m, B.data(), k, 0.0, C.data(), m);
+    return;
+  }
   for (int j = 0; j < n; ++j) {
     double* c = C.col(j);
     for (int t = 0; t < k; ++t) {
@@ -68,6 +87,11 @@ inline void gemm_nn(const Mat& A, const Mat& B, Mat& C) {
 inline bool chol_lower(Mat& P) {
   const int d = P.r;
   bool ok = true;
+  if (lapack_dpotrf() && d >= 96) {
+    int info = 0;
+    lapack_dpotrf()("L", &d, P.data(), &d, &info);
+    return info == 0;
+  }
   for (int j = 0; j < d; ++j) {
     double* cj = P.col(j);
     for (int t = 0; t < j; ++t) {

@@ -3,7 +3,7 @@
 // File format (both ways): repeated { int32 name_len, name bytes, int64 rows, int64 cols, rows*cols doubles }.
 #include <cstdio>
 #include <cstring>
-#include <bvhar_b200/forecast_run.hpp>
+#include <bvhar_b200/outforecast_run.hpp>
 
 using namespace bvhar_b200;
 
@@ -73,6 +73,41 @@ int main(int argc, char** argv) {
         std::fwrite(&dens[c].rows, sizeof(int64_t), 1, f); std::fwrite(&dens[c].cols, sizeof(int64_t), 1, f);
         std::fwrite(dens[c].data.data(), sizeof(double), dens[c].data.size(), f);
       }
+    }
+    if (all.count("outforecast")) {
+      // (vhar, expanding, lag | week, month, step, stable, level, get_lpl, sparse): the out-of-sample runners of
+      // include/bvhar_b200/outforecast_run.hpp on the fit_record stored in the problem file ("rec<c>.<name>")
+      const Matrix& of = all.at("outforecast");
+      const bool vhar = of.data[0] != 0, expanding = of.data[1] != 0, stable = of.data[5] != 0, get_lpl = of.data[7] != 0, sparse = of.data[8] != 0;
+      const int a0 = (int)of.data[2], a1 = (int)of.data[3], step = (int)of.data[4];
+      const double level = of.data[6];
+      std::vector<Records> fit_record(chains);
+      for (int c = 0; c < chains; ++c) {
+        const std::string pre = "rec" + std::to_string(c) + ".";
+        for (auto& kv : all)
+          if (kv.first.compare(0, pre.size(), pre) == 0) fit_record[c][kv.first.substr(pre.size())] = kv.second;
+      }
+      std::vector<uint32_t> sc(all.at("seed_window_chain").data.begin(), all.at("seed_window_chain").data.end());
+      std::vector<uint32_t> sf(all.at("seed_forecast").data.begin(), all.at("seed_forecast").data.end());
+      OutForecast res;
+#define OUT_ARGS chains, iters, burn, thin, sparse, level, fit_record, sub(all, "cov."), sub(all, "prior."), sub(all, "icpt."), init, prior, \
+                 ints(all.at("grp_id")), ints(all.at("own_id")), ints(all.at("cross_id")), ints(all.at("grp_mat")), mean, stable, step,     \
+                 all.at("y_test"), get_lpl, sc, sf, false, 1
+#define RUN_OUT(SV, GG)                                                                                                        \
+      if (vhar && expanding) res = McmcVharforecastRun<Window::Expand, SV, GG>(all.at("y_train"), a0, a1, OUT_ARGS).returnForecast(); \
+      else if (vhar) res = McmcVharforecastRun<Window::Roll, SV, GG>(all.at("y_train"), a0, a1, OUT_ARGS).returnForecast();           \
+      else if (expanding) res = McmcVarforecastRun<Window::Expand, SV, GG>(all.at("y_train"), a0, OUT_ARGS).returnForecast();        \
+      else res = McmcVarforecastRun<Window::Roll, SV, GG>(all.at("y_train"), a0, OUT_ARGS).returnForecast()
+      if (sv && ggl) { RUN_OUT(true, true); } else if (sv) { RUN_OUT(true, false); } else if (ggl) { RUN_OUT(false, true); } else { RUN_OUT(false, false); }
+      auto put = [&](const std::string& name, const Matrix& m) {
+        const int32_t nl = (int32_t)name.size();
+        std::fwrite(&nl, sizeof nl, 1, f); std::fwrite(name.data(), 1, nl, f);
+        std::fwrite(&m.rows, sizeof(int64_t), 1, f); std::fwrite(&m.cols, sizeof(int64_t), 1, f);
+        std::fwrite(m.data.data(), sizeof(double), m.data.size(), f);
+      };
+      for (size_t w = 0; w < res.forecast.size(); ++w)
+        for (int c = 0; c < chains; ++c) put("o" + std::to_string(w) + "." + std::to_string(c), res.forecast[w][c]);
+      if (res.has_lpl) put("lpl", res.lpl);
     }
     std::fclose(f);
     return 0;

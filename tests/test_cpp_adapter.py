@@ -132,3 +132,61 @@ def test_cpp_forecast_adapter_matches_python_adapter(tmp_path, vhar, sv, stable)
         pytest.skip(str(e))
     for c in range(2):
         assert np.array_equal(got[f"f{c}"], dens[c])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("vhar,sv,expanding,stable,level", [(False, True, False, False, 0.0), (False, False, True, False, 0.0),
+                                                            (True, True, True, False, 0.0), (True, False, False, False, 0.3),
+                                                            (False, True, False, True, 0.0)])
+def test_cpp_outforecast_runners_match_python_model(tmp_path, vhar, sv, expanding, stable, level):
+    """bvhar_b200::McmcVarforecastRun / McmcVharforecastRun<Roll | Expand, ...> (include/bvhar_b200/outforecast_run.hpp, the
+    mirrors of forecaster.h:966-1121) against `model.py::_outforecast_draws` on the same fit, seeds and test rows: the
+    forecast draws of every (window, chain) and the lpl table, bit for bit."""
+    _build()
+    from bvhar_b200 import _spec as sp
+    from bvhar_b200.model import VarBayes, VharBayes
+    y = pr.simulate_series(64, 3, 4242)
+    train, test = y[:58], y[58:]
+    step, chains, iters, burn = 2, 2, 12, 4
+    cov = sp.SvConfig() if sv else sp.LdltConfig()
+    if vhar:
+        m = VharBayes(train, 2, 4, chains, iters, burn, 1, sp.HorseshoeConfig(), cov, seed=5)
+    else:
+        m = VarBayes(train, 2, chains, iters, burn, 1, sp.HorseshoeConfig(), cov, seed=5)
+    m.fit()
+    n_hor = test.shape[0] - step + 1
+    fixed = {(chains, n_hor): np.arange(100, 100 + chains * n_hor).reshape(chains, n_hor), (chains,): np.arange(7, 7 + chains)}
+    m._seeds = lambda *shape: fixed[shape]
+    sparse_arg = level if level > 0 else False
+    try:
+        per_window, lpls = m._outforecast_draws(step, test, expanding, stable, sparse_arg, True)
+    except ValueError as e:
+        pytest.skip(str(e))
+    # the same job through the C++ runner: the model's own constructor arguments and fit records
+    arrays = {"meta": [chains, iters, burn, 1, int(m._prior_type), 1, int(sv), 1],
+              "x": m.design_, "y": m.response_, "y_train": train, "y_test": test,
+              "grp_id": m._group_id, "own_id": m._own_id, "cross_id": m._cross_id, "grp_mat": np.asarray(m.group_).reshape(-1, order="F"),
+              "seed_chain": np.arange(1, chains + 1), "seed_window_chain": fixed[(chains, n_hor)].T.reshape(-1), "seed_forecast": fixed[(chains,)],
+              "outforecast": [int(vhar), int(expanding), 2, 4 if vhar else 0, step, int(stable), level, 1, 0]}
+    for pre, dic in (("cov.", m.cov_spec_.to_dict()), ("prior.", m.spec_.to_dict()), ("icpt.", m.intercept_spec_.to_dict())):
+        for k2, v in dic.items():
+            v = np.asarray(v, dtype=np.float64)
+            arrays[pre + k2] = v if v.ndim == 2 else v.reshape(-1)
+    for c, ini in enumerate(m.init_):
+        for k2, v in ini.items():
+            v = np.asarray(v, dtype=np.float64)
+            arrays[f"init{c}.{k2}"] = v if v.ndim == 2 else v.reshape(-1)
+    for c in range(chains):
+        for nm, arr in m.param_.items():
+            arrays[f"rec{c}.{nm}"] = np.asarray(arr[c])
+    path = os.path.join(str(tmp_path), "problem.bin")
+    _write(path, arrays)
+    out = os.path.join(str(tmp_path), "out.bin")
+    r = subprocess.run([EXE, path, out], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    got = _read(out)
+    k = 3
+    for w in range(n_hor):
+        mine = np.concatenate([got[f"o{w}.{c}"].reshape(-1, k) for c in range(chains)], axis=0)
+        assert np.array_equal(mine, per_window[w]), (w, np.abs(mine - per_window[w]).max() if mine.shape == per_window[w].shape else (mine.shape, per_window[w].shape))
+    assert np.array_equal(got["lpl"], np.stack(lpls))
