@@ -16,6 +16,8 @@
 #include "kernels.h"
 #include "rng.cuh"
 #include "block_linalg.cuh"
+#include <algorithm>
+#include <cstdlib>
 
 namespace bvhar {
 
@@ -250,10 +252,12 @@ __constant__ double c_ksc_v[7] = {5.79596, 2.61369, 5.17950, 0.16735, 0.64009, 0
 // Same thread mapping as sv_prep (row of L in registers); the unit's residual rows are staged in smem.
 __constant__ double c_ksc_mm[7] = {-10.12999 - 1.2704, -3.97281 - 1.2704, -8.56686 - 1.2704, 2.77786 - 1.2704,
                                    0.61942 - 1.2704, 1.79518 - 1.2704, -1.08819 - 1.2704};
+constexpr float MIX_MARGIN = 2e-4f;
 template <int KMAX>
 __global__ void __launch_bounds__(256, (KMAX <= 32 ? 2 : 1)) sv_mix_kernel(const Dims D, const DevPtrs P) {
   extern __shared__ __align__(16) double sm[];  // [SVP_TT][blockDim.x span of Z columns]
   __shared__ double s_h2v[7], s_lw[7], s_iv[7];
+  __shared__ float s_lwf[7];
   const int w = blockIdx.z;
   const int n = P.win_n[w];
   const int t0 = blockIdx.y * SVP_TT;
@@ -264,6 +268,7 @@ __global__ void __launch_bounds__(256, (KMAX <= 32 ? 2 : 1)) sv_mix_kernel(const
     s_h2v[threadIdx.x] = 0.5 / v;
     s_iv[threadIdx.x] = 1.0 / v;
     s_lw[threadIdx.x] = c_ksc_p[threadIdx.x] / (sqrt(v) * sqrt(2 * 3.14159265358979323846));
+    s_lwf[threadIdx.x] = (float)s_lw[threadIdx.x];
   }
   const int tn = min(SVP_TT, n - t0);
   const int mbase = blockIdx.x * blockDim.x;
@@ -303,23 +308,54 @@ __global__ void __launch_bounds__(256, (KMAX <= 32 ? 2 : 1)) sv_mix_kernel(const
     if (!(t & 1) || tt == 0) rng.uniform_pair(ST_SV_MIX_U, (uint32_t)i * nh + ((uint32_t)t >> 1), 0, ua, ub);
     const double uni = (t & 1) ? ub : ua;
     const double r = ystar - h;
-    double pdf[7], tot = 0.0;
+    // The indicator only needs to know on which side of each cumulative weight u * tot falls.  A single-precision pass
+    // (7 MUFU exponentials instead of 7 fp64 ones: the fp64 pipe was this kernel's bound) decides that whenever u * tot is
+    // further than MIX_MARGIN * tot from every boundary - its weights are within 2e-5 relative of the fp64 ones (the
+    // exponent a is formed in fp64 and rounded once: 2^-24 |a|, |a| < 88; plus ex2.approx) - and only the rare ambiguous element (~0.1 %), or one whose
+    // weights underflow in fp32, takes the fp64 evaluation below.  The result is the fp64 decision in every case.
+    int s;
+    bool decided = false;
+    {
+      const float uf = (float)uni;
+      float pf[7], totf = 0.f;
 #pragma unroll
-    for (int cc = 0; cc < 7; ++cc) {
-      const double e = r - c_ksc_mm[cc];
-      pdf[cc] = s_lw[cc] * exp(-e * e * s_h2v[cc]);
-      tot += pdf[cc];
-    }
-    const double target = uni * tot;  // u < cum / tot  <=>  u * tot < cum
-    double cum = 0.0;
-    int cnt = 0;
+      for (int cc = 0; cc < 7; ++cc) {
+        const double e = r - c_ksc_mm[cc];
+        pf[cc] = s_lwf[cc] * __expf((float)(-e * e * s_h2v[cc]));  // exponent formed in fp64: its fp32 rounding is < 88 * 2^-24
+        totf += pf[cc];
+      }
+      const float tgt = uf * totf, mar = MIX_MARGIN * totf;
+      float cumf = 0.f;
+      int cnt = 0;
+      bool clear = totf > 1e-30f;
 #pragma unroll
-    for (int cc = 0; cc < 7; ++cc) {
-      cum += pdf[cc];
-      if (target < cum) ++cnt;
+      for (int cc = 0; cc < 6; ++cc) {  // the last boundary (cum = tot) is never ambiguous: u < 1
+        cumf += pf[cc];
+        clear = clear && fabsf(tgt - cumf) > mar;
+        if (tgt < cumf) ++cnt;
+      }
+      s = 6 - cnt;  // = 7 - (cnt + 1): the seventh cumulative weight always exceeds u * tot
+      decided = clear;
     }
-    int s = 7 - cnt;  // draw.h:468
-    if (s > 6) s = 6;
+    if (!decided) {
+      double pdf[7], tot = 0.0;
+#pragma unroll
+      for (int cc = 0; cc < 7; ++cc) {
+        const double e = r - c_ksc_mm[cc];
+        pdf[cc] = s_lw[cc] * exp(-e * e * s_h2v[cc]);
+        tot += pdf[cc];
+      }
+      const double target = uni * tot;  // u < cum / tot  <=>  u * tot < cum
+      double cum = 0.0;
+      int cnt = 0;
+#pragma unroll
+      for (int cc = 0; cc < 7; ++cc) {
+        cum += pdf[cc];
+        if (target < cum) ++cnt;
+      }
+      s = 7 - cnt;  // draw.h:468
+      if (s > 6) s = 6;
+    }
     const double iv = s_iv[s];
     P.Dinv[at] = iv;
     P.YLD[at] = (ystar - c_ksc_mm[s]) * iv;
@@ -521,6 +557,206 @@ __global__ void __launch_bounds__(128) sv_finish_kernel(const Dims D, const DevP
   if (threadIdx.x == 0 && bad) atomicOr(&P.flags[u], 4);
 }
 
+// ------------------------------------------------------------------ warp-tile forms of updateSv / the mixture step
+// Both elementwise SV kernels start from a small per-unit matrix product over the series index: (Y L')_{t,i} for
+// updateSv, (Z L')_{t,i} for the mixture indicators.  One warp owns an 8 (time) x k (series) tile of one unit and forms
+// it on the fp64 tensor pipe: DMMA m8n8k4 with A = the tile of Y / Z (rows = time, read straight from global memory:
+// every 32-byte sector fetched is fully used), B = L' fragments from a shared-memory copy of the unit's L (k-steps above
+// the diagonal block are skipped: L is lower triangular).  The accumulator fragment leaves every lane with the two
+// neighbouring series (8 nt + 2 fc, + 1) of time point t0 + fr, on which the elementwise work then runs with two
+// independent dependency chains per lane and no per-thread copy of a row of L (the thread-per-series versions kept 24-128
+// doubles of L in registers: 128 registers, 25 % occupancy, latency-bound at 0.58 / 0.26 ms for C3).
+constexpr int SVW_WARPS = 8;
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+// the fp64 evaluation of the indicator (draw.h:458-468), out of line: it is the rare path and must not cost the common
+// one its registers
+__device__ __noinline__ int ksc_indicator_fp64(double r, double uni, const double* lw, const double* h2v) {
+  double pdf[7], tot = 0.0;
+#pragma unroll
+  for (int cc = 0; cc < 7; ++cc) {
+    const double e = r - c_ksc_mm[cc];
+    pdf[cc] = lw[cc] * exp(-e * e * h2v[cc]);
+    tot += pdf[cc];
+  }
+  const double target = uni * tot;  // u < cum / tot  <=>  u * tot < cum
+  double cum = 0.0;
+  int cnt = 0;
+#pragma unroll
+  for (int cc = 0; cc < 7; ++cc) {
+    cum += pdf[cc];
+    if (target < cum) ++cnt;
+  }
+  const int s = 7 - cnt;  // draw.h:468
+  return s > 6 ? 6 : s;
+}
+// KS = ceil(k / 4) rounded up to the template bucket; MIX = false: updateSv (A = Y), true: mixture indicators (A = Z)
+template <int KS, bool MIX>
+__global__ void __launch_bounds__(SVW_WARPS * 32, 3) sv_tile_kernel(const Dims D, const DevPtrs P, const int tiles_per_cta) {
+  extern __shared__ __align__(16) double sm[];  // L of the unit, row pitch ldl (odd)
+  __shared__ double s_h2v[7], s_iv[7];
+  __shared__ float s_lwf[7];
+  __shared__ double s_lw[7];
+  const int u = blockIdx.x, w = u / D.C, c = u - w * D.C;
+  const int n = P.win_n[w], row0 = P.win_row0[w];
+  const int k = D.k, ldl = k | 1;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, fr = lane >> 2, fc = lane & 3;
+  for (int e = tid; e < k * k; e += blockDim.x) {
+    const int i = e / k, m = e - i * k;
+    sm[i * ldl + m] = P.L[(size_t)u * k * k + e];
+  }
+  if (MIX && tid < 7) {
+    const double v = c_ksc_v[tid];
+    s_h2v[tid] = 0.5 / v;
+    s_iv[tid] = 1.0 / v;
+    s_lw[tid] = c_ksc_p[tid] / (sqrt(v) * sqrt(2 * 3.14159265358979323846));
+    s_lwf[tid] = (float)s_lw[tid];
+  }
+  __syncthreads();
+  const int ntt = (n + 7) >> 3;
+  const int tile_lo = blockIdx.y * tiles_per_cta, tile_hi = min(ntt, tile_lo + tiles_per_cta);
+  const long long ubase = P.win_off[w] + (long long)c * k;
+  const Philox rng(P.seeds[u], (uint32_t)(D.ubase + u), *P.iter);
+  const uint32_t nh = (uint32_t)((n + 1) / 2);
+  const int nnt = (k + 7) >> 3;
+  const bool vec2 = ((k & 1) == 0);  // series pairs are 16-byte aligned in the [t][m] arrays (ldM and the window offsets are even)
+  for (int tile = tile_lo + warp; tile < tile_hi; tile += SVW_WARPS) {
+    const int t = tile * 8 + fr;
+    const bool tok = t < n;
+    double af[KS];
+    {
+      const double* arow = MIX ? P.Z + ubase + (long long)t * D.ldM : P.Y + (size_t)(row0 + t) * k;
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) {
+        const int m = 4 * ks + fc;
+        af[ks] = (tok && m < k) ? __ldg(arow + m) : 0.0;
+      }
+    }
+    for (int nt = 0; nt < nnt; ++nt) {
+      double a0 = 0.0, a1 = 0.0;
+      const int brow = min(8 * nt + fr, k - 1);
+      const double* bl = sm + brow * ldl;
+      const bool bok = 8 * nt + fr < k;
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) {
+        if (4 * ks <= 8 * nt + 7) {  // warp-uniform: columns beyond the diagonal block of L are zero
+          const int m = 4 * ks + fc;
+          const double b = (bok && m < k) ? bl[m] : 0.0;
+          dmma884(a0, a1, af[ks], b);
+        }
+      }
+      const int i0 = 8 * nt + 2 * fc;  // this lane's series i0, i0 + 1 at time t
+      const long long at = ubase + (long long)t * D.ldM + i0;
+      if (!MIX) {
+        // updateSv (tri.h:409): Dinv = exp(-h), YLD = (Y L')_{t,i} * Dinv
+        if (tok && i0 < k) {
+          if (vec2 && i0 + 1 < k) {
+            const double2 h = *reinterpret_cast<const double2*>(P.H + at);
+            const double d0 = exp(-h.x), d1 = exp(-h.y);
+            *reinterpret_cast<double2*>(P.Dinv + at) = make_double2(d0, d1);
+            *reinterpret_cast<double2*>(P.YLD + at) = make_double2(a0 * d0, a1 * d1);
+          } else {
+            const double d0 = exp(-P.H[at]);
+            P.Dinv[at] = d0; P.YLD[at] = a0 * d0;
+            if (i0 + 1 < k) { const double d1 = exp(-P.H[at + 1]); P.Dinv[at + 1] = d1; P.YLD[at + 1] = a1 * d1; }
+          }
+        }
+        continue;
+      }
+      // ---- mixture indicators (draw.h:458-468).  Uniforms: Philox pair (series i, t >> 1) holds times 2p, 2p + 1; the lane
+      // draws the pair of series i0 + (fr & 1) and swaps the half it does not need with the lane of the other parity of fr
+      double ua, ub;
+      {
+        const int sc = min(i0 + (fr & 1), k - 1);
+        rng.uniform_pair(ST_SV_MIX_U, (uint32_t)sc * nh + ((uint32_t)t >> 1), 0, ua, ub);
+      }
+      const double send = (fr & 1) ? ua : ub;
+      const double recv = __shfl_xor_sync(0xffffffffu, send, 4);
+      const double un0 = (fr & 1) ? recv : ua;   // series i0:     even t -> own ua, odd t -> partner's ub
+      const double un1 = (fr & 1) ? ub : recv;   // series i0 + 1: even t -> partner's ua, odd t -> own ub
+      double hh0 = 0.0, hh1 = 0.0;
+      if (tok && i0 < k) {
+        if (vec2 && i0 + 1 < k) { const double2 h = *reinterpret_cast<const double2*>(P.H + at); hh0 = h.x; hh1 = h.y; }
+        else { hh0 = P.H[at]; if (i0 + 1 < k) hh1 = P.H[at + 1]; }
+      }
+      double o_iv[2], o_b[2];
+#pragma unroll
+      for (int h2 = 0; h2 < 2; ++h2) {
+        const double uu = h2 ? a1 : a0, hcur = h2 ? hh1 : hh0, uni = h2 ? un1 : un0;
+        const double ystar = log(uu * uu + .0001);  // tri.h:401-402
+        const double r = ystar - hcur;
+        // The indicator only needs the side of u * tot relative to each cumulative weight.  A single-precision pass (exponent
+        // formed in fp64 and rounded once, 7 MUFU exponentials: weights within 2e-5 relative of the fp64 ones) decides it
+        // whenever u * tot is further than MIX_MARGIN * tot from every boundary; the rare ambiguous element (~0.1 %), or one
+        // whose weights underflow in fp32, takes the fp64 evaluation.  The result is the fp64 decision in every case.
+        int sidx;
+        bool decided;
+        {
+          float pf[7], totf = 0.f;
+#pragma unroll
+          for (int cc = 0; cc < 7; ++cc) {
+            const double e = r - c_ksc_mm[cc];
+            pf[cc] = s_lwf[cc] * __expf((float)(-e * e * s_h2v[cc]));
+            totf += pf[cc];
+          }
+          const float tgt = (float)uni * totf, mar = MIX_MARGIN * totf;
+          float cumf = 0.f;
+          int cnt = 0;
+          bool clear = totf > 1e-30f;
+#pragma unroll
+          for (int cc = 0; cc < 6; ++cc) {  // the last boundary (cum = tot) is never ambiguous: u < 1
+            cumf += pf[cc];
+            clear = clear && fabsf(tgt - cumf) > mar;
+            if (tgt < cumf) ++cnt;
+          }
+          sidx = 6 - cnt;
+          decided = clear;
+        }
+        if (!decided) sidx = ksc_indicator_fp64(r, uni, s_lw, s_h2v);
+        o_iv[h2] = s_iv[sidx];
+        o_b[h2] = (ystar - c_ksc_mm[sidx]) * s_iv[sidx];
+      }
+      if (tok && i0 < k) {  // tridiagonal system's diagonal term 1 / v_s and right-hand-side term (y* - m_s) / v_s
+        if (vec2 && i0 + 1 < k) {
+          *reinterpret_cast<double2*>(P.Dinv + at) = make_double2(o_iv[0], o_iv[1]);
+          *reinterpret_cast<double2*>(P.YLD + at) = make_double2(o_b[0], o_b[1]);
+        } else {
+          P.Dinv[at] = o_iv[0]; P.YLD[at] = o_b[0];
+          if (i0 + 1 < k) { P.Dinv[at + 1] = o_iv[1]; P.YLD[at + 1] = o_b[1]; }
+        }
+      }
+    }
+  }
+}
+template <bool MIX>
+static cudaError_t launch_sv_tile(const Dims& D, const DevPtrs& P, cudaStream_t st) {
+  const int k = D.k, ntt = (D.nmax + 7) / 8;
+  // enough CTAs to fill the machine a few times over, each warp keeping >= 2 time tiles
+  int ysplit = std::max(1, std::min((ntt + 2 * SVW_WARPS - 1) / (2 * SVW_WARPS), (148 * 8 + D.U - 1) / D.U));
+  const int tiles_per_cta = (ntt + ysplit - 1) / ysplit;
+  ysplit = (ntt + tiles_per_cta - 1) / tiles_per_cta;
+  const dim3 grid(D.U, ysplit);
+  const size_t smem = (size_t)k * (k | 1) * sizeof(double);
+#define BV_SVT(KSV)                                                                                             \
+  do {                                                                                                          \
+    if (smem > 48 * 1024) cudaFuncSetAttribute(sv_tile_kernel<KSV, MIX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    sv_tile_kernel<KSV, MIX><<<grid, SVW_WARPS * 32, smem, st>>>(D, P, tiles_per_cta);                            \
+  } while (0)
+  const int ks = (k + 3) / 4;
+  if (ks <= 2) BV_SVT(2);
+  else if (ks <= 4) BV_SVT(4);
+  else if (ks <= 5) BV_SVT(5);
+  else if (ks <= 6) BV_SVT(6);
+  else if (ks <= 8) BV_SVT(8);
+  else if (ks <= 13) BV_SVT(13);
+  else if (ks <= 16) BV_SVT(16);
+  else if (ks <= 26) BV_SVT(26);
+  else BV_SVT(32);
+#undef BV_SVT
+  return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------ records
 // updateRecords: row `rec_row` of every record matrix <- current state (config.h:850-857, 955-965,
 // 796-804 and the prior records config.h:1071-1076, 1122-1125, 1183-1188, 1229-1233).
@@ -625,6 +861,7 @@ cudaError_t launch_draw_coef_batched(long long batch, int d, const double* Pp, c
   return cudaGetLastError();
 }
 cudaError_t launch_sv_prep(const Dims& D, const DevPtrs& P, cudaStream_t st) {
+  if (D.k <= 128 && getenv("BVHAR_SV_THREAD_KERNELS") == nullptr) return launch_sv_tile<false>(D, P, st);
   const dim3 grid((D.M + 255) / 256, (D.nmax + SVP_TT - 1) / SVP_TT, D.W);
   const size_t smem = (size_t)SVP_TT * D.k * sizeof(double);
   if (D.k <= 8) sv_prep_kernel<8><<<grid, 256, smem, st>>>(D, P);
@@ -640,6 +877,7 @@ cudaError_t launch_sv_state(int part, const Dims& D, const DevPtrs& P, cudaStrea
     sv_normals_kernel<<<dim3((D.M + 255) / 256, (D.nmax + 1) / 2, D.W), 256, 0, st>>>(D, P);
     return cudaGetLastError();
   }
+  if (part == 0 && D.k <= 128 && getenv("BVHAR_SV_THREAD_KERNELS") == nullptr) return launch_sv_tile<true>(D, P, st);
   if (part == 0) {
     const dim3 grid((D.M + 255) / 256, (D.nmax + SVP_TT - 1) / SVP_TT, D.W);
     const size_t smem = (size_t)SVP_TT * (256 + 2 * D.k) * sizeof(double);
