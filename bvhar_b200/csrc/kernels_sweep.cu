@@ -391,7 +391,7 @@ __global__ void __launch_bounds__(256) sv_normals_kernel(const Dims D, const Dev
 //            the divisions and w_t = 1 / sqrt(q_t) are then independent per t and pipeline freely;
 //   forward  y_t = alpha_t + beta_t y_{t-1},   alpha_t = b_t w_t,  beta_t = isig w_{t-1} w_t;
 //   backward x_t = gamma_t + delta_t x_{t+1},  gamma_t = (y_t + z_t) w_t,  delta_t = isig w_t^2.
-constexpr int SVS_B = 8;
+constexpr int SVS_B = 16;  // time steps per block: 3 x 16 independent loads in flight per thread (the kernel runs ~140 threads per SM: latency-bound)
 __global__ void __launch_bounds__(128) sv_solve_kernel(const Dims D, const DevPtrs P) {
   const int w = blockIdx.y;
   const int m = blockIdx.x * blockDim.x + threadIdx.x;
@@ -440,7 +440,10 @@ __global__ void __launch_bounds__(128) sv_solve_kernel(const Dims D, const DevPt
     }
     double wv[SVS_B];
 #pragma unroll
-    for (int r = 0; r < SVS_B; ++r) wv[r] = rsqrt(Nr[r] / Dr[r]);  // independent: pipelined
+    for (int r = 0; r < SVS_B; ++r) {  // w = 1 / sqrt(N / D), without the division unless N D overflows; independent: pipelined
+      const double nd = Nr[r] * Dr[r];
+      wv[r] = nd < 1e300 ? Dr[r] * rsqrt(nd) : rsqrt(Nr[r] / Dr[r]);
+    }
     Nc = Nr[SVS_B - 1] / Dr[SVS_B - 1];  // re-normalise (q itself) for the next block
     Dc = 1.0;
 #pragma unroll
