@@ -361,6 +361,7 @@ def load_library():
                                        C.POINTER(C.c_int32)]
     L.bvhar_cuda_fit_record_names.argtypes = [vp, C.c_char_p, C.c_int64]
     L.bvhar_cuda_fit_record_mean.argtypes = [vp, C.c_char_p, c_dp, C.c_int64]
+    L.bvhar_cuda_fit_record_summary.argtypes = [vp, C.c_char_p, C.c_double, c_dp, C.c_int64]
     L.bvhar_cuda_fit_state_len.argtypes = [vp, C.c_char_p, C.POINTER(C.c_int64)]
     L.bvhar_cuda_fit_get_state.argtypes = [vp, C.c_int, C.c_int, C.c_char_p, c_dp, C.c_int64]
     L.bvhar_cuda_fit_set_state.argtypes = [vp, C.c_int, C.c_int, C.c_char_p, c_dp, C.c_int64]

@@ -170,6 +170,18 @@ class CudaFit:
         check(self.L.bvhar_cuda_fit_record_mean(self._h, name.encode(), out.ctypes.data_as(c_dp), c.value))
         return out
 
+    SUMMARY_COLUMNS = ("mean", "sd", "lower", "median", "upper", "rhat", "ess", "pip")
+
+    def record_summary(self, name: str, level: float = .05) -> Dict[str, np.ndarray]:
+        """Posterior summaries of each column over all chains and kept draws, reduced on the device
+        (``bvhar_cuda_fit_record_summary``): mean, sd, the level / 2, 1 / 2 and 1 - level / 2 quantiles, split-R-hat, ESS and the
+        share of non-zero entries (the PIP of the SAVS records)."""
+        r, c = C.c_int64(), C.c_int64()
+        check(self.L.bvhar_cuda_fit_record_dims(self._h, name.encode(), C.byref(r), C.byref(c)))
+        out = np.empty((c.value, 8))
+        check(self.L.bvhar_cuda_fit_record_summary(self._h, name.encode(), float(level), out.ctypes.data_as(c_dp), c.value))
+        return {nm: out[:, i].copy() for i, nm in enumerate(self.SUMMARY_COLUMNS)}
+
     def records(self, window: int = 0, chain: int = 0) -> Dict[str, np.ndarray]:
         return {nm: self.record(nm, window, chain) for nm in self.record_names()}
 

@@ -518,11 +518,27 @@ int build(const bvhar_fit_desc* d, bvhar_fit** out) {
   // 10 MB vector costs more in page faults than its upload; untouched slots are zero-filled on the device)
   for (auto& v : hhG) v.assign((size_t)U * G, 0.0);
   for (auto& v : hhq) v.assign((size_t)U * q, 0.0);
-  for (int w = 0; w < D.W; ++w)
-    for (int c = 0; c < D.C; ++c) {
+  {  // which N-long slots the prior initialises (allocated up front: the unit loop below runs on several threads)
+    const bvhar_chain_init& in0 = d->init[0];
+    auto useN = [&](int slot, const double* src) { if (src) hhN[slot].assign((size_t)U * N, 0.0); };
+    switch (D.prior) {
+      case 2: useN(0, in0.coef_dummy); useN(1, in0.coef_slab); break;
+      case 3: case 5: case 6: case 7: useN(0, in0.local_sparsity); break;
+      default: break;
+    }
+  }
+  std::mutex err_mutex;
+  int err_code = 0;
+  std::string err_msg;
+  auto unit_fail = [&](int code, const std::string& msg) {
+    std::lock_guard<std::mutex> lk(err_mutex);
+    if (!err_code) { err_code = code; err_msg = msg; }
+    return code;
+  };
+  auto init_unit = [&](int w, int c) -> int {
       const int u = w * D.C + c;
       const bvhar_chain_init& in = d->init[c];
-      if (!in.init_coef || (q > 0 && !in.init_contem)) return fail(BVHAR_ERR_BAD_ARG, "init_coef / init_contem missing");
+      if (!in.init_coef || (q > 0 && !in.init_contem)) return unit_fail(BVHAR_ERR_BAD_ARG, "init_coef / init_contem missing");
       for (int j = 0; j < k; ++j)
         for (int a = 0; a < dd; ++a) {
           const double v = in.init_coef[(size_t)j * dd + a];
@@ -537,29 +553,27 @@ int build(const bvhar_fit_desc* d, bvhar_fit** out) {
         for (int m = 0; m < i; ++m) hL[((size_t)u * k + i) * k + m] = in.init_contem[i * (i - 1) / 2 + m];
       }
       if (D.sv) {
-        if (!in.lvol_init || !in.lvol_sig) return fail(BVHAR_ERR_BAD_ARG, "lvol_init / lvol_sig missing");
+        if (!in.lvol_init || !in.lvol_sig) return unit_fail(BVHAR_ERR_BAD_ARG, "lvol_init / lvol_sig missing");
         const bool rep = d->lvol_from_init || !in.lvol;
-        if (!rep && F->win_n[w] != F->win_n[0]) return fail(BVHAR_ERR_BAD_ARG, "lvol inits need equal window lengths (use lvol_from_init)");
-        if (c > 0 && rep == lvol_explicit) return fail(BVHAR_ERR_BAD_ARG, "either every chain or no chain carries an explicit 'lvol' init");
-        lvol_explicit = !rep;
+        if (!rep && F->win_n[w] != F->win_n[0]) return unit_fail(BVHAR_ERR_BAD_ARG, "lvol inits need equal window lengths (use lvol_from_init)");
+        if (rep == lvol_explicit) return unit_fail(BVHAR_ERR_BAD_ARG, "either every chain or no chain carries an explicit 'lvol' init");
         for (int i = 0; i < k; ++i) {
           hli[(size_t)u * k + i] = in.lvol_init[i];
           hls[(size_t)u * k + i] = in.lvol_sig[i];
         }
         // (the lvol blocks themselves are gathered below, in parallel)
       } else {
-        if (!in.init_diag) return fail(BVHAR_ERR_BAD_ARG, "init_diag missing");
+        if (!in.init_diag) return unit_fail(BVHAR_ERR_BAD_ARG, "init_diag missing");
         for (int i = 0; i < k; ++i) hdiag[(size_t)u * k + i] = in.init_diag[i];
       }
       double* s = &hhs[(size_t)u * HS_SLOTS];
       auto cpN = [&](int slot, const double* src) {
-        if (!src) return;
-        if (hhN[slot].empty()) hhN[slot].assign((size_t)U * N, 0.0);
+        if (!src || hhN[slot].empty()) return;
         std::copy(src, src + N, hhN[slot].begin() + (size_t)u * N);
       };
       auto cpG = [&](int slot, const double* src) { if (src) std::copy(src, src + G, hhG[slot].begin() + (size_t)u * G); };
       auto cpq = [&](int slot, const double* src) { if (src) std::copy(src, src + q, hhq[slot].begin() + (size_t)u * q); };
-      auto need = [&](const void* p, const char* nm) { return p ? 0 : fail(BVHAR_ERR_BAD_ARG, std::string("param_init lacks ") + nm); };
+      auto need = [&](const void* p, const char* nm) { return p ? 0 : unit_fail(BVHAR_ERR_BAD_ARG, std::string("param_init lacks ") + nm); };
       switch (D.prior) {
         case 4:  // tri.h:478-494
           s[HS_OWN_LAMBDA] = in.own_lambda; s[HS_CROSS_LAMBDA] = in.cross_lambda; s[HS_CONTEM_LAMBDA] = in.contem_lambda;
@@ -601,7 +615,30 @@ int build(const bvhar_fit_desc* d, bvhar_fit** out) {
           break;
         default: break;
       }
+      return 0;
+  };
+  if (D.sv) {  // explicit `lvol` blocks: every chain or none (decided by chain 0, checked per unit)
+    const bvhar_chain_init& in0 = d->init[0];
+    lvol_explicit = !(d->lvol_from_init || !in0.lvol);
+  }
+  {
+    // units write disjoint slices of the host staging vectors: a few host threads share the loop (22 ms on one thread for
+    // the 1 024 chains of C3: a third of create's time)
+    const int nthr = std::max(1, std::min(8, U / 64));
+    if (nthr == 1) {
+      for (int u = 0; u < U && !err_code; ++u) init_unit(u / D.C, u % D.C);
+    } else {
+      std::vector<std::thread> pool;
+      for (int th = 0; th < nthr; ++th)
+        pool.emplace_back([&, th] {
+          for (int u = th; u < U; u += nthr) {
+            if (init_unit(u / D.C, u % D.C)) return;
+          }
+        });
+      for (auto& t : pool) t.join();
     }
+    if (err_code) return fail(err_code, err_msg);
+  }
   lap("host init loops");
   if (D.sv && lvol_explicit) {  // gather the chains' n x k lvol blocks into one staging buffer, a few host threads
     const size_t blk = (size_t)k * F->win_n[0];
@@ -1188,6 +1225,28 @@ int bvhar_cuda_fit_record_mean(bvhar_fit* fit, const char* name, double* out, in
       CU(dm.alloc((size_t)r.cols));
       CU(launch_record_mean(*r.slot, D.U, fit->R.cap, r.cols, (int)kept, fit->thin, dm.p, 0));
       CU(cudaMemcpy(out, dm.p, sizeof(double) * r.cols, cudaMemcpyDeviceToHost));
+      return 0;
+    }
+  return fail(BVHAR_ERR_BAD_ARG, std::string("no record named ") + name);
+}
+// Posterior summaries of every column of one record over all units (= chains of a one-window fit) and kept draws, computed
+// on the device: out[col * 8 + {0..7}] = mean, sd, quantile(level / 2), median, quantile(1 - level / 2), split-R-hat, ESS, pip.
+int bvhar_cuda_fit_record_summary(bvhar_fit* fit, const char* name, double level, double* out, int64_t cols) {
+  if (!fit || !name || !out) return fail(BVHAR_ERR_BAD_ARG, "null argument");
+  if (!(level > 0.0 && level < 1.0)) return fail(BVHAR_ERR_BAD_ARG, "level must be in (0, 1)");
+  API_LOCK;
+  const Dims& D = fit->D;
+  CU(cudaSetDevice(fit->device));
+  CU(cudaStreamSynchronize(fit->st));
+  for (auto& r : fit->rec_order)
+    if (r.name == name) {
+      const int64_t kept = (fit->rec_filled + fit->thin - 1) / fit->thin;
+      if (cols != r.cols) return fail(BVHAR_ERR_BAD_ARG, "record dims mismatch");
+      if (kept == 0) return fail(BVHAR_ERR_BAD_ARG, "no draws recorded yet");
+      DevBuf<double> dm;
+      CU(dm.alloc((size_t)r.cols * 8));
+      CU(launch_record_summary(*r.slot, D.U, fit->R.cap, r.cols, (int)kept, fit->thin, level, dm.p, 0));
+      CU(cudaMemcpy(out, dm.p, sizeof(double) * r.cols * 8, cudaMemcpyDeviceToHost));
       return 0;
     }
   return fail(BVHAR_ERR_BAD_ARG, std::string("no record named ") + name);

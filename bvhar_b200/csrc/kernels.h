@@ -48,6 +48,8 @@ cudaError_t launch_prior(const Dims& D, const DevPtrs& P, const PriorConst& C, i
 // setup helpers (kernels_setup.cu)
 cudaError_t launch_scatter_lvol(const double* src, double* dst, int n, int M, int ldM, int nsrc, cudaStream_t st);
 cudaError_t launch_record_mean(const double* rec, int U, int cap, int cols, int rows, int thin, double* out, cudaStream_t st);
+// posterior summaries of one record (kernels_summary.cu): out[col][8] = mean, sd, q(level / 2), median, q(1 - level / 2), split-R-hat, ESS, pip
+cudaError_t launch_record_summary(const double* rec, int U, int cap, int cols, int S, int thin, double level, double* out, cudaStream_t st);
 cudaError_t launch_build_xx(const Dims& D, const DevPtrs& P, double* XX, cudaStream_t st);
 // stability filter (kernels_stable.cu)
 constexpr int STAB_MAX_SQUARINGS = 40;

@@ -69,6 +69,7 @@ class _AutoregBayes:
         self.param_names_ = None
         self.param_: Optional[Dict[str, np.ndarray]] = None
         self.sparse_coef_ = None
+        self.summary_ = None
         self.init_ = None
         self._fit_obj = None
 
@@ -168,9 +169,11 @@ class _AutoregBayes:
             f.close()
         return names, recs
 
-    def fit(self, devices=None):
+    def fit(self, devices=None, summaries: bool = False, level: float = .05):
         """Conduct MCMC on the GPU and compute posterior means.  ``devices``: optional list of CUDA ordinals to split
-        the chains over (one engine and one host thread per entry)."""
+        the chains over (one engine and one host thread per entry).  ``summaries=True`` also leaves, in ``summary_``, the
+        posterior summaries the reference's users compute on the returned draws (posterior::summarise_draws: mean, sd,
+        ``level`` credible interval, split-R-hat, ESS, plus the PIP), reduced on the device."""
         if devices is not None and len(devices) > 1:
             names, recs = self._fit_sharded(list(devices))
             k = self.n_features_in_
@@ -211,6 +214,8 @@ class _AutoregBayes:
             self.coef_ = np.concatenate([self.coef_, self.intercept_[None, :]], axis=0)
             if self.sparse_coef_ is not None:
                 self.sparse_coef_ = np.concatenate([self.sparse_coef_, fit.record_mean("c_sparse_record")[None, :]], axis=0)
+        if summaries:  # mean / sd / credible interval / split-R-hat / ESS / pip of every column, reduced on the device
+            self.summary_ = {nm.replace("_record", ""): fit.record_summary(nm, level) for nm in names if recs[nm].shape[2] > 0 and recs[nm].shape[1] > 3}
         fit.close()
         self.param_ = recs
         self.param_names_ = [nm.replace("_record", "") for nm in names]

@@ -234,6 +234,14 @@ int bvhar_cuda_fit_bind_record_sink(bvhar_fit* fit, const char* name, double* ho
 int bvhar_cuda_fit_record_mean(bvhar_fit* fit, const char* name, double* out, int64_t cols);
 /* Names of the records this fit exports, '\n'-separated, in the reference's list order. */
 int bvhar_cuda_fit_record_names(bvhar_fit* fit, char* buf, int64_t buflen);
+/* Posterior summaries of one record over all chains and kept draws, reduced on the device (SURVEY.md section 8(f) row 1;
+ * replaces the host passes of R/var-bayes.R:503-531 - colMeans, pip = colMeans(alpha_sparse != 0) - and of
+ * posterior::summarise_draws on the returned draws).  out: `cols` x 8 row-major:
+ * mean, sd, quantile(level / 2), median, quantile(1 - level / 2)  (type-7 / numpy "linear"),
+ * split-R-hat (BDA3; posterior::rhat_basic), ESS (posterior::ess_basic: Geyer initial positive + monotone sequence),
+ * pip (share of non-zero entries).  NaN entries (SAVS 0/0) are skipped by mean / sd / pip; a column holding any has NaN
+ * order statistics and diagnostics. */
+int bvhar_cuda_fit_record_summary(bvhar_fit* fit, const char* name, double level, double* out, int64_t cols);
 
 /* Current sampler state of one unit, by member name of McmcTriangular (triangular.h:188-224) and
  * the prior classes: coef_mat, contem_coef, chol_lower, latent_innov, sqrt_sv, prior_alpha_prec,

@@ -10,6 +10,8 @@ from bvhar_b200 import datasets
 from bvhar_b200._spec import (DlConfig, GdpConfig, HorseshoeConfig, InterceptConfig, LambdaConfig, LdltConfig, MinnesotaConfig,
                               NgConfig, SsvsConfig, SvConfig)
 from bvhar_b200.model import VarBayes, VharBayes
+from bvhar_b200._engine import CudaFit
+import problems as pr
 
 pytestmark = pytest.mark.gpu
 
@@ -232,3 +234,68 @@ def test_streamed_record_sinks_equal_bulk_fetch(thin):
         assert x.shape == y.shape and np.array_equal(x, y, equal_nan=True), nm
         assert np.array_equal(a.record_all(nm, pinned=False), y, equal_nan=True)  # second fetch: plain copy
     a.close(); b.close()
+
+
+def _np_summary(x, level):
+    """NumPy reference of the device summaries: x [chain, draw] of one parameter.  R-hat / ESS follow the formulas of
+    posterior::rhat_basic / ess_basic (split chains, biased autocovariances, Geyer's initial positive and monotone sequences)."""
+    U, S = x.shape
+    flat = x.reshape(-1)
+    out = {"mean": flat.mean(), "sd": flat.std(ddof=1), "lower": np.quantile(flat, level / 2), "median": np.quantile(flat, .5),
+           "upper": np.quantile(flat, 1 - level / 2), "pip": np.mean(flat != 0)}
+    n2 = S // 2
+    halves = np.concatenate([x[:, :n2], x[:, (S + 1) // 2:]], axis=1).reshape(U, 2, n2).reshape(2 * U, n2)  # chain c -> halves 2c, 2c + 1
+    m = halves.shape[0]
+    cm = halves.mean(axis=1); cv = halves.var(axis=1, ddof=1)
+    W = cv.mean()
+    var_plus = W * (n2 - 1) / n2 + (cm.var(ddof=1) if m > 1 else 0.0)
+    out["rhat"] = np.sqrt(var_plus / W)
+    yc = halves - cm[:, None]
+    acov = np.array([(yc[:, : n2 - t] * yc[:, t:]).sum(axis=1).mean() / n2 for t in range(n2)])
+    rho = np.zeros(n2 + 2)
+    t = 0
+    even, odd = 1.0, 1 - (W - acov[1]) / var_plus
+    rho[0], rho[1] = even, odd
+    while t < n2 - 5 and not np.isnan(even + odd) and even + odd > 0:
+        t += 2
+        even = 1 - (W - acov[t]) / var_plus
+        odd = 1 - (W - acov[t + 1]) / var_plus
+        if even + odd >= 0:
+            rho[t], rho[t + 1] = even, odd
+    max_t = t
+    if even > 0:
+        rho[max_t] = even
+    t = 0
+    while t <= max_t - 4:
+        t += 2
+        if rho[t] + rho[t + 1] > rho[t - 2] + rho[t - 1]:
+            rho[t] = (rho[t - 2] + rho[t - 1]) / 2
+            rho[t + 1] = rho[t]
+    N = m * n2
+    tau = max(-1 + 2 * rho[: max(1, max_t)].sum() + rho[max_t], 1 / np.log10(N))
+    out["ess"] = N / tau
+    return out
+
+
+@pytest.mark.parametrize("chains,iters,burn,thin", [(4, 64, 14, 1), (3, 47, 4, 2), (24, 1100, 100, 1)])
+def test_record_summary_on_device(chains, iters, burn, thin):
+    """bvhar_cuda_fit_record_summary: mean / sd / quantiles / split-R-hat / ESS / pip of every column
+    of a record, computed on the device, against NumPy on the fetched draws (shared-memory and global-memory paths)."""
+    pk, _ = pr.pack(prior="Horseshoe", sv=True, dim=2, T=40, lag=1, chains=chains, iters=iters, burn=burn, thin=thin, seed=3)
+    g = CudaFit(pk); g.run()
+    for nm in ("alpha_record", "a_record", "sigh_record", "alpha_sparse_record"):
+        got = g.record_summary(nm, level=.1)
+        draws = g.record_all(nm)  # [chain, draw, col]
+        for col in range(draws.shape[2]):
+            x = draws[:, :, col]
+            if np.isnan(x).any():
+                ok = ~np.isnan(x)
+                assert abs(got["mean"][col] - x[ok].mean()) < 1e-12 * max(1, abs(x[ok].mean()))
+                assert np.isnan(got["rhat"][col]) and np.isnan(got["lower"][col])
+                continue
+            ref = _np_summary(x, .1)
+            for key, val in ref.items():
+                if np.isnan(val) or np.isinf(val):  # e.g. a SAVS column that is zero in every draw: W = 0
+                    assert np.isnan(got[key][col]) or got[key][col] == val, (nm, col, key, got[key][col], val)
+                    continue
+                assert abs(got[key][col] - val) <= 1e-9 * max(1.0, abs(val)), (nm, col, key, got[key][col], val)
