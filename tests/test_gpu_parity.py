@@ -55,9 +55,11 @@ def relerr(a, b):
 
 
 # ---------------------------------------------------------------- building blocks
-@pytest.mark.parametrize("M,N,K", [(37, 29, 50), (130, 257, 33), (256, 128, 64), (20, 1891, 1000), (1, 1, 1), (129, 3, 7)])
+@pytest.mark.parametrize("M,N,K", [(37, 29, 50), (130, 257, 33), (256, 128, 64), (20, 1891, 1000), (1, 1, 1), (129, 3, 7),
+                                   (2048, 1290, 70), (1024, 2600, 19), (2560, 1891, 48)])
 def test_dgemm_tn_dmma(M, N, K):
-    """The DMMA contraction (SV-weighted Gram / latent residual) against a float64 host contraction."""
+    """The DMMA contraction (SV-weighted Gram / latent residual) against a float64 host contraction; the last three
+    shapes give every persistent CTA several tiles (160 - 320 tiles on 148 SMs) with ragged k-tiles and edge tiles."""
     rng = np.random.default_rng(M * 1000 + N)
     A = rng.normal(size=(K, M)); B = rng.normal(size=(K, N)); Cg = np.zeros((M, N))
     L = _abi.load_library()
