@@ -119,6 +119,18 @@ class OutforecastParams(C.Structure):
     ]
 
 
+class MniwDesc(C.Structure):
+    """bvhar_mniw_desc (include/bvhar_cuda.h): the conjugate Minnesota samplers."""
+    _fields_ = [
+        ("device", C.c_int32), ("num_chains", C.c_int32), ("num_iter", C.c_int32), ("num_burn", C.c_int32), ("thin", C.c_int32),
+        ("dim", C.c_int32), ("dim_design", C.c_int32),
+        ("mn_mean", c_dp), ("mn_prec", c_dp), ("iw_scale", c_dp), ("iw_shape", C.c_double),
+        ("seed_chain", c_up), ("unit_id_base", C.c_uint32), ("mh", C.c_int32),
+        ("gam_shape", C.c_double), ("gam_rate", C.c_double), ("invgam_shape", C.c_double), ("invgam_scl", C.c_double),
+        ("init_par", c_dp), ("init_hess", c_dp), ("init_scale_variance", c_dp),
+    ]
+
+
 PROGRESS_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_int)
 
 
@@ -373,6 +385,7 @@ def load_library():
     L.bvhar_cuda_outforecast_params_size.argtypes = [C.POINTER(C.c_int64)]
     L.bvhar_cuda_dgemm_tn.argtypes = [C.c_int, C.c_int64, C.c_int64, C.c_int64, c_dp, C.c_int64, c_dp, C.c_int64, c_dp, C.c_int64]
     L.bvhar_cuda_draw_coef_batched.argtypes = [C.c_int, C.c_int64, C.c_int32, c_dp, c_dp, c_dp, c_dp]
+    L.bvhar_cuda_mniw_run.argtypes = [C.POINTER(MniwDesc), c_dp, c_dp, c_dp, c_dp, C.POINTER(C.c_uint8)]
     L.bvhar_cuda_bench_fp64_peak.argtypes = [C.c_int, C.c_int, c_dp]
     L.bvhar_cuda_bench_dgemm_tn.argtypes = [C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_int, c_dp]
     if L.bvhar_cuda_abi_version() != ABI_VERSION:

@@ -1854,3 +1854,138 @@ int bvhar_cuda_draw_coef_batched(int device, int64_t batch, int32_t d, const dou
 }
 
 }  // extern "C"
+
+// ---- conjugate Minnesota samplers (kernels_mniw.cu) -------------------------------------------------------------
+namespace {
+// lower Cholesky factor of a column-major symmetric n x n matrix (LLT, lower triangle referenced); false if not PD
+bool host_chol_lower(const double* a, int n, std::vector<double>& L) {
+  L.assign((size_t)n * n, 0.0);  // row-major L[i * n + j], j <= i
+  for (int j = 0; j < n; ++j) {
+    double s = a[(size_t)j * n + j];
+    for (int m = 0; m < j; ++m) s -= L[(size_t)j * n + m] * L[(size_t)j * n + m];
+    if (!(s > 0.0)) return false;
+    const double piv = std::sqrt(s);
+    L[(size_t)j * n + j] = piv;
+    for (int i = j + 1; i < n; ++i) {
+      double t = a[(size_t)j * n + i];  // A(i, j), column-major
+      for (int m = 0; m < j; ++m) t -= L[(size_t)i * n + m] * L[(size_t)j * n + m];
+      L[(size_t)i * n + j] = t / piv;
+    }
+  }
+  return true;
+}
+// general inverse (Gauss-Jordan, partial pivoting) of a column-major n x n matrix: Eigen's inverse() of minnesota.h:427
+bool host_inverse(const double* a, int n, std::vector<double>& inv) {
+  std::vector<double> w((size_t)n * 2 * n, 0.0);
+  for (int i = 0; i < n; ++i) {
+    for (int j = 0; j < n; ++j) w[(size_t)i * 2 * n + j] = a[(size_t)j * n + i];
+    w[(size_t)i * 2 * n + n + i] = 1.0;
+  }
+  for (int c = 0; c < n; ++c) {
+    int piv = c;
+    for (int i = c + 1; i < n; ++i)
+      if (std::fabs(w[(size_t)i * 2 * n + c]) > std::fabs(w[(size_t)piv * 2 * n + c])) piv = i;
+    if (w[(size_t)piv * 2 * n + c] == 0.0) return false;
+    if (piv != c)
+      for (int j = 0; j < 2 * n; ++j) std::swap(w[(size_t)c * 2 * n + j], w[(size_t)piv * 2 * n + j]);
+    const double d = 1.0 / w[(size_t)c * 2 * n + c];
+    for (int j = 0; j < 2 * n; ++j) w[(size_t)c * 2 * n + j] *= d;
+    for (int i = 0; i < n; ++i) {
+      if (i == c) continue;
+      const double f = w[(size_t)i * 2 * n + c];
+      if (f == 0.0) continue;
+      for (int j = 0; j < 2 * n; ++j) w[(size_t)i * 2 * n + j] -= f * w[(size_t)c * 2 * n + j];
+    }
+  }
+  inv.assign((size_t)n * n, 0.0);  // column-major
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j < n; ++j) inv[(size_t)j * n + i] = w[(size_t)i * 2 * n + n + j];
+  return true;
+}
+}  // namespace
+
+extern "C" int bvhar_cuda_mniw_run(const bvhar_mniw_desc* d, double* alpha_record, double* sigma_record, double* lambda_record,
+                                   double* psi_record, uint8_t* accept_record) {
+  API_LOCK;
+  if (!d) return fail(BVHAR_ERR_BAD_ARG, "null descriptor");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(BVHAR_ERR_CUDA, "no CUDA device available: no CPU fallback");
+  const int k = d->dim, dd = d->dim_design, C = d->num_chains;
+  const int thin = d->thin < 1 ? 1 : d->thin;
+  if (k < 1 || dd < 1 || C < 1 || d->num_iter < 1 || d->num_burn < 0 || d->num_burn >= d->num_iter)
+    return fail(BVHAR_ERR_BAD_ARG, "mniw: dim, dim_design, num_chains >= 1 and 0 <= num_burn < num_iter are required");
+  if (!d->mn_mean || !d->mn_prec || !d->iw_scale || !d->seed_chain) return fail(BVHAR_ERR_BAD_ARG, "mniw: null input");
+  if (d->iw_shape <= k - 1) return fail(BVHAR_ERR_BAD_ARG, "Wrong 'shape'. shape > dim - 1 must be satisfied.");  // random.h:179-181
+  if (k > 118) return fail(BVHAR_ERR_UNSUPPORTED, "mniw: dim <= 118 (two dim x dim work matrices per CTA in shared memory)");
+  if (d->mh && (!d->init_par || !d->init_hess || !d->init_scale_variance)) return fail(BVHAR_ERR_BAD_ARG, "mniw: mh = 1 needs the inits");
+  const int rows = (d->num_iter - d->num_burn + thin - 1) / thin;
+  CU(cudaSetDevice(d->device));
+  pool_setup(d->device);
+
+  std::vector<double> Lp, Ls, R((size_t)dd * dd, 0.0);
+  if (!host_chol_lower(d->mn_prec, dd, Lp)) return fail(BVHAR_ERR_NUMERICAL, "mniw: the matrix-normal precision is not positive definite");
+  if (!host_chol_lower(d->iw_scale, k, Ls)) return fail(BVHAR_ERR_NUMERICAL, "mniw: the inverse-Wishart scale is not positive definite");
+  for (int i = 0; i < dd; ++i)
+    for (int m = i; m < dd; ++m) R[(size_t)i * dd + m] = Lp[(size_t)m * dd + i];  // U_u = L'
+  DevBuf<double> dmean, dR, dLs, dalpha, dsigma, dws;
+  DevBuf<uint32_t> dseed;
+  DevBuf<int> dflags;
+  CU(dmean.upload(std::vector<double>(d->mn_mean, d->mn_mean + (size_t)dd * k)));
+  CU(dR.upload(R)); CU(dLs.upload(Ls));
+  CU(dseed.upload(std::vector<uint32_t>(d->seed_chain, d->seed_chain + C)));
+  CU(dflags.alloc(1));
+  CU(dalpha.alloc((size_t)C * dd * k * rows)); CU(dsigma.alloc((size_t)C * k * k * rows));
+
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, d->device));
+  const size_t limit = 200 * 1024;
+  const bool w_smem = mniw_smem(k, dd, true) <= limit;
+  const size_t smem = mniw_smem(k, dd, w_smem);
+  int per_sm = (int)std::min<size_t>(4, std::max<size_t>(1, (220 * 1024) / (smem + 1024)));
+  const long long total = (long long)C * rows;
+  const int grid = (int)std::min<long long>(total, (long long)prop.multiProcessorCount * per_sm);
+  if (!w_smem) CU(dws.alloc((size_t)grid * dd * k));
+  MniwArgs A{};
+  A.k = k; A.d = dd; A.chains = C; A.rows = rows; A.num_burn = d->num_burn; A.thin = thin; A.shape = d->iw_shape;
+  A.mean = dmean.p; A.Rfull = dR.p; A.Ls = dLs.p; A.seeds = dseed.p; A.ubase = d->unit_id_base;
+  A.wscratch = w_smem ? nullptr : dws.p; A.alpha = dalpha.p; A.sigma = dsigma.p; A.flags = dflags.p;
+  CU(launch_mniw(A, grid, smem, 0));
+
+  DevBuf<double> dpar, dG, dlam, dpsi;
+  DevBuf<unsigned char> dacc_all, dacc;
+  if (d->mh) {
+    const int np = 1 + k;
+    std::vector<double> G((size_t)C * np * np, 0.0), inv, V((size_t)np * np), Lv;
+    for (int c = 0; c < C; ++c) {
+      if (!host_inverse(d->init_hess + (size_t)c * np * np, np, inv)) return fail(BVHAR_ERR_NUMERICAL, "mniw: the hessian of the inits is singular");
+      for (size_t e = 0; e < (size_t)np * np; ++e) V[e] = d->init_scale_variance[c] * inv[e];  // gaussian_variance, minnesota.h:427
+      if (!host_chol_lower(V.data(), np, Lv)) return fail(BVHAR_ERR_NUMERICAL, "mniw: scale_variance * hessian^-1 is not positive definite");
+      for (int i = 0; i < np; ++i)
+        for (int j = i; j < np; ++j) G[(size_t)c * np * np + (size_t)i * np + j] = Lv[(size_t)j * np + i];  // llt().matrixU()
+    }
+    CU(dpar.upload(std::vector<double>(d->init_par, d->init_par + (size_t)C * np)));
+    CU(dG.upload(G));
+    CU(dacc_all.alloc((size_t)C * d->num_iter)); CU(dacc.alloc((size_t)C * rows));
+    CU(dlam.alloc((size_t)C * rows)); CU(dpsi.alloc((size_t)C * k * rows));
+    MhArgs M{};
+    M.k = k; M.chains = C; M.rows = rows; M.num_iter = d->num_iter; M.num_burn = d->num_burn; M.thin = thin;
+    M.gamma_shp = d->gam_rate; M.gamma_rate = d->gam_shape;  // the swap of minnesota.h:426
+    M.invgam_shp = d->invgam_shape; M.invgam_scl = d->invgam_scl;
+    M.init_par = dpar.p; M.chol_var = dG.p; M.seeds = dseed.p; M.ubase = d->unit_id_base;
+    M.accept_all = dacc_all.p; M.lambda = dlam.p; M.psi = dpsi.p; M.accept = dacc.p; M.flags = dflags.p;
+    CU(launch_mh(M, 0));
+  }
+  CU(cudaDeviceSynchronize());
+  int flags = 0;
+  CU(cudaMemcpy(&flags, dflags.p, sizeof(int), cudaMemcpyDeviceToHost));
+  if (alpha_record) CU(cudaMemcpy(alpha_record, dalpha.p, dalpha.n * sizeof(double), cudaMemcpyDeviceToHost));
+  if (sigma_record) CU(cudaMemcpy(sigma_record, dsigma.p, dsigma.n * sizeof(double), cudaMemcpyDeviceToHost));
+  if (d->mh) {
+    if (lambda_record) CU(cudaMemcpy(lambda_record, dlam.p, dlam.n * sizeof(double), cudaMemcpyDeviceToHost));
+    if (psi_record) CU(cudaMemcpy(psi_record, dpsi.p, dpsi.n * sizeof(double), cudaMemcpyDeviceToHost));
+    if (accept_record) CU(cudaMemcpy(accept_record, dacc.p, dacc.n, cudaMemcpyDeviceToHost));
+  }
+  if (flags & 2) return fail(BVHAR_ERR_NUMERICAL, "'x' should be larger than 0.");  // invgamma_dens, common.h:503-505
+  if (flags & 1) return fail(BVHAR_ERR_NUMERICAL, "mniw: a sampled covariance matrix was not positive definite");
+  return 0;
+}

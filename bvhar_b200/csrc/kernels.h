@@ -92,4 +92,35 @@ size_t activity_scratch_doubles(int n_units, int ncoef, int S);
 cudaError_t launch_activity(const RecView& coef, const RecView& cst, int n_units, int N, int kc, int S, int n_lo, int n_hi, double* act,
                             double* scratch, cudaStream_t st);
 
+// conjugate Minnesota samplers (kernels_mniw.cu): McmcMniw / MhMinnesota, bayes/mniw/minnesota.h:241-278, 413-510
+struct MniwArgs {
+  int k, d, chains, rows, num_burn, thin;
+  double shape;          // posterior inverse-Wishart shape
+  const double* mean;    // [k][d]: d x k posterior mean, column-major
+  const double* Rfull;   // [d][d] row-major upper factor R of the posterior precision (prec = R'R)
+  const double* Ls;      // [k][k] row-major lower Cholesky factor of the inverse-Wishart scale
+  const uint32_t* seeds; // [chains]
+  uint32_t ubase;
+  double* wscratch;      // nullptr: the d x k work matrix lives in shared memory; else [grid][d * k]
+  double* alpha;         // [chains][d * k][rows] (column-major rows x (d k) per chain)
+  double* sigma;         // [chains][k * k][rows]
+  int* flags;            // bit 0: a sampled Sigma was not positive definite
+};
+struct MhArgs {
+  int k, chains, rows, num_iter, num_burn, thin;
+  double gamma_shp, gamma_rate, invgam_shp, invgam_scl;  // as MhMinnesota stores them (minnesota.h:426-427)
+  const double* init_par;   // [chains][1 + k] prevprior = (lambda, psi)
+  const double* chol_var;   // [chains][(1 + k)^2] row-major upper Cholesky factor of scale_variance * hessian^-1
+  const uint32_t* seeds;
+  uint32_t ubase;
+  unsigned char* accept_all;  // [chains][num_iter] scratch
+  double* lambda;             // [chains][rows]
+  double* psi;                // [chains][k][rows]
+  unsigned char* accept;      // [chains][rows]
+  int* flags;                 // bit 1: a proposed psi was negative (the reference STOPs)
+};
+size_t mniw_smem(int k, int d, bool w_in_smem);
+cudaError_t launch_mniw(const MniwArgs& A, int grid, size_t smem, cudaStream_t st);
+cudaError_t launch_mh(const MhArgs& M, cudaStream_t st);
+
 }  // namespace bvhar

@@ -26,7 +26,13 @@ enum Stage : uint32_t {
   ST_FORECAST_H = 8,
   ST_FORECAST_Y = 9,
   ST_PRIOR_COEF = 16,
-  ST_PRIOR_CONTEM = 24
+  ST_PRIOR_CONTEM = 24,
+  // conjugate Minnesota samplers (kernels_mniw.cu)
+  ST_MNIW_CHI = 32,   // Bartlett diagonal: chi-square(shape - i), element i
+  ST_MNIW_BART = 33,  // Bartlett off-diagonal normals, element j * k + i (j < i)
+  ST_MNIW_Z = 34,     // d x k matrix-normal innovations, element i * k + j
+  ST_MH_CAND = 35,    // Metropolis proposal normals, element 0 .. k
+  ST_MH_U = 36        // Metropolis acceptance uniform
 };
 
 struct Philox {

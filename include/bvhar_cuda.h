@@ -386,6 +386,40 @@ typedef struct {
 } bvhar_dynspill_params;
 int bvhar_cuda_dynamic_spillover(const bvhar_fit_desc* fit, const bvhar_dynspill_params* p, double* to, double* from, double* tot);
 
+/* ---- conjugate Minnesota samplers ----
+ * One call replaces the per-chain iteration loops of
+ *   estimate_mniw    (src/mniw.cpp:130-190): McmcMniw::doPosteriorDraws, bayes/mniw/minnesota.h:241-278
+ *   estimate_bvar_mh (src/mniw.cpp:46-110):  MhMinnesota::doPosteriorDraws, minnesota.h:413-510 (mh = 1)
+ * i.e. sim_mn_iw (math/random.h:177-211) per iteration and, for mh = 1, the random-walk Metropolis step on (lambda, psi)
+ * (minnesota.h:446-461, jointdens_hyperparam draw.h:59-72).  The posterior moments (Minnesota::estimateCoef /
+ * estimateCov, minnesota.h:176-187) are inputs.  Every (chain, kept iteration) is an independent work item on the device
+ * (addressed Philox stream: key (seed_chain[c], unit_id_base + c), iteration = mcmc_step).
+ * Records follow thin_record (draw.h:1297-1310): rows = ceil((num_iter - num_burn) / thin), mcmc_step
+ * num_burn + 1 + r * thin; every record is column-major rows x cols per chain, chains stacked. */
+typedef struct {
+  int32_t device;
+  int32_t num_chains, num_iter, num_burn, thin;
+  int32_t dim, dim_design;
+  const double* mn_mean;  /* dim_design x dim, column-major: MinnFit::_coef */
+  const double* mn_prec;  /* dim_design x dim_design:        MinnFit::_prec */
+  const double* iw_scale; /* dim x dim:                      MinnFit::_iw_scale */
+  double iw_shape;        /*                                 MinnFit::_iw_shape */
+  const uint32_t* seed_chain; /* [num_chains] */
+  uint32_t unit_id_base;
+  int32_t mh; /* 0: McmcMniw; 1: MhMinnesota (the fields below are read) */
+  double gam_shape, gam_rate;       /* param_prior$lambda$param (MhMinnSpec, minnesota.h:97-99); the shape <-> rate swap of
+                                       minnesota.h:426 is applied inside, as the reference does */
+  double invgam_shape, invgam_scl;  /* param_prior$sigma$param */
+  const double* init_par;            /* [num_chains][1 + dim]: MhMinnInits par = (lambda, psi) */
+  const double* init_hess;           /* [num_chains] (1 + dim) x (1 + dim) column-major: MhMinnInits hessian */
+  const double* init_scale_variance; /* [num_chains]: MhMinnInits scale_variance */
+} bvhar_mniw_desc;
+/* alpha_record [chains][rows x dim_design*dim], sigma_record [chains][rows x dim*dim]; mh = 1 also fills
+ * lambda_record [chains][rows], psi_record [chains][rows x dim], accept_record [chains][rows] (0 / 1); NULL skips one.
+ * BVHAR_ERR_NUMERICAL: a proposed psi was negative (invgamma_dens STOPs, common.h:503) or a factorisation failed. */
+int bvhar_cuda_mniw_run(const bvhar_mniw_desc* d, double* alpha_record, double* sigma_record, double* lambda_record,
+                        double* psi_record, uint8_t* accept_record);
+
 /* ---- fp64 building blocks exported for stage-level parity tests and the roofline bench ---- */
 /* C[M x N] (row-major, ldc) = alpha * A^T B + beta * C with A stored K x M row-major (lda) and
  * B stored K x N row-major (ldb): the DMMA contraction that builds the SV-weighted Gram

@@ -68,6 +68,9 @@ def lib():
         L.oracle_draw_at.restype = C.c_double
         L.oracle_minnesota_moments.argtypes = [C.c_int, C.c_int, c_dp, C.c_double, C.c_double, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp]
         L.oracle_minnesota_moments.restype = None
+        L.oracle_mniw_run.argtypes = [C.c_int] * 6 + [c_dp, c_dp, c_dp, C.c_double, C.POINTER(C.c_uint32), C.c_uint32, C.c_int,
+                                      C.c_double, C.c_double, C.c_double, C.c_double, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp,
+                                      C.POINTER(C.c_uint8)]
         L.oracle_max_threads.restype = C.c_int
         L.oracle_use_blas.argtypes = [C.c_char_p, C.c_char_p]
         _lib = L
@@ -154,3 +157,32 @@ class OracleFit:
         rc = self.L.oracle_fit_record(self.h, window, chain, name.encode(), dp(out), r.value, c.value)
         assert rc == 0, rc
         return out
+
+
+def mniw_run(num_chains, num_iter, num_burn, thin, mn_mean, mn_prec, iw_scale, iw_shape, seed_chain, mh=None, unit_base=0):
+    """oracle_mniw_run: McmcMniw / MhMinnesota (minnesota.h:241-278, 413-510) on the addressed Philox stream.  ``mh`` =
+    dict(par [chains][1+k], chol_var [chains] upper factors of scale_variance * hessian^-1, lambda_param, psi_param).
+    Returns (status, records) with records laid out like bvhar_b200.minnesota (rows x cols per chain)."""
+    mean = np.asfortranarray(mn_mean, dtype=np.float64); prec = np.asfortranarray(mn_prec, dtype=np.float64)
+    scale = np.asfortranarray(iw_scale, dtype=np.float64)
+    d, k = mean.shape
+    thin = max(int(thin), 1)
+    rows = (num_iter - num_burn + thin - 1) // thin
+    seeds = np.ascontiguousarray(seed_chain, dtype=np.uint32)
+    alpha = np.zeros((num_chains, d * k, rows)); sigma = np.zeros((num_chains, k * k, rows))
+    lam = np.zeros((num_chains, rows)); psi = np.zeros((num_chains, k, rows)); acc = np.zeros((num_chains, rows), dtype=np.uint8)
+    par = np.zeros((num_chains, 1 + k)); G = np.zeros((num_chains, 1 + k, 1 + k)); lp = (1.0, 1.0); pp = (1.0, 1.0)
+    if mh is not None:
+        par = np.ascontiguousarray(mh["par"], dtype=np.float64); G = np.ascontiguousarray(mh["chol_var"], dtype=np.float64)
+        lp = mh["lambda_param"]; pp = mh["psi_param"]
+    rc = lib().oracle_mniw_run(num_chains, num_iter, num_burn, thin, k, d, dp(mean), dp(prec), dp(scale), float(iw_shape),
+                               seeds.ctypes.data_as(C.POINTER(C.c_uint32)), unit_base, 1 if mh is not None else 0,
+                               float(lp[0]), float(lp[1]), float(pp[0]), float(pp[1]), dp(par), dp(G), dp(alpha), dp(sigma),
+                               dp(lam), dp(psi), acc.ctypes.data_as(C.POINTER(C.c_uint8)))
+    out = []
+    for c in range(num_chains):
+        o = {"alpha_record": alpha[c].T, "sigma_record": sigma[c].T}
+        if mh is not None:
+            o.update(lambda_record=lam[c].copy(), psi_record=psi[c].T, accept_record=acc[c].astype(bool))
+        out.append(o)
+    return rc, out

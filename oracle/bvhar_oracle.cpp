@@ -1579,4 +1579,138 @@ int oracle_use_blas(const char* path, const char* prefix) {
   return 0;
 }
 
+// ---- conjugate Minnesota samplers: McmcMniw / MhMinnesota (bayes/mniw/minnesota.h:241-278, 413-510) ----------------
+// A literal restatement of one chain's iteration loop with the draws addressed on the Philox stream
+// (stages ST_MNIW_* / ST_MH_*, iteration = mcmc_step):
+//   sim_iw_tri  (math/random.h:177-200)  upper Bartlett factor Q: Q_ii = sqrt(chi^2(shape - i)), Q_ij ~ N(0,1) (j > i);
+//                                        result = llt(scale).L * (Q' lower-triangular)^-1
+//   sim_mn_iw   (random.h:203-211)       Sigma = res res'; coef = sim_mn(mean, prec, Sigma, prec = true)
+//   sim_mn      (random.h:158-175)       mean + llt(prec).U^-1 (Z * llt(Sigma).U),  Z filled row by row
+//   updateHyper (minnesota.h:446-461)    candprior = prevprior + z' llt(gaussian_variance).U  (sim_mgaussian_chol,
+//                                        random.h:9-21); prevprior is never moved (reference behaviour);
+//                                        accept = log(u) < min(numerator - denom, 0).  compute_logml and the constant
+//                                        terms of jointdens_hyperparam (draw.h:59-72) take identical arguments in the
+//                                        numerator and the denominator and cancel; gamma_shp / gamma_rate are swapped as
+//                                        in minnesota.h:426.
+// Records: row r of the thinned record is mcmc_step num_burn + 1 + r * thin (thin_record, draw.h:1297-1310); outputs are
+// column-major rows x cols per chain.  Returns 3 when a proposed psi is negative (invgamma_dens STOPs, common.h:503).
+static double orc_gamma_logdens(double x, double shp, double scl) {
+  if (!(x > 0.0)) return -std::numeric_limits<double>::infinity();
+  return (shp - 1.0) * std::log(x) - x / scl - std::lgamma(shp) - shp * std::log(scl);
+}
+static double orc_invgamma_logdens(double x, double shp, double scl) {
+  return std::log(std::pow(scl, shp) * std::pow(x, -shp - 1.0) * std::exp(-scl / x) / std::tgamma(shp));
+}
+
+int oracle_mniw_run(int num_chains, int num_iter, int num_burn, int thin, int k, int d, const double* mn_mean, const double* mn_prec,
+                    const double* iw_scale, double iw_shape, const uint32_t* seed_chain, uint32_t unit_base, int mh, double gam_shape,
+                    double gam_rate, double invgam_shape, double invgam_scl, const double* init_par, const double* chol_var_upper,
+                    double* alpha_record, double* sigma_record, double* lambda_record, double* psi_record, uint8_t* accept_record) {
+  if (thin < 1) thin = 1;
+  const int rows = (num_iter - num_burn + thin - 1) / thin;
+  Mat Lu(d, d), Ls(k, k);
+  for (int j = 0; j < d; ++j) for (int i = 0; i < d; ++i) Lu(i, j) = mn_prec[(size_t)j * d + i];
+  for (int j = 0; j < k; ++j) for (int i = 0; i < k; ++i) Ls(i, j) = iw_scale[(size_t)j * k + i];
+  if (!chol_lower(Lu) || !chol_lower(Ls)) return 2;
+  const double gamma_shp = gam_rate, gamma_rate = gam_shape;  // minnesota.h:426
+  const int np = 1 + k;
+  int status = 0;
+  for (int c = 0; c < num_chains; ++c) {
+    Rng rng;
+    rng.seed(seed_chain[c], unit_base + (uint32_t)c, true);
+    Vec lam_psi(np, 0.0);
+    if (mh) for (int j = 0; j < np; ++j) lam_psi[j] = init_par[(size_t)c * np + j];
+    bool is_accept = true;
+    for (int t = 1; t <= num_iter; ++t) {
+      rng.iter = (uint32_t)t;
+      if (mh) {
+        const double* prev = init_par + (size_t)c * np;
+        const double* G = chol_var_upper + (size_t)c * np * np;  // row-major upper factor
+        Vec z(np), cand(np);
+        rng.normal_vec(ST_MH_CAND, 0, np, z.data());
+        for (int j = 0; j < np; ++j) {
+          double v = prev[j];
+          for (int i = 0; i <= j; ++i) v = std::fma(z[i], G[(size_t)i * np + j], v);
+          cand[j] = v;
+        }
+        double num = orc_gamma_logdens(cand[0], gamma_shp, 1.0 / gamma_rate), den = orc_gamma_logdens(prev[0], gamma_shp, 1.0 / gamma_rate);
+        for (int j = 1; j < np; ++j) {
+          if (cand[j] < 0.0) status = 3;
+          num += orc_invgamma_logdens(cand[j], invgam_shape, invgam_scl);
+          den += orc_invgamma_logdens(prev[j], invgam_shape, invgam_scl);
+        }
+        const double u = rng.uniform(ST_MH_U, 0, 0);
+        is_accept = std::log(u) < std::min(num - den, 0.0);
+        if (is_accept) lam_psi = cand;
+      }
+      const int post = t - num_burn - 1;
+      if (post < 0 || post % thin) continue;  // only the kept iterations are materialised (draws are addressed)
+      const int r = post / thin;
+      // sim_iw_tri
+      Mat Q(k, k);
+      for (int i = 0; i < k; ++i) Q(i, i) = std::sqrt(rng.gamma(ST_MNIW_CHI, (uint32_t)i, 0.5 * (iw_shape - (double)i), 2.0));
+      for (int i = 0; i < k - 1; ++i)
+        for (int j = i + 1; j < k; ++j) {
+          const uint32_t e = (uint32_t)(i * k + j);
+          double z0, z1;
+          rng.normal_pair(ST_MNIW_BART, e >> 1, 0, z0, z1);
+          Q(i, j) = (e & 1u) ? z1 : z0;
+        }
+      Mat Binv(k, k);  // (Q')^-1, column by column: solve Q' y = e_c
+      for (int cc = 0; cc < k; ++cc) {
+        Vec y(k, 0.0);
+        y[cc] = 1.0;
+        for (int i = 0; i < k; ++i) {
+          double sacc = y[i];
+          for (int m = 0; m < i; ++m) sacc -= Q(m, i) * y[m];
+          y[i] = sacc / Q(i, i);
+        }
+        for (int i = 0; i < k; ++i) Binv(i, cc) = y[i];
+      }
+      Mat Cm(k, k), Sig(k, k);
+      for (int i = 0; i < k; ++i)
+        for (int j = 0; j < k; ++j) {
+          double sacc = 0.0;
+          for (int m = 0; m < k; ++m) sacc += (m <= i ? Ls(i, m) : 0.0) * Binv(m, j);
+          Cm(i, j) = sacc;
+        }
+      for (int i = 0; i < k; ++i)
+        for (int j = 0; j < k; ++j) {
+          double sacc = 0.0;
+          for (int m = 0; m < k; ++m) sacc += Cm(i, m) * Cm(j, m);
+          Sig(i, j) = sacc;
+        }
+      for (int j = 0; j < k; ++j)
+        for (int i = 0; i < k; ++i) sigma_record[((size_t)c * k * k + (size_t)j * k + i) * rows + r] = Sig(i, j);
+      // sim_mn with prec = true
+      Mat Lv = Sig;
+      if (!chol_lower(Lv)) status = status ? status : 2;
+      Mat Z(d, k);
+      for (int i = 0; i < d; ++i) {
+        Vec row(k);
+        rng.normal_vec(ST_MNIW_Z, (uint32_t)(i * k), k, row.data());
+        for (int j = 0; j < k; ++j) Z(i, j) = row[j];
+      }
+      Mat W(d, k);
+      for (int i = 0; i < d; ++i)
+        for (int cc = 0; cc < k; ++cc) {
+          double sacc = 0.0;
+          for (int j = 0; j <= cc; ++j) sacc += Z(i, j) * Lv(cc, j);  // U_v(j, cc) = L_v(cc, j)
+          W(i, cc) = sacc;
+        }
+      for (int cc = 0; cc < k; ++cc) {
+        solve_lower_t(Lu, W.col(cc));  // U_u x = w with U_u = L_u'
+        for (int i = 0; i < d; ++i)
+          alpha_record[((size_t)c * d * k + (size_t)cc * d + i) * rows + r] = mn_mean[(size_t)cc * d + i] + W(i, cc);
+      }
+      if (mh) {
+        lambda_record[(size_t)c * rows + r] = lam_psi[0];
+        for (int j = 1; j < np; ++j) psi_record[((size_t)c * k + (j - 1)) * rows + r] = lam_psi[j];
+        accept_record[(size_t)c * rows + r] = is_accept ? 1 : 0;
+      }
+    }
+  }
+  return status;
+}
+
 }  // extern "C"

@@ -64,7 +64,8 @@ enum Stage : uint32_t {
   ST_FORECAST_H = 8,
   ST_FORECAST_Y = 9,
   ST_PRIOR_COEF = 16,   // + site 0..7
-  ST_PRIOR_CONTEM = 24  // + site 0..7
+  ST_PRIOR_CONTEM = 24, // + site 0..7
+  ST_MNIW_CHI = 32, ST_MNIW_BART = 33, ST_MNIW_Z = 34, ST_MH_CAND = 35, ST_MH_U = 36  // conjugate Minnesota samplers
 };
 
 struct Rng {
