@@ -127,8 +127,9 @@ struct bvhar_fit {
   DevBuf<long long> d_off, g1_b, g1_c, g2_b, g2_c, g3_a, g3_b, g3_y;
   DevBuf<uint32_t> seeds, iter;
   DevBuf<double> H, Z, Dinv, YLD, S, Cm, Acoef, alpha, cvec, prec, contem, L, chol_prec, sparse_coef, sparse_contem;
-  DevBuf<double> Zn, lvol_init, lvol_sig, diag, znorm, hN[4], hG[3], hq[4], hs, vscratch, pscratch, gscratch, Pfac, hscr, Qn;
+  DevBuf<double> Zn, lvol_init, lvol_sig, diag, znorm, hN[4], hG[3], hq[4], hs, vscratch, pscratch, gscratch, Pfac, hscr, Qn, Wt;
   bool coef_v2 = false, coef_big = false;
+  bool direct_p = false;  // large-design SV path: G1 contracts the mixed weights and writes the P_j themselves (no S_i, no pbuild)
   std::map<std::string, std::unique_ptr<DevBuf<double>>> rec;
   std::vector<RecordSpec> rec_order;
   GemmArgs g1{}, g2{}, g3{};
@@ -244,12 +245,13 @@ struct bvhar_fit {
       if (fork) CU(cudaEventRecord(evf[6], s2));
       // (updateSv, stage 3, was already done at the end of the previous sweep - see below - or at create time)
       if (fork) { CU(cudaEventRecord(evf[2], st)); CU(cudaStreamWaitEvent(s3, evf[2], 0)); }
-      LAUNCH("gram_C_dmma", launch_dgemm_tn(g2, sg));
+      if (direct_p) LAUNCH("sv_wmix", launch_sv_wmix(D, P, Wt.p, st));
+      else LAUNCH("gram_C_dmma", launch_dgemm_tn(g2, sg));
       if (fork) CU(cudaEventRecord(evf[3], s3));
       LAUNCH("gram_S_dmma", launch_dgemm_tn(g1, st));
     }
     if (coef_big) {
-      if (D.sv) LAUNCH("coef_pbuild", launch_coef_v2(0, D, P, Pfac.p, Qn.p, smem_limit, st));
+      if (D.sv && !direct_p) LAUNCH("coef_pbuild", launch_coef_v2(0, D, P, Pfac.p, Qn.p, smem_limit, st));
       if (fork) { CU(cudaStreamWaitEvent(st, evf[1], 0)); if (D.sv) CU(cudaStreamWaitEvent(st, evf[3], 0)); }
       LAUNCH("coef_chol_cta", launch_coef_big(1, D, P, Pfac.p, hscr.p, smem_limit, st));
       LAUNCH("coef_seq_big", launch_coef_big(2, D, P, Pfac.p, hscr.p, smem_limit, st));
@@ -680,7 +682,13 @@ int build(const bvhar_fit_desc* d, bvhar_fit** out) {
     }
     lap("coef uploads + lvol upload / scatter");
     CU(F->Dinv.alloc((size_t)tm_total)); CU(F->YLD.alloc((size_t)tm_total)); CU(F->Zn.alloc((size_t)tm_total));
-    CU(F->S.alloc((size_t)U * k * D.ldS)); CU(F->Cm.alloc((size_t)U * k * D.ldX));
+    {  // same decision as the coefficient-stage dispatch below: designs on the CTA-per-matrix path never touch S_i / C_i
+      const bool v1 = getenv("BVHAR_COEF_V1") != nullptr, fbig = getenv("BVHAR_COEF_BIG") != nullptr;
+      const bool v2 = coef_v2_fits(D, F->smem_limit) && !v1;
+      F->direct_p = coef_big_fits(D, F->smem_limit) && !v1 && (D.d > 128 || !v2 || fbig) && getenv("BVHAR_NO_DIRECT_P") == nullptr;
+    }
+    if (F->direct_p) CU(F->Wt.alloc((size_t)tm_total));
+    else { CU(F->S.alloc((size_t)U * k * D.ldS)); CU(F->Cm.alloc((size_t)U * k * D.ldX)); }
     CU(F->XX.alloc((size_t)D.T * D.ldXX));
   } else {
     CU(F->diag.upload(hdiag));
@@ -753,6 +761,10 @@ int build(const bvhar_fit_desc* d, bvhar_fit** out) {
   F->coef_big = coef_big_fits(D, F->smem_limit) && !force_v1 && (D.d > 128 || !F->coef_v2 || force_big);
   if (F->coef_big) F->coef_v2 = false;
   if (F->coef_v2 || F->coef_big) CU(F->Pfac.alloc((size_t)U * k * D.ldS));
+  if (F->direct_p) {
+    if (!F->coef_big) return fail(BVHAR_ERR_CUDA, "internal: direct precision build without the large-design path");
+    F->g1.A = F->Wt.p; F->g1.C = F->Pfac.p;
+  }
   if (F->coef_big) CU(F->hscr.alloc(D.sv ? seq_time_scratch_doubles(D) : (size_t)U * k * dd));
   if (F->coef_v2 && coef_pipe_fits(D, F->smem_limit) && getenv("BVHAR_COEF_NOPIPE") == nullptr) CU(F->Qn.alloc((size_t)U * k * D.ldS));
   if (!F->coef_v2 && !F->coef_big && !coef_plan(D, F->smem_limit, &ch_plan, &need_v, &need_p))
@@ -1302,9 +1314,10 @@ int bvhar_cuda_fit_run_stage(bvhar_fit* fit, int stage, int iter) {
     case 2: break;  // alpha_penalty is a constant of the group structure here
     case 3: if (D.sv) CU(launch_sv_prep(D, fit->P, fit->st)); break;
     case 4:
-      if (D.sv) { CU(launch_dgemm_tn(fit->g1, fit->st)); CU(launch_dgemm_tn(fit->g2, fit->st)); }
+      if (D.sv && fit->direct_p) { CU(launch_sv_wmix(D, fit->P, fit->Wt.p, fit->st)); CU(launch_dgemm_tn(fit->g1, fit->st)); }
+      else if (D.sv) { CU(launch_dgemm_tn(fit->g1, fit->st)); CU(launch_dgemm_tn(fit->g2, fit->st)); }
       if (fit->coef_big) {
-        if (D.sv) CU(launch_coef_v2(0, D, fit->P, fit->Pfac.p, fit->Qn.p, fit->smem_limit, fit->st));
+        if (D.sv && !fit->direct_p) CU(launch_coef_v2(0, D, fit->P, fit->Pfac.p, fit->Qn.p, fit->smem_limit, fit->st));
         CU(launch_coef_big(1, D, fit->P, fit->Pfac.p, fit->hscr.p, fit->smem_limit, fit->st));
         CU(launch_coef_big(2, D, fit->P, fit->Pfac.p, fit->hscr.p, fit->smem_limit, fit->st));
       } else if (fit->coef_v2) {

@@ -7,6 +7,7 @@
 namespace bvhar {
 
 cudaError_t launch_sv_prep(const Dims& D, const DevPtrs& P, cudaStream_t st);
+cudaError_t launch_sv_wmix(const Dims& D, const DevPtrs& P, double* Wt, cudaStream_t st);  // weights of the direct P_j build (large-design SV path)
 bool coef_plan(const Dims& D, size_t smem_limit, int* CH_out, bool* vglobal_out, bool* pglobal_out);
 cudaError_t launch_coef(const Dims& D, const DevPtrs& P, double* vscratch, double* pscratch, size_t smem_limit, cudaStream_t st);
 cudaError_t launch_draw_coef_batched(long long batch, int d, const double* Pp, const double* b, const double* z, double* out,
@@ -82,6 +83,7 @@ struct ForecastArgs {
   const double *last_obs, *valid;
   const uint32_t* seed;
   double *out, *lpl;
+  double* lpl_draw;   // [n_units][step][S] per-draw log predictive likelihoods (scratch owned by launch_forecast)
   const double* act;  // [n_units][ncoef] activity graph of the Select forecasters (0 or 1.1), nullptr for the plain ones
   int ncoef;          // nrow * k + k * mean
 };

@@ -185,17 +185,23 @@ __global__ void __launch_bounds__(CB_THREADS) coef_seq_big_kernel(const Dims D, 
           }
         }
       } else {
-        // X'X delta once, rows split over the warps: warp q takes the 32-row blocks q, q + nw, ...
-        for (int a = tid; a < d; a += blockDim.x) tv[a] = 0.0;
-        __syncthreads();
+        // X'X delta once, rows split over the warps: warp q takes the 32-row blocks q, q + nw, ... and leaves its partial
+        // product in its own row of wscr; the partials are then added in warp order (a shared-memory atomicAdd here made
+        // the last bits of the draw depend on the warp scheduling: the trajectories were not reproducible)
         {
           double out[NC];
           symv_packed_warp<NC>(X2, yv, d, out, warp, nw);
 #pragma unroll
           for (int sidx = 0; sidx < NC; ++sidx) {
             const int b = lane + 32 * sidx;
-            if (b < d && out[sidx] != 0.0) atomicAdd(&tv[b], out[sidx]);
+            if (b < d) wscr[(size_t)warp * d + b] = out[sidx];
           }
+        }
+        __syncthreads();
+        for (int a = tid; a < d; a += blockDim.x) {
+          double s = 0.0;
+          for (int q = 0; q < nw; ++q) s += wscr[(size_t)q * d + a];
+          tv[a] = s;
         }
         __syncthreads();
         for (int e = tid; e < (k - j - 1) * d; e += blockDim.x) {

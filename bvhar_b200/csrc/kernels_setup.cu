@@ -100,9 +100,6 @@ __global__ void __launch_bounds__(128) forecast_kernel(const ForecastArgs A) {
   double* svu = pm + k;
   double* zn = svu + k;
   double* hx = zn + k;
-  __shared__ double lpl_acc[64];
-  for (int h = threadIdx.x; h < step && h < 64; h += blockDim.x) lpl_acc[h] = 0.0;
-  __syncthreads();
   if (i < S) {
     auto at = [&](const RecView& v, int col) { return v.p[(long long)u * v.us + (long long)i * v.sd + (long long)col * v.sc]; };
     const double* last = A.last_obs + (size_t)u * p * k;
@@ -175,14 +172,27 @@ __global__ void __launch_bounds__(128) forecast_kernel(const ForecastArgs A) {
           quad += s * s;
         }
         const double val = lg - k * log(2 * 3.14159265358979323846) / 2 - quad / 2;
-        if (h < 64) atomicAdd(&lpl_acc[h], val);
+        if (A.lpl_draw) A.lpl_draw[((size_t)u * step + h) * S + i] = val;  // summed in a fixed order by lpl_reduce_kernel
       }
       for (int e = 0; e < (p - 1) * k; ++e) tmp[e] = last_pvec[e];
     }
   }
+}
+// lpl[u][h] = mean over the S draws of the per-draw log predictive likelihood (fc.h:92-96), summed in an order that depends
+// on S only (strided per-thread partial sums, then a fixed tree): bit-identical on any GPU count and for any block size of
+// the forecast kernel (a floating-point atomicAdd here made the last bits of the LPL depend on the scheduling).
+__global__ void __launch_bounds__(128) lpl_reduce_kernel(const double* __restrict__ lpl_draw, int S, double* __restrict__ lpl) {
+  __shared__ double part[128];
+  const double* src = lpl_draw + (size_t)blockIdx.x * S;
+  double s = 0.0;
+  for (int i = threadIdx.x; i < S; i += 128) s += src[i];
+  part[threadIdx.x] = s;
   __syncthreads();
-  if (A.lpl)
-    for (int h = threadIdx.x; h < step && h < 64; h += blockDim.x) atomicAdd(&A.lpl[(size_t)u * step + h], lpl_acc[h] / S);
+  for (int o = 64; o > 0; o >>= 1) {
+    if (threadIdx.x < o) part[threadIdx.x] += part[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) lpl[blockIdx.x] = part[0] / S;
 }
 // RegRecords::computeActivity (config.h:747-758): per record column, the two order statistics that
 // boost::accumulators::tail_quantile<left / right> return with the whole sample cached (BH >= 1.87, un-vendored:
@@ -265,7 +275,18 @@ cudaError_t launch_forecast(const ForecastArgs& A, cudaStream_t st) {
   const size_t smem = (size_t)threads * per * sizeof(double);
   if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
   cudaFuncSetAttribute(forecast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  forecast_kernel<<<dim3((A.S + threads - 1) / threads, A.n_units), threads, smem, st>>>(A);
+  ForecastArgs B = A;
+  B.lpl_draw = nullptr;
+  const bool want_lpl = A.lpl && A.get_lpl && A.valid;
+  if (want_lpl) {
+    cudaError_t e = cudaMallocAsync(&B.lpl_draw, (size_t)A.n_units * A.step * A.S * sizeof(double), st);
+    if (e != cudaSuccess) return e;
+  }
+  forecast_kernel<<<dim3((A.S + threads - 1) / threads, A.n_units), threads, smem, st>>>(B);
+  if (want_lpl) {
+    lpl_reduce_kernel<<<(unsigned)((size_t)A.n_units * A.step), 128, 0, st>>>(B.lpl_draw, A.S, A.lpl);
+    cudaFreeAsync(B.lpl_draw, st);
+  }
   return cudaGetLastError();
 }
 

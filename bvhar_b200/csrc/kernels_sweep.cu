@@ -863,6 +863,45 @@ cudaError_t launch_draw_coef_batched(long long batch, int d, const double* Pp, c
   draw_coef_batched_kernel<<<(unsigned)batch, 256, smem, st>>>(d, Pp, b, z, out);
   return cudaGetLastError();
 }
+// ---- large-design SV path: the weights of the direct precision build -------------------------------------------------
+// P_j = X' diag(w_j) X with w_tj = sum_{i>=j} L_ij^2 / s_ti^2 (the weighted Gram of equation j's Kronecker design,
+// triangular.h:286 + draw.h:380).  Where the S_i = X' D_i X themselves are not needed (designs with d > 128: the
+// sequential part runs in the time domain, kernels_seq_big.cu) the Gram contraction G1 takes these weights as its A
+// operand and writes the k precision matrices of a unit directly - no S_i, no [k x k] x [k x Pp] mixing pass over them.
+// One CTA per (unit, 32 time points): L o L in shared memory, one thread per (t, j).
+constexpr int WMX_TT = 32;
+__global__ void __launch_bounds__(256) sv_wmix_kernel(const Dims D, const DevPtrs P, double* __restrict__ Wt) {
+  extern __shared__ __align__(16) double sm[];
+  const int u = blockIdx.x, w = u / D.C, c = u % D.C, k = D.k;
+  const int n = P.win_n[w], t0 = blockIdx.y * WMX_TT;
+  if (t0 >= n) return;
+  double* L2 = sm;           // [k][k] L_ij^2
+  double* dt = L2 + k * k;   // [TT][k]
+  const long long off = P.win_off[w] + (long long)c * k;
+  for (int e = threadIdx.x; e < k * k; e += blockDim.x) {
+    const double l = P.L[(size_t)u * k * k + e];
+    L2[e] = l * l;
+  }
+  for (int e = threadIdx.x; e < WMX_TT * k; e += blockDim.x) {
+    const int tt = e / k, i = e - tt * k;
+    dt[e] = t0 + tt < n ? P.Dinv[off + (long long)(t0 + tt) * D.ldM + i] : 0.0;
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < WMX_TT * k; e += blockDim.x) {
+    const int tt = e / k, j = e - tt * k;
+    if (t0 + tt >= n) continue;
+    double acc = 0.0;
+    for (int i = j; i < k; ++i) acc = fma(L2[i * k + j], dt[tt * k + i], acc);
+    Wt[off + (long long)(t0 + tt) * D.ldM + j] = acc;
+  }
+}
+cudaError_t launch_sv_wmix(const Dims& D, const DevPtrs& P, double* Wt, cudaStream_t st) {
+  const size_t smem = ((size_t)D.k * D.k + (size_t)WMX_TT * D.k) * sizeof(double);
+  if (smem > 200 * 1024) return cudaErrorInvalidConfiguration;
+  cudaFuncSetAttribute(sv_wmix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  sv_wmix_kernel<<<dim3(D.U, (D.nmax + WMX_TT - 1) / WMX_TT), 256, smem, st>>>(D, P, Wt);
+  return cudaGetLastError();
+}
 cudaError_t launch_sv_prep(const Dims& D, const DevPtrs& P, cudaStream_t st) {
   if (D.k <= 128 && getenv("BVHAR_SV_THREAD_KERNELS") == nullptr) return launch_sv_tile<false>(D, P, st);
   const dim3 grid((D.M + 255) / 256, (D.nmax + SVP_TT - 1) / SVP_TT, D.W);
