@@ -123,8 +123,8 @@ struct bvhar_fit {
   std::vector<long long> win_off;
   // device storage
   DevBuf<double> X, XT, Y, XX, xnorm, XtX, XtY, prior_mean, sig_shp, sig_scl, sv_mean, sv_prec, ssvs_s1, ssvs_s2;
-  DevBuf<int> d_row0, d_n, grp_idx, grp_cnt, own_flag, flags, rec_row, gKg, gMg;
-  DevBuf<long long> d_off, g1_b, g1_c, g2_b, g2_c, g3_a, g3_b, g3_y;
+  DevBuf<int> d_row0, d_n, grp_idx, grp_cnt, own_flag, flags, rec_row, gKg, gMg, gz_K;
+  DevBuf<long long> d_off, g1_b, g1_c, g2_b, g2_c, g3_a, g3_b, g3_y, gz_a, gz_c;
   DevBuf<uint32_t> seeds, iter;
   DevBuf<double> H, Z, Dinv, YLD, S, Cm, Acoef, alpha, cvec, prec, contem, L, chol_prec, sparse_coef, sparse_contem;
   DevBuf<double> Zn, lvol_init, lvol_sig, diag, znorm, hN[4], hG[3], hq[4], hs, vscratch, pscratch, gscratch, Pfac, hscr, Qn, Wt;
@@ -132,7 +132,7 @@ struct bvhar_fit {
   bool direct_p = false;  // large-design SV path: G1 contracts the mixed weights and writes the P_j themselves (no S_i, no pbuild)
   std::map<std::string, std::unique_ptr<DevBuf<double>>> rec;
   std::vector<RecordSpec> rec_order;
-  GemmArgs g1{}, g2{}, g3{};
+  GemmArgs g1{}, g2{}, g3{}, gz{};  // gz: Z'Z per unit (LDLT contemporaneous draw + state)
   bool g3_aligned = true;
   bool timed = false;
   // per-kernel profiling (eager launches bracketed by CUDA events on the engine's stream)
@@ -265,7 +265,9 @@ struct bvhar_fit {
       LAUNCH("coef_draw", launch_coef(D, P, vscratch.p, pscratch.p, smem_limit, st));
     }
     LAUNCH("latent_dmma", launch_dgemm_tn(g3, st));
+    if (!D.sv && !ldlt_own_gram(D)) LAUNCH("gram_Z_dmma", launch_dgemm_tn(gz, st));
     if (D.k > 1) LAUNCH("impact_draw", launch_impact(D, P, gscratch.p, st));
+    else if (!D.sv) LAUNCH("gram_Z", launch_ldlt_gram_small(D, P, gscratch.p, st));  // univariate LDLT: the state draw still reads Z'Z
     if (D.sv) {
       LAUNCH("sv_mix", launch_sv_state(0, D, P, st));
       if (fork) CU(cudaStreamWaitEvent(st, evf[6], 0));
@@ -277,7 +279,7 @@ struct bvhar_fit {
       if (fork) CU(cudaEventRecord(evf[5], s2));
       LAUNCH("sv_finish", launch_sv_state(2, D, P, st));
     }
-    else LAUNCH("ldlt_state", launch_ldlt_state(D, P, st));
+    else LAUNCH("ldlt_state", launch_ldlt_state(D, P, gscratch.p, st));
     if (record) {
       LAUNCH("record", launch_record(D, P, R, st));
       LAUNCH("bump", launch_bump(P, 0, 1, st));
@@ -772,6 +774,22 @@ int build(const bvhar_fit_desc* d, bvhar_fit** out) {
   if (need_v) CU(F->vscratch.alloc((size_t)U * 2 * k * dd));
   if (need_p) CU(F->pscratch.alloc((size_t)U * D.ldS));
   CU(F->gscratch.alloc((size_t)U * impact_gsize(D)));
+  if (!D.sv) {  // Z'Z of every unit: one group per unit, A = B = the unit's k columns of the window's residual array
+    const int kz = (k + 1) & ~1, gs = impact_gsize(D);
+    std::vector<long long> za(U), zc(U);
+    std::vector<int> zk(U);
+    bool al = (D.ldM % 2) == 0;
+    for (int u = 0; u < U; ++u) {
+      const int w = u / D.C, c = u % D.C;
+      za[u] = F->win_off[w] + (long long)c * k; zc[u] = (long long)u * gs; zk[u] = F->win_n[w];
+      if (za[u] & 1) al = false;
+    }
+    CU(F->gz_a.upload(za)); CU(F->gz_c.upload(zc)); CU(F->gz_K.upload(zk));
+    GemmArgs& gz = F->gz;
+    gz.A = P.Z; gz.B = P.Z; gz.C = F->gscratch.p; gz.M = k; gz.N = k; gz.K = 0; gz.lda = D.ldM; gz.ldb = D.ldM; gz.ldc = kz;
+    gz.groups = U; gz.a_off = F->gz_a.p; gz.b_off = F->gz_a.p; gz.c_off = F->gz_c.p; gz.Kg = F->gz_K.p; gz.Mg = nullptr;
+    gz.epi = EPI_STORE; gz.aligned16 = al ? 1 : 0;
+  }
   if (!impact_supported(D, F->smem_limit))
     return fail(BVHAR_ERR_UNSUPPORTED, "dim too large for the shared-memory contemporaneous draw of this build");
   // every allocation, memset and upload above was issued on stream 0, and F->st is a non-blocking stream: order
@@ -1330,11 +1348,19 @@ int bvhar_cuda_fit_run_stage(bvhar_fit* fit, int stage, int iter) {
       break;
     case 5: CU(launch_prior(D, fit->P, fit->PC, 1, fit->st)); break;
     case 6: CU(launch_dgemm_tn(fit->g3, fit->st)); break;
-    case 7: if (D.k > 1) CU(launch_impact(D, fit->P, fit->gscratch.p, fit->st)); break;
+    case 7:
+      if (!D.sv && !ldlt_own_gram(D)) CU(launch_dgemm_tn(fit->gz, fit->st));
+      if (D.k > 1) CU(launch_impact(D, fit->P, fit->gscratch.p, fit->st));
+      else if (!D.sv) CU(launch_ldlt_gram_small(D, fit->P, fit->gscratch.p, fit->st));
+      break;
     case 8: break;  // chol_lower is rebuilt inside the contemporaneous draw
     case 9:
       if (D.sv) { CU(launch_sv_state(3, D, fit->P, fit->st)); CU(launch_sv_state(0, D, fit->P, fit->st)); CU(launch_sv_state(1, D, fit->P, fit->st)); CU(launch_sv_state(2, D, fit->P, fit->st)); }
-      else CU(launch_ldlt_state(D, fit->P, fit->st));
+      else {  // the state draw reads Z'Z: recompute it for the residuals in place now
+        if (ldlt_own_gram(D)) CU(launch_ldlt_gram_small(D, fit->P, fit->gscratch.p, fit->st));
+        else CU(launch_dgemm_tn(fit->gz, fit->st));
+        CU(launch_ldlt_state(D, fit->P, fit->gscratch.p, fit->st));
+      }
       break;
     default: return fail(BVHAR_ERR_BAD_ARG, "stage must be 1..9");
   }

@@ -7,7 +7,7 @@
 //   stage 6  updateLatent  G3 contraction                          tri.h:342
 //   stage 7  updateImpact  impact_kernel       tri.h:322-336, draw.h:398-415   (+ stage 8 updateChol, draw.h:124-132)
 //   stage 9  updateState   SV:   sv_mix_kernel + sv_solve_kernel + sv_finish_kernel   tri.h:400-408, draw.h:440-537
-//                          LDLT: ldlt_state_kernel                                    tri.h:371, draw.h:1244-1259
+//                          LDLT: ldlt_state_kernel (kernels_impact.cu)                tri.h:371, draw.h:1244-1259
 //   records                record_kernel       config.h:850-857, 955-965, 796-804
 //
 // Arithmetic follows the "efficient" formulation proved equal to the reference's in
@@ -216,29 +216,6 @@ __global__ void __launch_bounds__(256) coef_kernel(const Dims D, const DevPtrs P
     __syncthreads();
   }
   if (tid == 0 && bad) atomicOr(&P.flags[u], 1);
-}
-
-// ------------------------------------------------------------------ stage 9 (LDLT): updateState
-// d_i = 1 / Gamma(shape_i + floor(n/2), 1 / (scl_i + ||(Z L')_i||^2 / 2))   (draw.h:1244-1259)
-__global__ void __launch_bounds__(128) ldlt_state_kernel(const Dims D, const DevPtrs P) {
-  __shared__ double scratch[40];
-  const int u = blockIdx.x, w = u / D.C, c = u % D.C;
-  const int k = D.k, n = P.win_n[w];
-  const long long off = P.win_off[w] + (long long)c * k;
-  const Philox rng(P.seeds[u], (uint32_t)(D.ubase + u), *P.iter);
-  const double* Lu = P.L + (size_t)u * k * k;
-  for (int i = 0; i < k; ++i) {
-    double ss = 0.0;
-    for (int t = threadIdx.x; t < n; t += blockDim.x) {
-      const double* z = P.Z + off + (long long)t * D.ldM;
-      double uu = 0.0;
-      for (int m = 0; m <= i; ++m) uu += Lu[i * k + m] * z[m];
-      ss += uu * uu;
-    }
-    ss = block_sum(ss, scratch);
-    if (threadIdx.x == 0)
-      P.diag[(size_t)u * k + i] = 1.0 / rng.gamma(ST_LDLT_DIAG, (uint32_t)i, P.sig_shp[i] + (double)(n / 2), 1.0 / (P.sig_scl[i] + ss / 2));
-  }
 }
 
 // ------------------------------------------------------------------ stage 9 (SV): updateState
@@ -941,10 +918,6 @@ cudaError_t launch_sv_state(int part, const Dims& D, const DevPtrs& P, cudaStrea
     cudaFuncSetAttribute(sv_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     sv_finish_kernel<<<D.U, 128, smem, st>>>(D, P);
   }
-  return cudaGetLastError();
-}
-cudaError_t launch_ldlt_state(const Dims& D, const DevPtrs& P, cudaStream_t st) {
-  ldlt_state_kernel<<<D.U, 128, 0, st>>>(D, P);
   return cudaGetLastError();
 }
 cudaError_t launch_record(const Dims& D, const DevPtrs& P, const RecPtrs& R, cudaStream_t st) {
