@@ -41,6 +41,9 @@ size_t impact_smem(const Dims& D);
 bool impact_supported(const Dims& D, size_t smem_limit);
 cudaError_t launch_impact(const Dims& D, const DevPtrs& P, double* gscratch, cudaStream_t st);
 cudaError_t launch_sv_state(int part, const Dims& D, const DevPtrs& P, cudaStream_t st);  // 0 mix, 1 solve, 2 finish, 3 normals of the solve
+cudaError_t launch_impact_rows_nc1(const Dims& D, const DevPtrs& P, const double* gscratch, int gsize, int kz, int jlo, int jhi, cudaStream_t st);
+cudaError_t launch_impact_rows_nc2(const Dims& D, const DevPtrs& P, const double* gscratch, int gsize, int kz, int jlo, int jhi, cudaStream_t st);
+cudaError_t launch_impact_rows_nc4(const Dims& D, const DevPtrs& P, const double* gscratch, int gsize, int kz, int jlo, int jhi, cudaStream_t st);
 bool ldlt_own_gram(const Dims& D);  // small k: impact_ldlt_kernel forms Z'Z itself, no gram_Z contraction
 cudaError_t launch_ldlt_gram_small(const Dims& D, const DevPtrs& P, double* gscratch, cudaStream_t st);
 cudaError_t launch_ldlt_state(const Dims& D, const DevPtrs& P, const double* gscratch, cudaStream_t st);  // reads the Z'Z of gram_Z

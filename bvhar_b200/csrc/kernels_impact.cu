@@ -17,6 +17,7 @@
 //   phase 2  one warp per row: packed Cholesky of the j x j precision, the two triangular solves, the draw,
 //            the SAVS copy, and the rebuilt row of L.
 #include <algorithm>
+#include <cstdlib>
 
 #include "block_linalg.cuh"
 #include "engine.cuh"
@@ -259,6 +260,7 @@ __global__ void __launch_bounds__(IMP_WARPS * 32) impact_sv_kernel(const Dims D,
     for (int q = 0; q < IMP_WARPS; ++q) s += part[q * k + tid];
     P.znorm[(size_t)u * k + tid] = s;
   }
+  if (pw == 0) return;  // the row draws run as their own batch-wide launches (kernels_impact_rows.cu)
   __threadfence_block();
   __syncthreads();
   impact_draw_rows<true>(D, P, G, wbuf, u, &bad, pw, 0);
@@ -309,6 +311,7 @@ __global__ void __launch_bounds__(256) impact_ldlt_kernel(const Dims D, const De
   }
   if (mode & 2) return;
   for (int a = tid; a < k; a += blockDim.x) P.znorm[(size_t)u * k + a] = G[a * kz + a];
+  if (pw == 0) return;  // the row draws run as their own batch-wide launches (kernels_impact_rows.cu)
   __threadfence_block();
   __syncthreads();
   impact_draw_rows<false>(D, P, G, sm, u, &bad, pw, kz);
@@ -380,13 +383,17 @@ static int impact_warps(const Dims& D, size_t smem_limit) {  // as many of the 8
 }
 size_t impact_smem(const Dims& D) { return impact_smem_pw(D, 1); }
 
+// rows of at most 128 unknowns are drawn by the batch-wide warp-per-row kernels; wider models keep the in-CTA draws
+static bool impact_split(const Dims& D) { return D.k - 1 <= 128 && getenv("BVHAR_IMPACT_FUSED") == nullptr; }
+
 bool impact_supported(const Dims& D, size_t smem_limit) {
-  return impact_warps(D, smem_limit) >= 1 && (!D.sv || D.k <= 104);
+  return (impact_split(D) || impact_warps(D, smem_limit) >= 1) && (!D.sv || D.k <= 104);
 }
 
 cudaError_t launch_impact(const Dims& D, const DevPtrs& P, double* gscratch, cudaStream_t st) {
-  const int pw = impact_warps(D, 227 * 1024);
-  if (pw < 1) return cudaErrorInvalidConfiguration;
+  const bool split = impact_split(D);
+  const int pw = split ? 0 : impact_warps(D, 227 * 1024);
+  if (!split && pw < 1) return cudaErrorInvalidConfiguration;
   const size_t smem = impact_smem_pw(D, pw);
   const int gs = impact_gsize(D);
   if (D.sv) {
@@ -408,7 +415,12 @@ cudaError_t launch_impact(const Dims& D, const DevPtrs& P, double* gscratch, cud
     cudaFuncSetAttribute(impact_ldlt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     impact_ldlt_kernel<<<D.U, 256, smem, st>>>(D, P, gscratch, gs, (D.k + 1) & ~1, pw, ldlt_own_gram(D) ? 1 : 0);
   }
-  return cudaGetLastError();
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess || !split) return e;
+  const int kz = (D.k + 1) & ~1, jmax = D.k - 1;  // widest rows first
+  if (jmax > 64) { e = launch_impact_rows_nc4(D, P, gscratch, gs, kz, 65, jmax, st); if (e != cudaSuccess) return e; }
+  if (jmax > 32) { e = launch_impact_rows_nc2(D, P, gscratch, gs, kz, 33, std::min(jmax, 64), st); if (e != cudaSuccess) return e; }
+  return launch_impact_rows_nc1(D, P, gscratch, gs, kz, 1, std::min(jmax, 32), st);
 }
 
 // Z'Z alone (stage-wise entry points: updateState of a small-k model run on its own)
