@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(CB_THREADS, (MTW <= 4 ? 2 : 1)) coef_chol_cta_
       double dg[32];
 #pragma unroll
       for (int c = 0; c < 32; ++c) dg[c] = (lane < nc && c <= lane) ? pan[lane * 33 + c] : (c == lane ? 1.0 : 0.0);
-      const double dinv = chol32_smem(dg, colbuf, &bad);
+      const double dinv = chol32_smem_chain(dg, colbuf, &bad);
 #pragma unroll
       for (int c = 0; c < 32; ++c)
         if (lane < nc && c <= lane) pan[lane * 33 + c] = dg[c];
@@ -353,7 +353,7 @@ __global__ void __launch_bounds__(CB2_THREADS, 1) coef_chol_cta2_kernel(const Di
       double dg[32];
 #pragma unroll
       for (int c = 0; c < 32; ++c) dg[c] = (lane < nc && c <= lane) ? pan[lane * 33 + c] : (c == lane ? 1.0 : 0.0);
-      const double dinv = chol32_smem(dg, colbuf, &bad);
+      const double dinv = chol32_smem_chain(dg, colbuf, &bad);
 #pragma unroll
       for (int c = 0; c < 32; ++c)
         if (lane < nc && c <= lane) pan[lane * 33 + c] = dg[c];

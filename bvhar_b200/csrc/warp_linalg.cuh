@@ -50,6 +50,34 @@ __device__ __forceinline__ double chol32_smem(double (&dg)[32], double* colbuf, 
   return dinv;
 }
 
+// The same factorisation for a warp that runs ALONE (the CTA-per-matrix Cholesky of large designs: the other warps wait
+// for this block): there the 32-step pivot chain is the critical path, and the next pivot does not need the column
+// broadcast - lane c+1 updates its own diagonal entry with its own multiplier (bit-identical to what the broadcast
+// update writes a moment later) and shuffles it out before the shared-memory round trip, so a step of the chain is
+// shuffle + rsqrt + multiply + FMA instead of that plus store, warp barrier and load.
+__device__ __forceinline__ double chol32_smem_chain(double (&dg)[32], double* colbuf, int* bad) {
+  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  double dinv = 1.0;
+  double pc = __shfl_sync(FULL, dg[0], 0);
+#pragma unroll
+  for (int c = 0; c < 32; ++c) {
+    const double inv = rsqrt(pc), piv = pc * inv;
+    if (lane == c && !(pc > 0.0)) *bad = 1;
+    const double lc = lane > c ? dg[c] * inv : 0.0;
+    if (lane == c) { dg[c] = piv; dinv = inv; }
+    else dg[c] = lc;
+    if (c < 31) pc = __shfl_sync(FULL, fma(-lc, lc, dg[c + 1]), c + 1);  // next pivot, ahead of the broadcast
+    double* cb = colbuf + 32 * (c & 1);
+    cb[lane] = lc;
+    __syncwarp();
+#pragma unroll
+    for (int b = c + 1; b < 32; ++b) dg[b] = fma(-lc, cb[b], dg[b]);
+  }
+  __syncwarp();
+  return dinv;
+}
+
 // Column `c` (one thread per column) of the inverse of a 32 x 32 lower-triangular block whose rows are read through
 // `Lrow(r)` (pointer to L[r][0], the same address for every thread => shared-memory broadcasts) and whose reciprocal
 // diagonal is dinv[r]: forward substitution L x = e_c, 496 predicated FMAs per thread with two partial sums.  Rows >= nv
