@@ -264,15 +264,32 @@ class PackedFit:
 
         n0 = int(wn[0])
         inits = (ChainInit * num_chains)()
+        # every field of bvhar_chain_init is 8 bytes wide (a pointer or a double): the table is filled column by column through
+        # numpy views of its memory instead of ~10 ctypes attribute assignments and pointer casts per chain (thousands of chains)
+        slots = C.sizeof(ChainInit) // 8
+        raw_u = np.frombuffer(inits, dtype=np.uint64).reshape(num_chains, slots)
+        raw_f = raw_u.view(np.float64)
+        slot_of = {nm: getattr(ChainInit, nm).offset // 8 for nm, _ in ChainInit._fields_}
+        pcols: Dict[str, List[int]] = {}
+        scols: Dict[str, List[float]] = {}
+
+        def setp(field, arr):
+            pcols.setdefault(field, []).append(arr.__array_interface__["data"][0] if arr is not None else 0)
+
+        def sets(field, v):
+            scols.setdefault(field, []).append(float(v) if type(v) is float else _scalar(v))
+
+        f8 = np.float64
         for c, ini in enumerate(param_init):
-            I = inits[c]
 
             def ivec(key, n, required=True):
                 if key not in ini:
                     if required:
                         raise ValueError(f"'param_init[{c}]' lacks '{key}'")
                     return None
-                a = _f64(np.asarray(ini[key], dtype=np.float64).reshape(-1, order="F"))
+                a = ini[key]
+                if not (type(a) is np.ndarray and a.dtype == f8 and a.ndim == 1 and a.flags.c_contiguous and a.flags.aligned):
+                    a = _f64(np.asarray(a, dtype=np.float64).reshape(-1, order="F"))
                 if a.size == 1 and n > 1:
                     a = _f64(np.repeat(a, n))
                 if a.size != n:
@@ -283,42 +300,46 @@ class PackedFit:
             coef = _f64(np.asarray(ini["init_coef"], dtype=np.float64))
             if coef.shape != (d, dim):
                 raise ValueError(f"'init_coef' must be {d} x {dim}")
-            k(coef); I.init_coef = _dp(coef)
-            I.init_contem = _dp(ivec("init_contem", q))
+            k(coef); setp("init_coef", coef)
+            setp("init_contem", ivec("init_contem", q))
             if sv:
-                I.lvol_init = _dp(ivec("lvol_init", dim))
-                I.lvol_sig = _dp(ivec("lvol_sig", dim))
+                setp("lvol_init", ivec("lvol_init", dim))
+                setp("lvol_sig", ivec("lvol_sig", dim))
                 if not lvol_from_init:
                     lv = _f64(np.asarray(ini["lvol"], dtype=np.float64))
                     if lv.shape != (n0, dim):
                         raise ValueError(f"'lvol' must be {n0} x {dim}")
                     if n_win > 1 and np.any(wn != n0):
                         raise ValueError("'lvol' inits need equal window lengths; use lvol_from_init")
-                    k(lv); I.lvol = _dp(lv)
+                    k(lv); setp("lvol", lv)
             else:
-                I.init_diag = _dp(ivec("init_diag", dim))
+                setp("init_diag", ivec("init_diag", dim))
             G = len(gid)
             if pt == PRIOR_HIERMINN:
-                I.own_lambda = _scalar(ini["own_lambda"]); I.cross_lambda = _scalar(ini["cross_lambda"])
-                I.contem_lambda = _scalar(ini["contem_lambda"])
+                sets("own_lambda", ini["own_lambda"]); sets("cross_lambda", ini["cross_lambda"])
+                sets("contem_lambda", ini["contem_lambda"])
             elif pt == PRIOR_SSVS:
-                I.coef_dummy = _dp(ivec("init_coef_dummy", n_alpha)); I.coef_mixture = _dp(ivec("coef_mixture", G))
-                I.chol_mixture = _dp(ivec("chol_mixture", q)); I.coef_slab = _dp(ivec("coef_slab", n_alpha))
-                I.contem_slab = _dp(ivec("contem_slab", q))
-                I.coef_spike_scl = _scalar(ini["coef_spike_scl"]); I.chol_spike_scl = _scalar(ini["chol_spike_scl"])
+                setp("coef_dummy", ivec("init_coef_dummy", n_alpha)); setp("coef_mixture", ivec("coef_mixture", G))
+                setp("chol_mixture", ivec("chol_mixture", q)); setp("coef_slab", ivec("coef_slab", n_alpha))
+                setp("contem_slab", ivec("contem_slab", q))
+                sets("coef_spike_scl", ini["coef_spike_scl"]); sets("chol_spike_scl", ini["chol_spike_scl"])
             elif pt in (PRIOR_HORSESHOE, PRIOR_NG, PRIOR_DL):
-                I.local_sparsity = _dp(ivec("local_sparsity", n_alpha)); I.global_sparsity = _scalar(ini["global_sparsity"])
-                I.contem_local_sparsity = _dp(ivec("contem_local_sparsity", q))
-                I.contem_global_sparsity = _scalar(ini["contem_global_sparsity"])
+                setp("local_sparsity", ivec("local_sparsity", n_alpha)); sets("global_sparsity", ini["global_sparsity"])
+                setp("contem_local_sparsity", ivec("contem_local_sparsity", q))
+                sets("contem_global_sparsity", ini["contem_global_sparsity"])
                 if pt in (PRIOR_HORSESHOE, PRIOR_NG):
-                    I.group_sparsity = _dp(ivec("group_sparsity", G))
+                    setp("group_sparsity", ivec("group_sparsity", G))
                 if pt == PRIOR_NG:
-                    I.local_shape = _dp(ivec("local_shape", G)); I.contem_shape = _scalar(ini["contem_shape"])
+                    setp("local_shape", ivec("local_shape", G)); sets("contem_shape", ini["contem_shape"])
             elif pt == PRIOR_GDP:
-                I.local_sparsity = _dp(ivec("local_sparsity", n_alpha)); I.group_rate = _dp(ivec("group_rate", G))
-                I.contem_local_sparsity = _dp(ivec("contem_local_sparsity", q)); I.contem_rate = _dp(ivec("contem_rate", q))
-                I.gamma_shape = _scalar(ini["gamma_shape"]); I.gamma_rate = _scalar(ini["gamma_rate"])
-                I.contem_gamma_shape = _scalar(ini["contem_gamma_shape"]); I.contem_gamma_rate = _scalar(ini["contem_gamma_rate"])
+                setp("local_sparsity", ivec("local_sparsity", n_alpha)); setp("group_rate", ivec("group_rate", G))
+                setp("contem_local_sparsity", ivec("contem_local_sparsity", q)); setp("contem_rate", ivec("contem_rate", q))
+                sets("gamma_shape", ini["gamma_shape"]); sets("gamma_rate", ini["gamma_rate"])
+                sets("contem_gamma_shape", ini["contem_gamma_shape"]); sets("contem_gamma_rate", ini["contem_gamma_rate"])
+        for nm, col in pcols.items():
+            raw_u[:, slot_of[nm]] = col
+        for nm, col in scols.items():
+            raw_f[:, slot_of[nm]] = col
         k(inits)
         D.init = C.cast(inits, C.POINTER(ChainInit))
         D.seed_chain = seeds.ctypes.data_as(c_up)

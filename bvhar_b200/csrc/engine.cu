@@ -72,6 +72,37 @@ inline double* lvol_stage_buffer(size_t count) {
   }
   return buf;
 }
+// Host staging vectors of an engine's set-up are recycled through a small process-wide pool: a fresh 10 MB std::vector
+// costs more in page faults than the loop that fills it (the set-up of 1 024 chains stages ~50 MB).
+struct HostStagePool {
+  std::mutex m;
+  std::vector<std::vector<double>> free;
+  // a vector of n elements; `fill`: every element is set to `value`, otherwise the contents are unspecified (caller overwrites all)
+  std::vector<double> take(size_t n, bool fill, double value = 0.0) {
+    std::vector<double> v;
+    {
+      std::lock_guard<std::mutex> lk(m);
+      size_t best = free.size();
+      for (size_t i = 0; i < free.size(); ++i)
+        if (free[i].capacity() >= n && (best == free.size() || free[i].capacity() < free[best].capacity())) best = i;
+      if (best < free.size()) { v = std::move(free[best]); free.erase(free.begin() + best); }
+    }
+    if (fill) v.assign(n, value);
+    else v.resize(n);
+    return v;
+  }
+  void give(std::vector<double>&& v) {
+    if (v.capacity() < (1u << 16)) return;
+    std::lock_guard<std::mutex> lk(m);
+    if (free.size() < 12) free.push_back(std::move(v));
+  }
+};
+inline HostStagePool& host_stage_pool() { static HostStagePool p; return p; }
+struct HostStageReturn {  // hands the listed vectors back when the set-up leaves scope (any exit path)
+  std::vector<std::vector<double>*> vs;
+  ~HostStageReturn() { for (auto* v : vs) host_stage_pool().give(std::move(*v)); }
+};
+
 template <typename T>
 struct DevBuf {
   T* p = nullptr;
@@ -253,7 +284,7 @@ struct bvhar_fit {
     if (coef_big) {
       if (D.sv && !direct_p) LAUNCH("coef_pbuild", launch_coef_v2(0, D, P, Pfac.p, Qn.p, smem_limit, st));
       if (fork) { CU(cudaStreamWaitEvent(st, evf[1], 0)); if (D.sv) CU(cudaStreamWaitEvent(st, evf[3], 0)); }
-      LAUNCH("coef_chol_cta", launch_coef_big(1, D, P, Pfac.p, hscr.p, smem_limit, st));
+      LAUNCH("coef_chol_cta", launch_coef_big(1, D, P, Pfac.p, hscr.p, smem_limit, st)); ++nl;  // + invert_diag_kernel
       LAUNCH("coef_seq_big", launch_coef_big(2, D, P, Pfac.p, hscr.p, smem_limit, st));
     } else if (coef_v2) {
       if (D.sv) LAUNCH("coef_pbuild", launch_coef_v2(0, D, P, Pfac.p, Qn.p, smem_limit, st));
@@ -266,7 +297,7 @@ struct bvhar_fit {
     }
     LAUNCH("latent_dmma", launch_dgemm_tn(g3, st));
     if (!D.sv && !ldlt_own_gram(D)) LAUNCH("gram_Z_dmma", launch_dgemm_tn(gz, st));
-    if (D.k > 1) LAUNCH("impact_draw", launch_impact(D, P, gscratch.p, st));
+    if (D.k > 1) { LAUNCH("impact_draw", launch_impact(D, P, gscratch.p, st)); nl += impact_launches(D) - 1; }
     else if (!D.sv) LAUNCH("gram_Z", launch_ldlt_gram_small(D, P, gscratch.p, st));  // univariate LDLT: the state draw still reads Z'Z
     if (D.sv) {
       LAUNCH("sv_mix", launch_sv_state(0, D, P, st));
@@ -364,9 +395,16 @@ int build(const bvhar_fit_desc* d, bvhar_fit** out) {
     return fail(BVHAR_ERR_BAD_ARG, "missing required pointer in descriptor");
   CU(cudaSetDevice(d->device));
   pool_setup(d->device);
-  cudaDeviceProp prop;
-  CU(cudaGetDeviceProperties(&prop, d->device));
-  if (prop.major < 10) return fail(BVHAR_ERR_CUDA, "bvhar_b200 is built for sm_100a (B200) only");
+  // two attributes, cached per device: cudaGetDeviceProperties fills the whole property struct on every call and showed up
+  // as tens of milliseconds of an engine's set-up when the device was busy
+  static int cc_major[64] = {}, smem_optin[64] = {};
+  const int dv = d->device;
+  if (dv < 0 || dv >= 64) return fail(BVHAR_ERR_BAD_ARG, "device index out of range");
+  if (!cc_major[dv]) {
+    CU(cudaDeviceGetAttribute(&cc_major[dv], cudaDevAttrComputeCapabilityMajor, dv));
+    CU(cudaDeviceGetAttribute(&smem_optin[dv], cudaDevAttrMaxSharedMemoryPerBlockOptin, dv));
+  }
+  if (cc_major[dv] < 10) return fail(BVHAR_ERR_CUDA, "bvhar_b200 is built for sm_100a (B200) only");
 
   const bool timing = getenv("BVHAR_TIMING") != nullptr;
   auto now = [] { return std::chrono::steady_clock::now(); };
@@ -380,7 +418,7 @@ int build(const bvhar_fit_desc* d, bvhar_fit** out) {
   };
   std::unique_ptr<bvhar_fit> F(new bvhar_fit);
   F->device = d->device;
-  F->smem_limit = prop.sharedMemPerBlockOptin;
+  F->smem_limit = (size_t)smem_optin[dv];
   F->num_iter = d->num_iter; F->num_burn = d->num_burn; F->thin = d->thin < 1 ? 1 : d->thin;
   F->rec_mask = d->record_mask;
   Dims& D = F->D;
@@ -507,8 +545,10 @@ int build(const bvhar_fit_desc* d, bvhar_fit** out) {
 
   lap("shared data + uploads");
   // ---- per-unit state from the chain inits (McmcTriangular ctor tri.h:40-71 and prior ctors) ----
-  std::vector<double> hA((size_t)D.W * dd * D.ldM, 0.0), halpha((size_t)U * N), hc((size_t)U * k, 0.0), hprec((size_t)U * k * dd);
-  std::vector<double> hcontem((size_t)U * q), hL((size_t)U * k * k, 0.0), hcp((size_t)U * q, 1.0);
+  HostStagePool& hpool = host_stage_pool();
+  std::vector<double> hA = hpool.take((size_t)D.W * dd * D.ldM, true), halpha = hpool.take((size_t)U * N, false), hc((size_t)U * k, 0.0),
+                      hprec = hpool.take((size_t)U * k * dd, false);
+  std::vector<double> hcontem((size_t)U * q), hL = hpool.take((size_t)U * k * k, true), hcp((size_t)U * q, 1.0);
   std::vector<double> hH, hli, hls, hdiag;
   // SV: the n x k `lvol` blocks of the chains are staged series-major ([chain][series][t], a plain memcpy per
   // chain) and transposed into the time-major layout on the device; replicated inits are k values per unit.
@@ -518,13 +558,14 @@ int build(const bvhar_fit_desc* d, bvhar_fit** out) {
   if (D.sv) { hli.resize((size_t)U * k); hls.resize((size_t)U * k); }
   else hdiag.resize((size_t)U * k);
   std::vector<double> hhN[4], hhG[3], hhq[4], hhs((size_t)U * HS_SLOTS, 0.0);
+  HostStageReturn hret{{&hA, &halpha, &hprec, &hL, &hhN[0], &hhN[1]}};
   // (the N-long prior vectors are materialised on the host only for the slots a prior actually initialises: a fresh
   // 10 MB vector costs more in page faults than its upload; untouched slots are zero-filled on the device)
   for (auto& v : hhG) v.assign((size_t)U * G, 0.0);
   for (auto& v : hhq) v.assign((size_t)U * q, 0.0);
   {  // which N-long slots the prior initialises (allocated up front: the unit loop below runs on several threads)
     const bvhar_chain_init& in0 = d->init[0];
-    auto useN = [&](int slot, const double* src) { if (src) hhN[slot].assign((size_t)U * N, 0.0); };
+    auto useN = [&](int slot, const double* src) { if (src) hhN[slot] = hpool.take((size_t)U * N, false); };  // every unit copies all N
     switch (D.prior) {
       case 2: useN(0, in0.coef_dummy); useN(1, in0.coef_slab); break;
       case 3: case 5: case 6: case 7: useN(0, in0.local_sparsity); break;

@@ -40,6 +40,7 @@ int impact_gsize(const Dims& D);
 size_t impact_smem(const Dims& D);
 bool impact_supported(const Dims& D, size_t smem_limit);
 cudaError_t launch_impact(const Dims& D, const DevPtrs& P, double* gscratch, cudaStream_t st);
+int impact_launches(const Dims& D);  // kernels one launch_impact call starts
 cudaError_t launch_sv_state(int part, const Dims& D, const DevPtrs& P, cudaStream_t st);  // 0 mix, 1 solve, 2 finish, 3 normals of the solve
 cudaError_t launch_impact_rows_nc1(const Dims& D, const DevPtrs& P, const double* gscratch, int gsize, int kz, int jlo, int jhi, cudaStream_t st);
 cudaError_t launch_impact_rows_nc2(const Dims& D, const DevPtrs& P, const double* gscratch, int gsize, int kz, int jlo, int jhi, cudaStream_t st);

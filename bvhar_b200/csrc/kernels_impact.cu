@@ -390,6 +390,13 @@ bool impact_supported(const Dims& D, size_t smem_limit) {
   return (impact_split(D) || impact_warps(D, smem_limit) >= 1) && (!D.sv || D.k <= 104);
 }
 
+// kernels one launch_impact call starts (the engine's launch counter)
+int impact_launches(const Dims& D) {
+  if (!impact_split(D)) return 1;
+  const int jmax = D.k - 1;
+  return 1 + (jmax > 64) + (jmax > 32) + 1;
+}
+
 cudaError_t launch_impact(const Dims& D, const DevPtrs& P, double* gscratch, cudaStream_t st) {
   const bool split = impact_split(D);
   const int pw = split ? 0 : impact_warps(D, 227 * 1024);
