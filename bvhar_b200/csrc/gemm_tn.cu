@@ -290,10 +290,12 @@ __global__ void __launch_bounds__(TB_THREADS, 1) dgemm_tn_bulk_kernel(const Gemm
     const int M = t.M, m0 = t.m0, n0 = t.n0;
     double* C = g.C + (g.c_off ? g.c_off[t.grp] : 0);
     const long long yoff = (g.epi == EPI_Y_MINUS && g.y_off) ? g.y_off[t.grp] : 0;
-    auto store2 = [&](int row, int col, double v0, double v1) {
+    // (ym0, ym1: col % ymod and (col + 1) % ymod, computed once per column pair of the tile - the runtime modulo cost as
+    // much as the rest of the epilogue when it was evaluated per stored element)
+    auto store2 = [&](int row, int col, double v0, double v1, int ym0, int ym1) {
       if (g.epi == EPI_Y_MINUS) {
-        if (col < g.N) v0 = g.Y[yoff + (size_t)row * g.ldy + (col % g.ymod)] - v0;
-        if (col + 1 < g.N) v1 = g.Y[yoff + (size_t)row * g.ldy + ((col + 1) % g.ymod)] - v1;
+        if (col < g.N) v0 = g.Y[yoff + (size_t)row * g.ldy + ym0] - v0;
+        if (col + 1 < g.N) v1 = g.Y[yoff + (size_t)row * g.ldy + ym1] - v1;
       }
       double* dst = C + (size_t)row * g.ldc + col;
       if (col + 1 < g.N && ((g.ldc & 1) == 0) && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
@@ -332,12 +334,17 @@ __global__ void __launch_bounds__(TB_THREADS, 1) dgemm_tn_bulk_kernel(const Gemm
         __syncwarp();
         if (lane == 0) mbar_arrive(empty + s);
       }
+      int qm[4][2] = {};
+      if (g.epi == EPI_Y_MINUS) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { qm[j][0] = (n0 + j * 8 + fc * 2) % g.ymod; qm[j][1] = (n0 + j * 8 + fc * 2 + 1) % g.ymod; }
+      }
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
         const int row = m0 + warp * 16 + i * 8 + fr;
         if (row >= M) continue;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) store2(row, n0 + j * 8 + fc * 2, qa[i][j][0], qa[i][j][1]);
+        for (int j = 0; j < 4; ++j) store2(row, n0 + j * 8 + fc * 2, qa[i][j][0], qa[i][j][1], qm[j][0], qm[j][1]);
       }
       continue;
     }
@@ -383,12 +390,17 @@ __global__ void __launch_bounds__(TB_THREADS, 1) dgemm_tn_bulk_kernel(const Gemm
       __syncwarp();
       if (lane == 0) mbar_arrive(empty + s);
     }
+    int ym[4][2] = {};
+    if (g.epi == EPI_Y_MINUS) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { ym[j][0] = (n0 + wn0 + j * 8 + fc * 2) % g.ymod; ym[j][1] = (n0 + wn0 + j * 8 + fc * 2 + 1) % g.ymod; }
+    }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int row = m0 + (PART ? (2 * i + wr) * 8 : wr * 64 + i * 8) + fr;
       if (row >= M) continue;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) store2(row, n0 + wn0 + j * 8 + fc * 2, acc[i][j][0], acc[i][j][1]);
+      for (int j = 0; j < 4; ++j) store2(row, n0 + wn0 + j * 8 + fc * 2, acc[i][j][0], acc[i][j][1], ym[j][0], ym[j][1]);
     }
   }
 }
