@@ -227,7 +227,10 @@ __device__ __forceinline__ int work_decode(const GemmArgs& g, int w, int mtiles,
   return (t.m0 < t.M && t.n0 < g.N) ? 2 : 1;
 }
 
-template <bool PART>
+// NARROW (N <= 64, full row tiles): the eight consumer warps form a 4 x 2 grid (32 rows x 32 columns each) instead of
+// 2 x 4: with the wide layout a right-hand side of 61 columns leaves the warp columns 2 and 3 - and with them two of the
+// SM's four tensor sub-partitions - without a single useful DMMA.
+template <bool PART, bool NARROW = false>
 __global__ void __launch_bounds__(TB_THREADS, 1) dgemm_tn_bulk_kernel(const GemmArgs g, const int mtiles, const int ntiles, const int total,
                                                                       const int split_from) {
   extern __shared__ __align__(128) unsigned char gemm_smem_raw[];
@@ -280,7 +283,8 @@ __global__ void __launch_bounds__(TB_THREADS, 1) dgemm_tn_bulk_kernel(const Gemm
   }
 
   // ---------------- consumer warps ----------------
-  const int wr = warp >> 2, wn0 = (warp & 3) * 32;
+  constexpr int NMT = NARROW ? 4 : 8, WROWS = NARROW ? 32 : 64;  // m-tiles and rows per warp (full-tile path)
+  const int wr = NARROW ? warp >> 1 : warp >> 2, wn0 = NARROW ? (warp & 1) * 32 : (warp & 3) * 32;
   const int fr = lane >> 2, fc = lane & 3;
   for (int w = blockIdx.x;; w += gridDim.x) {
     TileCoord t;
@@ -356,21 +360,25 @@ __global__ void __launch_bounds__(TB_THREADS, 1) dgemm_tn_bulk_kernel(const Gemm
     for (int i = 0; i < 8; ++i)
 #pragma unroll
       for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    // a warp whose 32 columns lie past N (narrow right-hand sides: N = 61 leaves two of the four warp columns empty) only
+    // keeps the barrier protocol going: its DMMAs would take the tensor pipe from the warps that have columns
+    const bool dead = n0 + wn0 >= g.N;
     for (int kt = 0; kt < nk; ++kt, ++it) {
       const int s = it % TB_STAGES;
       mbar_wait(full + s, (it / TB_STAGES) & 1);
       const double* as = stages + (size_t)s * TB_STAGE_DOUBLES;
       const double* bs = as + GBK * TB_ROW;
-      if (!PART) {
+      if (dead) {
+      } else if (!PART) {
 #pragma unroll
         for (int kk = 0; kk < GBK; kk += 4) {
-          double af[8], bf[4];
+          double af[NMT], bf[4];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) af[i] = as[(kk + fc) * TB_ROW + wr * 64 + i * 8 + fr];
+          for (int i = 0; i < NMT; ++i) af[i] = as[(kk + fc) * TB_ROW + wr * WROWS + i * 8 + fr];
 #pragma unroll
           for (int j = 0; j < 4; ++j) bf[j] = bs[(kk + fc) * TB_ROW + wn0 + j * 8 + fr];
 #pragma unroll
-          for (int i = 0; i < 8; ++i)
+          for (int i = 0; i < NMT; ++i)
 #pragma unroll
             for (int j = 0; j < 4; ++j) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
         }
@@ -396,8 +404,8 @@ __global__ void __launch_bounds__(TB_THREADS, 1) dgemm_tn_bulk_kernel(const Gemm
       for (int j = 0; j < 4; ++j) { ym[j][0] = (n0 + wn0 + j * 8 + fc * 2) % g.ymod; ym[j][1] = (n0 + wn0 + j * 8 + fc * 2 + 1) % g.ymod; }
     }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int row = m0 + (PART ? (2 * i + wr) * 8 : wr * 64 + i * 8) + fr;
+    for (int i = 0; i < (PART ? 8 : NMT); ++i) {
+      const int row = m0 + (PART ? (2 * i + wr) * 8 : wr * WROWS + i * 8) + fr;
       if (row >= M) continue;
 #pragma unroll
       for (int j = 0; j < 4; ++j) store2(row, n0 + wn0 + j * 8 + fc * 2, acc[i][j][0], acc[i][j][1], ym[j][0], ym[j][1]);
@@ -421,6 +429,7 @@ cudaError_t launch_dgemm_tn(const GemmArgs& g, cudaStream_t st) {
       cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
       cudaFuncSetAttribute(dgemm_tn_bulk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TB_SMEM);
       cudaFuncSetAttribute(dgemm_tn_bulk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TB_SMEM);
+      cudaFuncSetAttribute(dgemm_tn_bulk_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TB_SMEM);
     }
     const int mtiles = (g.M + GBM - 1) / GBM, ntiles = (g.N + GBN - 1) / GBN;
     const long long total = (long long)mtiles * ntiles * g.groups;
@@ -429,6 +438,7 @@ cudaError_t launch_dgemm_tn(const GemmArgs& g, cudaStream_t st) {
     const long long rem = total % grid;
     const long long split_from = (total > grid && rem > 0 && 2 * rem <= grid) ? total - rem : total;
     if (part) dgemm_tn_bulk_kernel<true><<<grid, TB_THREADS, TB_SMEM, st>>>(g, mtiles, ntiles, (int)total, (int)split_from);
+    else if (g.N <= 64) dgemm_tn_bulk_kernel<false, true><<<grid, TB_THREADS, TB_SMEM, st>>>(g, mtiles, ntiles, (int)total, (int)split_from);
     else dgemm_tn_bulk_kernel<false><<<grid, TB_THREADS, TB_SMEM, st>>>(g, mtiles, ntiles, (int)total, (int)split_from);
     return cudaGetLastError();
   }
