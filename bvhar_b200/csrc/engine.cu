@@ -5,6 +5,7 @@
 // (window, chain) unit advances together, one fixed kernel sequence per sweep on one CUDA stream,
 // captured once into a CUDA graph and replayed.  There is no CPU path: every entry point fails with
 // BVHAR_ERR_CUDA when no device is usable.
+#include <nvtx3/nvToolsExt.h>  // header-only NVTX v3: ranges are no-ops unless a tool (ncu --nvtx, Nsight Systems) is attached
 #include <algorithm>
 #include <chrono>
 #include <cmath>
@@ -74,6 +75,13 @@ inline double* lvol_stage_buffer(size_t count) {
 }
 // Host staging vectors of an engine's set-up are recycled through a small process-wide pool: a fresh 10 MB std::vector
 // costs more in page faults than the loop that fills it (the set-up of 1 024 chains stages ~50 MB).
+// NVTX range around one updater's launches: visible to `ncu --nvtx` / Nsight Systems on the eager path (set_profiling or the
+// first sweep of each kind; a replayed CUDA graph carries no host ranges).  Without a tool attached the calls are no-ops.
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
+
 struct HostStagePool {
   std::mutex m;
   std::vector<std::vector<double>> free;
@@ -254,6 +262,7 @@ struct bvhar_fit {
     do {                                                                       \
       cudaEvent_t ea__ = nullptr, eb__ = nullptr;                              \
       if (profiling) { ea__ = prof_event(); eb__ = prof_event(); cudaEventRecord(ea__, st); } \
+      NvtxRange nvtx__(name);  /* one range per updater launch */ \
       CU(expr);                                                                \
       if (profiling) { cudaEventRecord(eb__, st); prof_pending.push_back({prof_id(name), ea__, eb__}); } \
       ++nl;                                                                    \
