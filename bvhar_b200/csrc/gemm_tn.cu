@@ -338,17 +338,18 @@ __global__ void __launch_bounds__(TB_THREADS, 1) dgemm_tn_bulk_kernel(const Gemm
         __syncwarp();
         if (lane == 0) mbar_arrive(empty + s);
       }
-      int qm[4][2] = {};
-      if (g.epi == EPI_Y_MINUS) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) { qm[j][0] = (n0 + j * 8 + fc * 2) % g.ymod; qm[j][1] = (n0 + j * 8 + fc * 2 + 1) % g.ymod; }
-      }
+      const int qbase = g.epi == EPI_Y_MINUS ? (n0 + fc * 2) % g.ymod : 0;  // one runtime modulo per tile; the columns advance by 8
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
         const int row = m0 + warp * 16 + i * 8 + fr;
         if (row >= M) continue;
+        int cm = qbase;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) store2(row, n0 + j * 8 + fc * 2, qa[i][j][0], qa[i][j][1], qm[j][0], qm[j][1]);
+        for (int j = 0; j < 4; ++j) {
+          store2(row, n0 + j * 8 + fc * 2, qa[i][j][0], qa[i][j][1], cm, cm + 1 == g.ymod ? 0 : cm + 1);
+          cm += 8;
+          while (cm >= g.ymod && g.epi == EPI_Y_MINUS) cm -= g.ymod;
+        }
       }
       continue;
     }
@@ -361,15 +362,23 @@ __global__ void __launch_bounds__(TB_THREADS, 1) dgemm_tn_bulk_kernel(const Gemm
 #pragma unroll
       for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
     // a warp whose 32 columns lie past N (narrow right-hand sides: N = 61 leaves two of the four warp columns empty) only
-    // keeps the barrier protocol going: its DMMAs would take the tensor pipe from the warps that have columns
-    const bool dead = n0 + wn0 >= g.N;
+    // keeps the barrier protocol going: its DMMAs would take the tensor pipe from the warps that have columns.  (Its own
+    // loop: a branch inside the hot loop below cost the full-width contractions 3 - 8 %.)
+    if (n0 + wn0 >= g.N) {
+      for (int kt = 0; kt < nk; ++kt, ++it) {
+        const int s = it % TB_STAGES;
+        mbar_wait(full + s, (it / TB_STAGES) & 1);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty + s);
+      }
+      continue;
+    }
     for (int kt = 0; kt < nk; ++kt, ++it) {
       const int s = it % TB_STAGES;
       mbar_wait(full + s, (it / TB_STAGES) & 1);
       const double* as = stages + (size_t)s * TB_STAGE_DOUBLES;
       const double* bs = as + GBK * TB_ROW;
-      if (dead) {
-      } else if (!PART) {
+      if (!PART) {
 #pragma unroll
         for (int kk = 0; kk < GBK; kk += 4) {
           double af[NMT], bf[4];
@@ -398,17 +407,18 @@ __global__ void __launch_bounds__(TB_THREADS, 1) dgemm_tn_bulk_kernel(const Gemm
       __syncwarp();
       if (lane == 0) mbar_arrive(empty + s);
     }
-    int ym[4][2] = {};
-    if (g.epi == EPI_Y_MINUS) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) { ym[j][0] = (n0 + wn0 + j * 8 + fc * 2) % g.ymod; ym[j][1] = (n0 + wn0 + j * 8 + fc * 2 + 1) % g.ymod; }
-    }
+    const int ybase = g.epi == EPI_Y_MINUS ? (n0 + wn0 + fc * 2) % g.ymod : 0;  // one runtime modulo per tile; the columns advance by 8
 #pragma unroll
     for (int i = 0; i < (PART ? 8 : NMT); ++i) {
       const int row = m0 + (PART ? (2 * i + wr) * 8 : wr * WROWS + i * 8) + fr;
       if (row >= M) continue;
+      int cm = ybase;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) store2(row, n0 + wn0 + j * 8 + fc * 2, acc[i][j][0], acc[i][j][1], ym[j][0], ym[j][1]);
+      for (int j = 0; j < 4; ++j) {
+        store2(row, n0 + wn0 + j * 8 + fc * 2, acc[i][j][0], acc[i][j][1], cm, cm + 1 == g.ymod ? 0 : cm + 1);
+        cm += 8;
+        while (cm >= g.ymod && g.epi == EPI_Y_MINUS) cm -= g.ymod;
+      }
     }
   }
 }

@@ -39,7 +39,8 @@ __device__ __forceinline__ void pair_of(int pid, int& a, int& b) {  // pid = a(a
   b = pid - tri_idx(a, 0);
 }
 
-constexpr int IMP_TT = 32;      // time points per staged tile
+constexpr int IMP_TT_SMALL = 64, IMP_TT_LARGE = 32;  // time points per staged tile: 64 when the tile is narrow (k <= 32), else 32
+__host__ __device__ constexpr int imp_tt(int nt) { return nt <= 4 ? IMP_TT_SMALL : IMP_TT_LARGE; }
 constexpr int IMP_STAGES = 3;   // cp.async pipeline depth
 constexpr int IMP_WARPS = 8;
 
@@ -106,7 +107,7 @@ __device__ void impact_draw_rows(const Dims& D, const DevPtrs& P, const double* 
 template <int NT, int C>
 __device__ __forceinline__ void impact_slot_steps(double (*acc)[2], const double* __restrict__ za, const double* __restrict__ zb,
                                                   const double* __restrict__ dr) {
-  constexpr int KPT = 8 * NT + 4;
+  constexpr int KPT = 8 * NT + 4, IMP_TT = imp_tt(NT);
 #pragma unroll
   for (int s = 0; s < IMP_TT / 4; ++s) {
     const double af = za[s * 4 * KPT] * zb[s * 4 * KPT];
@@ -129,7 +130,7 @@ struct ImpactSlot<NT, 0> {
 template <int NT, int IMP_MT>
 __global__ void __launch_bounds__(IMP_WARPS * 32) impact_sv_kernel(const Dims D, const DevPtrs P, double* gscratch, const int gsize, const int pw) {
   extern __shared__ __align__(16) double sm[];
-  constexpr int KPT = 8 * NT + 4;
+  constexpr int KPT = 8 * NT + 4, IMP_TT = imp_tt(NT);
   constexpr int NCOL = (8 * NT + 31) / 32;  // columns of Z per lane in the norm accumulation
   const int u = blockIdx.x, w = u / D.C, c = u % D.C;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -211,14 +212,15 @@ __global__ void __launch_bounds__(IMP_WARPS * 32) impact_sv_kernel(const Dims D,
       }
       const double* zs = zt + (tile % IMP_STAGES) * IMP_TT * KPT + fc * KPT;
       const double* ds = dt + (tile % IMP_STAGES) * IMP_TT * KPT + fc * KPT + fr;
-      if (mt0 == 0) {  // squared column norms: warp w takes rows 4 w .. 4 w + 3 of the tile, lane l the columns l, l + 32, ...
-        const double* zn = zt + (tile % IMP_STAGES) * IMP_TT * KPT + 4 * warp * KPT;
+      if (mt0 == 0) {  // squared column norms: warp w takes rows RPW w .. RPW w + RPW - 1 of the tile, lane l the columns l, l + 32, ...
+        constexpr int RPW = IMP_TT / IMP_WARPS;
+        const double* zn = zt + (tile % IMP_STAGES) * IMP_TT * KPT + RPW * warp * KPT;
 #pragma unroll
         for (int q = 0; q < NCOL; ++q) {
           const int m = lane + 32 * q;
           if (m < k) {
 #pragma unroll
-            for (int r = 0; r < 4; ++r) nacc[q] = fma(zn[r * KPT + m], zn[r * KPT + m], nacc[q]);
+            for (int r = 0; r < RPW; ++r) nacc[q] = fma(zn[r * KPT + m], zn[r * KPT + m], nacc[q]);
           }
         }
       }
@@ -373,7 +375,7 @@ static int impact_nt_bucket(int k) {
 static size_t impact_smem_pw(const Dims& D, int pw) {
   const int k = D.k;
   const size_t work = (size_t)pw * (k * (k + 1) / 2 + 3 * k);
-  if (D.sv) return (2 * (size_t)IMP_STAGES * IMP_TT * (8 * impact_nt_bucket(k) + 4) + ((k + 1) & ~1) + work) * sizeof(double);
+  if (D.sv) return (2 * (size_t)IMP_STAGES * imp_tt(impact_nt_bucket(k)) * (8 * impact_nt_bucket(k) + 4) + ((k + 1) & ~1) + work) * sizeof(double);
   return std::max(work, (size_t)16 * k) * sizeof(double);
 }
 static int impact_warps(const Dims& D, size_t smem_limit) {  // as many of the 8 warps as fit a workspace
