@@ -29,6 +29,66 @@ __device__ __forceinline__ int rows_row_off(int j) {  // sum_{j'<j} (j'(j'+1)/2 
   return ((j - 1) * j * (2 * j - 1) / 6 + 3 * (j - 1) * j / 2) / 2;
 }
 
+#if BV_NC == 1
+// j <= 32: the whole system is one register block (lane = row).  Same arithmetic as chol_blocked_warp<1> +
+// precision_solve_blocked<1>, but every 32-step chain stops at step j (warp-uniform exit: the unrolled bodies keep their
+// static register indices) - the rows of a k = 20 model average 10 unknowns, a third of the block.
+__device__ __forceinline__ void small_system_solve(double* Pw, const int j, const double* r, const double* z, double* x, double* colbuf, int* bad) {
+  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const bool va = lane < j;
+  const int ra = lane * (lane + 1) / 2;
+  double dg[32];
+#pragma unroll
+  for (int c = 0; c < 32; ++c) dg[c] = (va && c <= lane) ? Pw[ra + c] : (c == lane ? 1.0 : 0.0);
+  // Cholesky, pivot chain without the shared-memory round trip (chol32_smem_chain)
+  double dinv = 1.0;
+  double pc = __shfl_sync(FULL, dg[0], 0);
+#pragma unroll
+  for (int c = 0; c < 32; ++c) {
+    if (c >= j) break;
+    const double inv = rsqrt(pc), piv = pc * inv;
+    if (lane == c && !(pc > 0.0)) *bad = 1;
+    const double lc = lane > c ? dg[c] * inv : 0.0;
+    if (lane == c) { dg[c] = piv; dinv = inv; }
+    else dg[c] = lc;
+    if (c < 31) pc = __shfl_sync(FULL, fma(-lc, lc, dg[c + 1]), c + 1);
+    double* cb = colbuf + 32 * (c & 1);
+    cb[lane] = lc;
+    __syncwarp();
+#pragma unroll
+    for (int b = c + 1; b < 32; ++b) dg[b] = fma(-lc, cb[b], dg[b]);
+  }
+  __syncwarp();
+  // the factor back to shared memory (the backward solve reads columns)
+#pragma unroll
+  for (int c = 0; c < 32; ++c)
+    if (va && c <= lane) Pw[ra + c] = dg[c];
+  __syncwarp();
+  // forward: L y = r, lanes own rows, unknowns scaled by 1 / L_aa
+  double y = va ? r[lane] * dinv : 0.0;
+#pragma unroll
+  for (int c = 0; c < 32; ++c) {
+    if (c >= j) break;
+    const double yc = __shfl_sync(FULL, y, c);
+    if (lane > c) y = fma(-(dg[c] * dinv), yc, y);
+  }
+  // backward: L' x = y + z, lanes own columns
+  double xv = va ? (y + z[lane]) * dinv : 0.0;
+  double dgT[32];
+#pragma unroll
+  for (int c = 0; c < 32; ++c) dgT[c] = (c > lane && c < j) ? Pw[c * (c + 1) / 2 + lane] * dinv : 0.0;
+#pragma unroll
+  for (int c = 31; c >= 0; --c) {
+    if (c >= j) continue;
+    const double xc = __shfl_sync(FULL, xv, c);
+    xv = fma(-dgT[c], xc, xv);
+  }
+  if (va) x[lane] = xv;
+  __syncwarp();
+}
+#endif
+
 __global__ void __launch_bounds__(32 * IR_MAXW) BV_CAT(impact_rows_kernel_nc, BV_NC)(const Dims D, const DevPtrs P, const double* __restrict__ gscratch,
                                                                                     const int gsize, const int kz, const int jlo, const int nrows,
                                                                                     const int wstride) {
@@ -65,9 +125,13 @@ __global__ void __launch_bounds__(32 * IR_MAXW) BV_CAT(impact_rows_kernel_nc, BV
     z[b] = rng.normal_elem(ST_IMPACT_Z, (uint32_t)(id + b));
   }
   __syncwarp();
+#if BV_NC == 1
+  small_system_solve(Pw, j, r, z, x, colbuf[warp], &bad[warp]);
+#else
   chol_blocked_warp<NC>(Pw, j, &bad[warp], colbuf[warp]);
   precision_solve_blocked<NC>(Pw, j, r, z, x);
   __syncwarp();
+#endif
   double* Lu = P.L + (size_t)u * k * k;
   for (int b = lane; b < k; b += 32) {
     double val = b == j ? 1.0 : 0.0;
