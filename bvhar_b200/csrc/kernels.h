@@ -7,6 +7,7 @@
 namespace bvhar {
 
 cudaError_t launch_sv_prep(const Dims& D, const DevPtrs& P, cudaStream_t st);
+cudaError_t launch_sv_finish(const Dims& D, const DevPtrs& P, cudaStream_t st);  // sigma_h^2 and h_0 (kernels_sv_finish.cu)
 cudaError_t launch_sv_wmix(const Dims& D, const DevPtrs& P, double* Wt, cudaStream_t st);  // weights of the direct P_j build (large-design SV path)
 bool coef_plan(const Dims& D, size_t smem_limit, int* CH_out, bool* vglobal_out, bool* pglobal_out);
 cudaError_t launch_coef(const Dims& D, const DevPtrs& P, double* vscratch, double* pscratch, size_t smem_limit, cudaStream_t st);

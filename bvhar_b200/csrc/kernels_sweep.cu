@@ -488,54 +488,7 @@ __global__ void __launch_bounds__(128) sv_solve_kernel(const Dims D, const DevPt
   P.znorm[(size_t)D.U * D.k + (size_t)u * D.k + i] = ssq;  // per-series sum of squared increments, consumed by sv_finish
 }
 
-// varsv_sigh (draw.h:498-512, the squared increments are summed over ALL series, integer n/2) and
-// varsv_h0 (draw.h:523-537, dense k x k precision).
-__global__ void __launch_bounds__(128) sv_finish_kernel(const Dims D, const DevPtrs P) {
-  extern __shared__ __align__(16) double sm[];
-  __shared__ double scratch[40];
-  __shared__ int bad;
-  const int u = blockIdx.x, w = u / D.C, c = u % D.C;
-  const int k = D.k, n = P.win_n[w];
-  const long long off = P.win_off[w] + (long long)c * k;
-  const Philox rng(P.seeds[u], (uint32_t)(D.ubase + u), *P.iter);
-  double* Kp = sm;                      // packed k(k+1)/2
-  double* r = Kp + k * (k + 1) / 2;
-  double* z = r + k;
-  double* x = z + k;
-  double* sig = x + k;
-  if (threadIdx.x == 0) bad = 0;
-  // S = sum over ALL series and t of (h_t - h_{t-1})^2 (quirk draw.h:508): the per-series sums come from sv_solve
-  double ss = 0.0;
-  for (int i = 0; i < k; ++i) ss += P.znorm[(size_t)D.U * k + (size_t)u * k + i];  // fixed order: deterministic
-  (void)scratch; (void)n;
-  for (int i = threadIdx.x; i < k; i += blockDim.x) {
-    const double s = 1.0 / rng.gamma(ST_SV_SIGH, (uint32_t)i, P.sig_shp[i] + (double)(n / 2), 1.0 / (P.sig_scl[i] + ss / 2));
-    sig[i] = s;
-    P.lvol_sig[(size_t)u * k + i] = s;
-  }
-  __syncthreads();
-  for (int p = threadIdx.x; p < k * (k + 1) / 2; p += blockDim.x) {
-    int a = (int)((sqrt(8.0 * p + 1.0) - 1.0) * 0.5);
-    while (tri_idx(a + 1, 0) <= p) ++a;
-    while (tri_idx(a, 0) > p) --a;
-    const int b = p - tri_idx(a, 0);
-    Kp[p] = P.sv_prec[a * k + b] + (a == b ? 1.0 / sig[a] : 0.0);
-  }
-  for (int i = threadIdx.x; i < k; i += blockDim.x) {
-    double s = 0.0;
-    for (int m = 0; m < k; ++m) s += P.sv_prec[i * k + m] * P.sv_mean[m];
-    r[i] = s + P.H[off + i] / sig[i];
-    z[i] = rng.normal_elem(ST_SV_H0_Z, (uint32_t)i);
-  }
-  __syncthreads();
-  if (threadIdx.x < 32) {
-    chol_packed_warp(Kp, k, &bad);
-    precision_solve_warp(Kp, k, r, z, x);
-    __syncwarp();
-    for (int i = threadIdx.x; i < k; i += 32) P.lvol_init[(size_t)u * k + i] = x[i];
-  }
-  if (threadIdx.x == 0 && bad) atomicOr(&P.flags[u], 4);
-}
+// (varsv_sigh / varsv_h0: sv_finish_kernel, kernels_sv_finish.cu)
 
 // ------------------------------------------------------------------ warp-tile forms of updateSv / the mixture step
 // Both elementwise SV kernels start from a small per-unit matrix product over the series index: (Y L')_{t,i} for
@@ -914,9 +867,7 @@ cudaError_t launch_sv_state(int part, const Dims& D, const DevPtrs& P, cudaStrea
   } else if (part == 1) {
     sv_solve_kernel<<<dim3((D.M + 127) / 128, D.W), 128, 0, st>>>(D, P);
   } else {
-    const size_t smem = ((size_t)D.k * (D.k + 1) / 2 + 4 * D.k) * sizeof(double);
-    cudaFuncSetAttribute(sv_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    sv_finish_kernel<<<D.U, 128, smem, st>>>(D, P);
+    return launch_sv_finish(D, P, st);
   }
   return cudaGetLastError();
 }
