@@ -436,7 +436,7 @@ size_t chol_cta_smem(const Dims& D) {
   return ((size_t)D.d * 33 + 32 * CB_PB + 64 + (size_t)std::max(0, D.d - 32) * 33) * sizeof(double);
 }
 size_t seq_big_smem(const Dims& D) {
-  return ((size_t)D.k * D.k + 3 * (size_t)D.d + 32 * 33 + (size_t)(CB_THREADS / 32) * D.d + D.k + 8) * sizeof(double);
+  return ((((size_t)D.k * (D.k + 1) / 2 + 1) & ~(size_t)1) + 3 * (size_t)D.d + 32 * 33 + (size_t)(CB_THREADS / 32) * D.d + D.k + 8) * sizeof(double);
 }
 
 bool coef_big_fits(const Dims& D, size_t smem_limit) {

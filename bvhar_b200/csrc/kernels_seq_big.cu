@@ -99,14 +99,14 @@ __device__ void precision_solve_cta(const double* __restrict__ Lg, int d, double
 
 // ---- B (large d): the sequential-in-j part, one CTA per unit ----------------------------------------------------
 template <bool SV, int NC>
-__global__ void __launch_bounds__(CB_THREADS) coef_seq_big_kernel(const Dims D, const DevPtrs P, const double* __restrict__ Pfac,
+__global__ void __launch_bounds__(CB_THREADS, 2) coef_seq_big_kernel(const Dims D, const DevPtrs P, const double* __restrict__ Pfac,
                                                                    double* __restrict__ hscr) {
   extern __shared__ __align__(16) double sm[];
   const int u = blockIdx.x, w = u / D.C, c = u % D.C;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
   const int k = D.k, d = D.d, ldM = D.ldM;
-  double* Lsm = sm;                          // [k][k]
-  double* yv = Lsm + (size_t)k * k;          // [d] rhs -> delta
+  double* Lsm = sm;                          // packed lower k(k+1)/2 (row i at i(i+1)/2): half the square, so that two CTAs share an SM
+  double* yv = Lsm + (((size_t)k * (k + 1) / 2 + 1) & ~(size_t)1);  // [d] rhs -> delta
   double* zv = yv + d;                       // [d]
   double* tv = zv + d;                       // [d] LDLT: X'X delta
   double* blk = tv + d;                      // [32][33]
@@ -119,14 +119,17 @@ __global__ void __launch_bounds__(CB_THREADS) coef_seq_big_kernel(const Dims D, 
   const double* xn = P.xnorm + (size_t)w * d;
   const double* X2 = SV ? nullptr : P.XtX + (size_t)w * D.ldS;
 
-  for (int e = tid; e < k * k; e += blockDim.x) Lsm[e] = P.L[(size_t)u * k * k + e];
+  for (int e = tid; e < k * k; e += blockDim.x) {
+    const int i = e / k, m = e - i * k;
+    if (m <= i) Lsm[i * (i + 1) / 2 + m] = P.L[(size_t)u * k * k + e];
+  }
   if (!SV) for (int i = tid; i < k; i += blockDim.x) idg[i] = 1.0 / P.diag[(size_t)u * k + i];
   __syncthreads();
   for (int i = warp; i < k; i += nw) {  // h_i = C_i - S_i v_i, v_i = A L_i'
     double* v = wscr + (size_t)warp * d;
     for (int a = lane; a < d; a += 32) {
       double sacc = 0.0;
-      for (int m = 0; m <= i; ++m) sacc = fma(Lsm[i * k + m], Ac[(size_t)a * ldM + m], sacc);
+      for (int m = 0; m <= i; ++m) sacc = fma(Lsm[i * (i + 1) / 2 + m], Ac[(size_t)a * ldM + m], sacc);
       v[a] = sacc;
     }
     __syncwarp();
@@ -141,7 +144,7 @@ __global__ void __launch_bounds__(CB_THREADS) coef_seq_big_kernel(const Dims D, 
         } else {
           const double* xty = P.XtY + ((size_t)w * d + b) * k;
           double sacc = 0.0;
-          for (int m = 0; m <= i; ++m) sacc = fma(xty[m], Lsm[i * k + m], sacc);
+          for (int m = 0; m <= i; ++m) sacc = fma(xty[m], Lsm[i * (i + 1) / 2 + m], sacc);
           h[(size_t)i * d + b] = (sacc - out[sidx]) * idg[i];
         }
       }
@@ -154,7 +157,7 @@ __global__ void __launch_bounds__(CB_THREADS) coef_seq_big_kernel(const Dims D, 
   for (int j = 0; j < k; ++j) {
     for (int a = tid; a < d; a += blockDim.x) {
       double acc = prec_u[j * d + a] * (P.prior_mean[j * d + a] - Ac[(size_t)a * ldM + j]);
-      for (int i = j; i < k; ++i) acc = fma(Lsm[i * k + j], h[(size_t)i * d + a], acc);
+      for (int i = j; i < k; ++i) acc = fma(Lsm[i * (i + 1) / 2 + j], h[(size_t)i * d + a], acc);
       yv[a] = acc;
       zv[a] = rng.normal_elem(ST_COEF_Z, (uint32_t)(j * d + a));
     }
@@ -177,7 +180,7 @@ __global__ void __launch_bounds__(CB_THREADS) coef_seq_big_kernel(const Dims D, 
         for (int i = j + 1 + warp; i < k; i += nw) {
           double out[NC];
           symv_packed_warp<NC>(P.S + ((size_t)u * k + i) * D.ldS, yv, d, out);
-          const double lij = Lsm[i * k + j];
+          const double lij = Lsm[i * (i + 1) / 2 + j];
 #pragma unroll
           for (int sidx = 0; sidx < NC; ++sidx) {
             const int b = lane + 32 * sidx;
@@ -206,7 +209,7 @@ __global__ void __launch_bounds__(CB_THREADS) coef_seq_big_kernel(const Dims D, 
         __syncthreads();
         for (int e = tid; e < (k - j - 1) * d; e += blockDim.x) {
           const int i = j + 1 + e / d, a = e % d;
-          h[(size_t)i * d + a] = fma(-Lsm[i * k + j] * idg[i], tv[a], h[(size_t)i * d + a]);
+          h[(size_t)i * d + a] = fma(-Lsm[i * (i + 1) / 2 + j] * idg[i], tv[a], h[(size_t)i * d + a]);
         }
       }
     }
