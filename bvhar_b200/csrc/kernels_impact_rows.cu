@@ -114,9 +114,27 @@ __global__ void __launch_bounds__(32 * IR_MAXW) BV_CAT(impact_rows_kernel_nc, BV
     const double* Gj = G + rows_row_off(j);
     for (int p = lane; p < j * (j + 1) / 2; p += 32) Pw[p] = Gj[p];
     for (int b = lane; b < j; b += 32) r[b] = Gj[j * (j + 1) / 2 + b];  // prior_chol_mean = 0 (tri.h:52)
-  } else {  // leading j x j block and row j of the full Z'Z (row pitch kz)
-    for (int a = 0; a < j; ++a)
-      for (int b = lane; b <= a; b += 32) Pw[a * (a + 1) / 2 + b] = G[a * kz + b] * inv_dj;
+  } else {  // leading j x j block and row j of the full Z'Z (row pitch kz), walked in packed order: the loads of a lane are
+            // independent of one another (a row-by-row loop left ONE load in flight per warp: 99 dependent L2 round trips)
+    const int np = j * (j + 1) / 2;
+    int a = 0, rs = 0;  // row of packed index p and its first packed index
+    for (int p0 = lane; p0 < np; p0 += 32 * 8) {
+      double v[8];
+      int at[8];
+#pragma unroll
+      for (int q8 = 0; q8 < 8; ++q8) {
+        const int p = p0 + 32 * q8;
+        while (p < np && p >= rs + a + 1) { rs += a + 1; ++a; }
+        at[q8] = p < np ? a * kz + (p - rs) : 0;
+      }
+#pragma unroll
+      for (int q8 = 0; q8 < 8; ++q8) v[q8] = G[at[q8]];
+#pragma unroll
+      for (int q8 = 0; q8 < 8; ++q8) {
+        const int p = p0 + 32 * q8;
+        if (p < np) Pw[p] = v[q8] * inv_dj;
+      }
+    }
     for (int b = lane; b < j; b += 32) r[b] = G[j * kz + b] * inv_dj;
   }
   __syncwarp();
