@@ -26,17 +26,35 @@ __device__ __forceinline__ size_t rowoff(int a) { return (size_t)a * (a + 1) / 2
 
 // ---- blocked two-sided triangular solve by the whole CTA, factor in global memory ---------------------------
 // delta = L^-T (L^-1 r + z).  y (shared, d doubles) holds r on entry and delta on exit; z in shared memory.
+// The (inverted) diagonal block of step jb +- 1 is fetched into registers while step jb's off-diagonal update runs, so the
+// 2 ceil(d / 32) dependent block steps do not each start with an exposed global-memory round trip; blockDim.x >= 256.
 __device__ void precision_solve_cta(const double* __restrict__ Lg, int d, double* y, const double* z, double* blk /* 32 x 33 */) {
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nt = blockDim.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nt = blockDim.x;  // CB_THREADS (256) or TD_THREADS (1024)
+  constexpr int DPT = 4;      // diagonal-block elements per thread at 256 threads (fewer are used by larger blocks)
   const int nb = (d + 31) / 32;
+  double dv[DPT];
+  auto load_diag = [&](int jb) {
+    const int c0 = 32 * jb, nc = min(32, d - c0);
+#pragma unroll
+    for (int q = 0; q < DPT; ++q) {
+      const int e = tid + q * nt, rr = e >> 5, cc = e & 31;
+      dv[q] = (e < 1024 && rr < nc && cc <= rr) ? Lg[rowoff(c0 + rr) + c0 + cc] : 0.0;
+    }
+  };
+  auto store_diag = [&]() {
+#pragma unroll
+    for (int q = 0; q < DPT; ++q) {
+      const int e = tid + q * nt;
+      if (e < 1024) blk[(e >> 5) * 33 + (e & 31)] = dv[q];
+    }
+  };
   // forward: L y = r
+  load_diag(0);
   for (int jb = 0; jb < nb; ++jb) {
     const int c0 = 32 * jb, nc = min(32, d - c0);
     __syncthreads();
-    for (int e = tid; e < 32 * 32; e += nt) {  // diagonal block rows into shared memory
-      const int rr = e >> 5, cc = e & 31;
-      blk[rr * 33 + cc] = (rr < nc && cc <= rr) ? Lg[rowoff(c0 + rr) + c0 + cc] : 0.0;
-    }
+    store_diag();
     __syncthreads();
     if (warp == 0) {  // y_blk = Linv_blk y_blk (the diagonal blocks hold the inverse, kernels_chol_big.cu)
       double v0 = 0.0, v1 = 0.0;
@@ -48,6 +66,7 @@ __device__ void precision_solve_cta(const double* __restrict__ Lg, int d, double
       __syncwarp();
       if (lane < nc) y[c0 + lane] = v0 + v1;
     }
+    if (jb + 1 < nb) load_diag(jb + 1);
     __syncthreads();
     for (int r = c0 + 32 + tid; r < d; r += nt) {  // rows below: y_r -= L[r][c0 : c0+32] . y_blk
       const double* row = Lg + rowoff(r) + c0;
@@ -62,16 +81,14 @@ __device__ void precision_solve_cta(const double* __restrict__ Lg, int d, double
       y[r] -= (s0 + s1) + (s2 + s3);
     }
   }
+  load_diag(nb - 1);
   __syncthreads();
   for (int a = tid; a < d; a += nt) y[a] += z[a];
   // backward: L' x = y + z
   for (int jb = nb - 1; jb >= 0; --jb) {
     const int c0 = 32 * jb, nc = min(32, d - c0);
     __syncthreads();
-    for (int e = tid; e < 32 * 32; e += nt) {
-      const int rr = e >> 5, cc = e & 31;
-      blk[rr * 33 + cc] = (rr < nc && cc <= rr) ? Lg[rowoff(c0 + rr) + c0 + cc] : 0.0;
-    }
+    store_diag();
     __syncthreads();
     if (warp == 0) {  // x_blk = Linv_blk' y_blk
       double v0 = 0.0, v1 = 0.0;
@@ -83,15 +100,22 @@ __device__ void precision_solve_cta(const double* __restrict__ Lg, int d, double
       __syncwarp();
       if (lane < nc) y[c0 + lane] = v0 + v1;
     }
+    if (jb > 0) load_diag(jb - 1);
     __syncthreads();
     for (int b = tid; b < c0; b += nt) {  // columns to the left: y_b -= sum_a L[c0 + a][b] x_a   (coalesced in b)
-      double s0 = 0.0, s1 = 0.0;
-      for (int a = 0; a + 1 < nc; a += 2) {
-        s0 = fma(Lg[rowoff(c0 + a) + b], y[c0 + a], s0);
-        s1 = fma(Lg[rowoff(c0 + a + 1) + b], y[c0 + a + 1], s1);
+      double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+      if (nc == 32) {  // full block: all 32 loads of the thread in flight together
+#pragma unroll
+        for (int a = 0; a < 32; a += 4) {
+          s0 = fma(Lg[rowoff(c0 + a) + b], y[c0 + a], s0);
+          s1 = fma(Lg[rowoff(c0 + a + 1) + b], y[c0 + a + 1], s1);
+          s2 = fma(Lg[rowoff(c0 + a + 2) + b], y[c0 + a + 2], s2);
+          s3 = fma(Lg[rowoff(c0 + a + 3) + b], y[c0 + a + 3], s3);
+        }
+      } else {
+        for (int a = 0; a < nc; ++a) s0 = fma(Lg[rowoff(c0 + a) + b], y[c0 + a], s0);
       }
-      if (nc & 1) s0 = fma(Lg[rowoff(c0 + nc - 1) + b], y[c0 + nc - 1], s0);
-      y[b] -= s0 + s1;
+      y[b] -= (s0 + s1) + (s2 + s3);
     }
   }
   __syncthreads();
@@ -157,7 +181,16 @@ __global__ void __launch_bounds__(CB_THREADS, 2) coef_seq_big_kernel(const Dims 
   for (int j = 0; j < k; ++j) {
     for (int a = tid; a < d; a += blockDim.x) {
       double acc = prec_u[j * d + a] * (P.prior_mean[j * d + a] - Ac[(size_t)a * ldM + j]);
-      for (int i = j; i < k; ++i) acc = fma(Lsm[i * (i + 1) / 2 + j], h[(size_t)i * d + a], acc);
+      double a1 = 0.0, a2 = 0.0, a3 = 0.0;
+      int i = j;
+      for (; i + 3 < k; i += 4) {  // four independent loads / chains per step
+        acc = fma(Lsm[i * (i + 1) / 2 + j], h[(size_t)i * d + a], acc);
+        a1 = fma(Lsm[(i + 1) * (i + 2) / 2 + j], h[(size_t)(i + 1) * d + a], a1);
+        a2 = fma(Lsm[(i + 2) * (i + 3) / 2 + j], h[(size_t)(i + 2) * d + a], a2);
+        a3 = fma(Lsm[(i + 3) * (i + 4) / 2 + j], h[(size_t)(i + 3) * d + a], a3);
+      }
+      for (; i < k; ++i) acc = fma(Lsm[i * (i + 1) / 2 + j], h[(size_t)i * d + a], acc);
+      acc = (acc + a1) + (a2 + a3);
       yv[a] = acc;
       zv[a] = rng.normal_elem(ST_COEF_Z, (uint32_t)(j * d + a));
     }
