@@ -2,6 +2,7 @@
 // warp per matrix, 32 x 32 register blocks (warp_linalg.cuh).  Compiled once per BV_NC = ceil(d / 32) in
 // {1, 2, 4, 8} (separate translation units: the fully unrolled register-block code is slow to compile).
 #include "engine.cuh"
+#include "gemm_tn.cuh"
 #include "kernels.h"
 #include "warp_linalg.cuh"
 
@@ -30,8 +31,11 @@ __global__ void __launch_bounds__(128) BV_CAT(coef_chol_kernel_nc, BV_NC)(const 
   __shared__ int bad[8];
   __shared__ double colbuf[8][64];  // column broadcast buffers of the warp Cholesky (warp_linalg.cuh)
   if (lane == 0) bad[warp] = 0;
-  if (SV) {
-    for (int p = lane; p < Pp; p += 32) Pk[p] = Pg[p];
+  if (SV) {  // 16-byte asynchronous copies: all of a lane's ~30 chunks in flight (both bases and the padded length are 16-byte multiples)
+    const int ppad = (Pp + 1) & ~1;
+    for (int p = 2 * lane; p < ppad; p += 64) cp_async16(Pk + p, Pg + p, 16);
+    cp_async_commit();
+    cp_async_wait<0>();
   } else {  // P_j = (sum_{i>=j} L_ij^2 / d_i) X'X
     double ws = 0.0;
     for (int i = j; i < k; ++i) {
