@@ -126,7 +126,10 @@ __device__ __forceinline__ double log1p_sum(const double* __restrict__ x, int n,
 
 }  // namespace
 
-__global__ void __launch_bounds__(512) prior_kernel(const Dims D, const DevPtrs P, const PriorConst C, const int side) {
+// MAXT = 512: the 16-warp launch of long coefficient vectors; MAXT = 256: three CTAs per SM (the kernel is latency-bound: one
+// CTA per unit, serial reductions and rejection samplers)
+template <int MAXT>
+__global__ void __launch_bounds__(MAXT, (MAXT == 256 ? 3 : 1)) prior_kernel(const Dims D, const DevPtrs P, const PriorConst C, const int side) {
   __shared__ double red[40];
   __shared__ double gridbuf[512];
   __shared__ double gsm[3][64];  // per-group scratch (G <= 64)
@@ -608,7 +611,8 @@ cudaError_t launch_prior(const Dims& D, const DevPtrs& P, const PriorConst& C, i
   if (D.prior == 1) return cudaSuccess;
   // one CTA per unit; large coefficient vectors (k = 100, d = 301: N = 30 000) get 16 warps
   const int threads = (side == 0 ? D.N : D.q) >= 8192 ? 512 : 256;
-  prior_kernel<<<D.U, threads, 0, st>>>(D, P, C, side);
+  if (threads == 512) prior_kernel<512><<<D.U, 512, 0, st>>>(D, P, C, side);
+  else prior_kernel<256><<<D.U, 256, 0, st>>>(D, P, C, side);
   return cudaGetLastError();
 }
 
