@@ -130,7 +130,7 @@ __device__ __forceinline__ double log1p_sum(const double* __restrict__ x, int n,
 // 4 / 6 CTAs: 0.36 / 0.31 / 0.29 / 0.30 ms at C3 - the kernel is latency-bound: one
 // CTA per unit, serial reductions and rejection samplers)
 template <int MAXT>
-__global__ void __launch_bounds__(MAXT, (MAXT == 256 ? 4 : 1)) prior_kernel(const Dims D, const DevPtrs P, const PriorConst C, const int side) {
+__global__ void __launch_bounds__(MAXT, (MAXT == 256 ? 4 : 2)) prior_kernel(const Dims D, const DevPtrs P, const PriorConst C, const int side) {
   __shared__ double red[40];
   __shared__ double gridbuf[512];
   __shared__ double gsm[3][64];  // per-group scratch (G <= 64)
