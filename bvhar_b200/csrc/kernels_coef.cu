@@ -38,7 +38,7 @@ namespace {
 // (cp.async) while equation j is solved.  Per equation only the solve (one warp) and the k-j-1 products
 // S_i delta (all warps, S_i from L2) remain on the critical path.
 template <bool SV, int NC>
-__global__ void __launch_bounds__(SEQ_THREADS) coef_seq_kernel(const Dims D, const DevPtrs P, const double* __restrict__ Pfac) {
+__global__ void __launch_bounds__(SEQ_THREADS, (NC <= 2 ? 4 : 1)) coef_seq_kernel(const Dims D, const DevPtrs P, const double* __restrict__ Pfac) {
   extern __shared__ __align__(16) double sm[];
   const int u = blockIdx.x, w = u / D.C, c = u % D.C;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
