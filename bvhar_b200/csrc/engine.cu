@@ -127,9 +127,12 @@ struct DevBuf {
     if (e != cudaSuccess || h.empty()) return e;
     return cudaMemcpyAsync(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, 0);  // pageable source: staged before return
   }
-  ~DevBuf() {
+  void release() {
     if (p) cudaFreeAsync(p, 0);
+    p = nullptr;
+    n = 0;
   }
+  ~DevBuf() { release(); }
 };
 
 struct RecordSpec {
@@ -171,7 +174,10 @@ struct bvhar_fit {
   bool direct_p = false;  // large-design SV path: G1 contracts the mixed weights and writes the P_j themselves (no S_i, no pbuild)
   std::map<std::string, std::unique_ptr<DevBuf<double>>> rec;
   std::vector<RecordSpec> rec_order;
-  GemmArgs g1{}, g2{}, g3{}, gz{};  // gz: Z'Z per unit (LDLT contemporaneous draw + state)
+  GemmArgs g1{}, g2{}, g3{}, gz{}, g4{};  // gz: Z'Z per unit (LDLT contemporaneous draw + state); g4: R = X'Y - X'X A (LDLT, large designs)
+  DevBuf<double> XtXf, Rres;              // full X'X per window (pitch even(d)) and R [W][d][ldM]
+  DevBuf<long long> g4_a, g4_y;
+  bool ldlt_res = false;                  // the large-design LDLT sequential kernel starts from R instead of k symmetric products
   bool g3_aligned = true;
   bool timed = false;
   // per-kernel profiling (eager launches bracketed by CUDA events on the engine's stream)
@@ -294,7 +300,8 @@ struct bvhar_fit {
       if (D.sv && !direct_p) LAUNCH("coef_pbuild", launch_coef_v2(0, D, P, Pfac.p, Qn.p, smem_limit, st));
       if (fork) { CU(cudaStreamWaitEvent(st, evf[1], 0)); if (D.sv) CU(cudaStreamWaitEvent(st, evf[3], 0)); }
       LAUNCH("coef_chol_cta", launch_coef_big(1, D, P, Pfac.p, hscr.p, smem_limit, st)); ++nl;  // + invert_diag_kernel
-      LAUNCH("coef_seq_big", launch_coef_big(2, D, P, Pfac.p, hscr.p, smem_limit, st));
+      if (ldlt_res) LAUNCH("gram_R_dmma", launch_dgemm_tn(g4, st));
+      LAUNCH("coef_seq_big", launch_coef_big(2, D, P, Pfac.p, hscr.p, smem_limit, st, ldlt_res ? Rres.p : nullptr));
     } else if (coef_v2) {
       if (D.sv) LAUNCH("coef_pbuild", launch_coef_v2(0, D, P, Pfac.p, Qn.p, smem_limit, st));
       if (fork) { CU(cudaStreamWaitEvent(st, evf[1], 0)); if (D.sv) CU(cudaStreamWaitEvent(st, evf[3], 0)); }
@@ -854,28 +861,45 @@ int build(const bvhar_fit_desc* d, bvhar_fit** out) {
   else {
     // X'X (packed) and X'Y per window through the same contraction kernel
     CU(F->XtX.alloc((size_t)D.W * D.ldS)); CU(F->XtY.alloc((size_t)D.W * dd * k));
-    DevBuf<double> full;
-    CU(full.alloc((size_t)D.W * dd * dd));
+    DevBuf<double>& full = F->XtXf;  // kept: the A operand of the residual contraction g4
+    const int ldg = (dd + 1) & ~1;
+    CU(full.alloc((size_t)D.W * dd * ldg));
     std::vector<long long> bo(D.W), co(D.W), yo(D.W), cy(D.W);
-    for (int w = 0; w < D.W; ++w) { bo[w] = (long long)F->win_row0[w] * D.ldX; co[w] = (long long)w * dd * dd; yo[w] = (long long)F->win_row0[w] * k; cy[w] = (long long)w * dd * k; }
+    for (int w = 0; w < D.W; ++w) { bo[w] = (long long)F->win_row0[w] * D.ldX; co[w] = (long long)w * dd * ldg; yo[w] = (long long)F->win_row0[w] * k; cy[w] = (long long)w * dd * k; }
     DevBuf<long long> dbo, dco, dyo, dcy;
     CU(dbo.upload(bo)); CU(dco.upload(co)); CU(dyo.upload(yo)); CU(dcy.upload(cy));
     if (int rc = order_after_stream0()) return rc;  // XtX / XtY / full / the offset tables live on stream 0
     GemmArgs g{};
-    g.A = P.X; g.B = P.X; g.C = full.p; g.M = dd; g.N = dd; g.lda = D.ldX; g.ldb = D.ldX; g.ldc = dd; g.groups = D.W;
+    g.A = P.X; g.B = P.X; g.C = full.p; g.M = dd; g.N = dd; g.lda = D.ldX; g.ldb = D.ldX; g.ldc = ldg; g.groups = D.W;
     g.a_off = dbo.p; g.b_off = dbo.p; g.c_off = dco.p; g.Kg = F->gKg.p; g.epi = EPI_STORE; g.aligned16 = 1;
     CU(launch_dgemm_tn(g, F->st));
     GemmArgs gy = g;
     gy.B = P.Y; gy.b_off = dyo.p; gy.ldb = k; gy.N = k; gy.C = F->XtY.p; gy.ldc = k; gy.c_off = dcy.p; gy.aligned16 = (k % 2 == 0) ? 1 : 0;
     CU(launch_dgemm_tn(gy, F->st));
     CU(cudaStreamSynchronize(F->st));
-    std::vector<double> hf((size_t)D.W * dd * dd), hp((size_t)D.W * D.ldS, 0.0);
+    std::vector<double> hf((size_t)D.W * dd * ldg), hp((size_t)D.W * D.ldS, 0.0);
     CU(cudaMemcpy(hf.data(), full.p, hf.size() * sizeof(double), cudaMemcpyDeviceToHost));
     for (int w = 0; w < D.W; ++w)
       for (int a = 0; a < dd; ++a)
-        for (int b = 0; b <= a; ++b) hp[(size_t)w * D.ldS + a * (a + 1) / 2 + b] = hf[(size_t)w * dd * dd + a * dd + b];
+        for (int b = 0; b <= a; ++b) hp[(size_t)w * D.ldS + a * (a + 1) / 2 + b] = hf[((size_t)w * dd + a) * ldg + b];
     CU(cudaMemcpy(F->XtX.p, hp.data(), hp.size() * sizeof(double), cudaMemcpyHostToDevice));
     P.XtX = F->XtX.p; P.XtY = F->XtY.p;
+    if (F->coef_big && getenv("BVHAR_LDLT_NO_RES") == nullptr) {
+      // R = X'Y - X'X A for every chain of every window in one grouped contraction per sweep (X'X is symmetric: it is its own
+      // K-major operand): the sequential kernel's prologue then needs no symmetric product at all
+      CU(F->Rres.alloc((size_t)D.W * dd * D.ldM));
+      std::vector<long long> ga(D.W), gy4(D.W);
+      for (int w = 0; w < D.W; ++w) { ga[w] = (long long)w * dd * ldg; gy4[w] = (long long)w * dd * k; }
+      CU(F->g4_a.upload(ga)); CU(F->g4_y.upload(gy4));
+      if (int rc = order_after_stream0()) return rc;
+      GemmArgs& g4 = F->g4;
+      g4.A = full.p; g4.B = P.Acoef; g4.C = F->Rres.p; g4.M = dd; g4.N = D.M; g4.K = dd; g4.lda = ldg; g4.ldb = D.ldM; g4.ldc = D.ldM;
+      g4.groups = D.W; g4.a_off = F->g4_a.p; g4.b_off = F->g3_b.p; g4.c_off = F->g3_b.p; g4.Kg = nullptr; g4.Mg = nullptr;
+      g4.epi = EPI_Y_MINUS; g4.Y = P.XtY; g4.y_off = F->g4_y.p; g4.ldy = k; g4.ymod = k; g4.aligned16 = 1;
+      F->ldlt_res = true;
+    } else {
+      F->XtXf.release();  // not needed
+    }
   }
   // latent_innov = y - x * coef_mat (tri.h:57)
   CU(launch_dgemm_tn(F->g3, F->st));
@@ -1387,7 +1411,8 @@ int bvhar_cuda_fit_run_stage(bvhar_fit* fit, int stage, int iter) {
       if (fit->coef_big) {
         if (D.sv && !fit->direct_p) CU(launch_coef_v2(0, D, fit->P, fit->Pfac.p, fit->Qn.p, fit->smem_limit, fit->st));
         CU(launch_coef_big(1, D, fit->P, fit->Pfac.p, fit->hscr.p, fit->smem_limit, fit->st));
-        CU(launch_coef_big(2, D, fit->P, fit->Pfac.p, fit->hscr.p, fit->smem_limit, fit->st));
+        if (fit->ldlt_res) CU(launch_dgemm_tn(fit->g4, fit->st));
+        CU(launch_coef_big(2, D, fit->P, fit->Pfac.p, fit->hscr.p, fit->smem_limit, fit->st, fit->ldlt_res ? fit->Rres.p : nullptr));
       } else if (fit->coef_v2) {
         CU(launch_coef_v2(0, D, fit->P, fit->Pfac.p, fit->Qn.p, fit->smem_limit, fit->st));
         CU(launch_coef_v2(1, D, fit->P, fit->Pfac.p, fit->Qn.p, fit->smem_limit, fit->st));

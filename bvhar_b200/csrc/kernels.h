@@ -28,10 +28,12 @@ inline cudaError_t launch_coef_chol(int nc, const Dims& D, const DevPtrs& P, dou
                  : launch_coef_chol_nc4(D, P, Pfac, smem_limit, st);
 }
 bool coef_big_fits(const Dims& D, size_t smem_limit);
-cudaError_t launch_coef_big(int part, const Dims& D, const DevPtrs& P, double* Pfac, double* hscr, size_t smem_limit, cudaStream_t st);
+// Rres (part 2, LDLT): R = X'Y - X'X A of the sweep's initial coefficients ([W][d][ldM], from the engine's residual contraction) or nullptr
+cudaError_t launch_coef_big(int part, const Dims& D, const DevPtrs& P, double* Pfac, double* hscr, size_t smem_limit, cudaStream_t st,
+                            const double* Rres = nullptr);
 cudaError_t launch_chol_big(const Dims& D, const DevPtrs& P, double* Pfac, size_t smem_limit, cudaStream_t st);
-cudaError_t launch_seq_big_nc8(const Dims& D, const DevPtrs& P, const double* Pfac, double* hscr, size_t smem, cudaStream_t st);
-cudaError_t launch_seq_big_nc16(const Dims& D, const DevPtrs& P, const double* Pfac, double* hscr, size_t smem, cudaStream_t st);
+cudaError_t launch_seq_big_nc8(const Dims& D, const DevPtrs& P, const double* Pfac, double* hscr, size_t smem, cudaStream_t st, const double* Rres = nullptr);
+cudaError_t launch_seq_big_nc16(const Dims& D, const DevPtrs& P, const double* Pfac, double* hscr, size_t smem, cudaStream_t st, const double* Rres = nullptr);
 size_t seq_time_smem(const Dims& D);
 size_t seq_time_scratch_doubles(const Dims& D);  // per-fit scratch of the time-domain sequential kernel (SV, large d)
 cudaError_t launch_seq_time(const Dims& D, const DevPtrs& P, const double* Pfac, double* escr, size_t smem_limit, cudaStream_t st);

@@ -482,12 +482,13 @@ cudaError_t launch_chol_big(const Dims& D, const DevPtrs& P, double* Pfac, size_
 
 // part 1: batched Cholesky (one CTA per matrix), part 2: sequential draws.  (Part 0, the P build, is shared with
 // the small-d path: launch_coef_v2(0, ...).)
-cudaError_t launch_coef_big(int part, const Dims& D, const DevPtrs& P, double* Pfac, double* hscr, size_t smem_limit, cudaStream_t st) {
+cudaError_t launch_coef_big(int part, const Dims& D, const DevPtrs& P, double* Pfac, double* hscr, size_t smem_limit, cudaStream_t st,
+                            const double* Rres) {
   if (part == 1) return launch_chol_big(D, P, Pfac, smem_limit, st);
   if (D.sv) return launch_seq_time(D, P, Pfac, hscr, smem_limit, st);  // SV: time-domain recurrence (kernels_seq_big.cu)
   const size_t smem = seq_big_smem(D);
   if (smem > smem_limit) return cudaErrorInvalidConfiguration;
-  return (D.d + 31) / 32 <= 8 ? launch_seq_big_nc8(D, P, Pfac, hscr, smem, st) : launch_seq_big_nc16(D, P, Pfac, hscr, smem, st);
+  return (D.d + 31) / 32 <= 8 ? launch_seq_big_nc8(D, P, Pfac, hscr, smem, st, Rres) : launch_seq_big_nc16(D, P, Pfac, hscr, smem, st, Rres);
 }
 
 }  // namespace bvhar

@@ -124,7 +124,7 @@ __device__ void precision_solve_cta(const double* __restrict__ Lg, int d, double
 // ---- B (large d): the sequential-in-j part, one CTA per unit ----------------------------------------------------
 template <bool SV, int NC>
 __global__ void __launch_bounds__(CB_THREADS, 2) coef_seq_big_kernel(const Dims D, const DevPtrs P, const double* __restrict__ Pfac,
-                                                                   double* __restrict__ hscr) {
+                                                                   double* __restrict__ hscr, const double* __restrict__ Rres) {
   extern __shared__ __align__(16) double sm[];
   const int u = blockIdx.x, w = u / D.C, c = u % D.C;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
@@ -149,6 +149,22 @@ __global__ void __launch_bounds__(CB_THREADS, 2) coef_seq_big_kernel(const Dims 
   }
   if (!SV) for (int i = tid; i < k; i += blockDim.x) idg[i] = 1.0 / P.diag[(size_t)u * k + i];
   __syncthreads();
+  if (!SV && Rres) {
+    // LDLT with the residual contraction: h_i = (X'Y - X'X A) L_i' / d_i = R L_i' / d_i, no symmetric product (the k products
+    // with the same X'X per unit were a third of this kernel's L2 traffic)
+    const double* Ru = Rres + (size_t)w * d * ldM + (size_t)c * k;
+    for (int i = warp; i < k; i += nw) {
+      const double* Li = Lsm + i * (i + 1) / 2;
+      for (int a = lane; a < d; a += 32) {
+        const double* ra = Ru + (size_t)a * ldM;
+        double s0 = 0.0, s1 = 0.0;
+        int m = 0;
+        for (; m + 1 <= i; m += 2) { s0 = fma(Li[m], ra[m], s0); s1 = fma(Li[m + 1], ra[m + 1], s1); }
+        if (m <= i) s0 = fma(Li[m], ra[m], s0);
+        h[(size_t)i * d + a] = (s0 + s1) * idg[i];
+      }
+    }
+  } else
   for (int i = warp; i < k; i += nw) {  // h_i = C_i - S_i v_i, v_i = A L_i'
     double* v = wscr + (size_t)warp * d;
     for (int a = lane; a < d; a += 32) {
@@ -547,13 +563,14 @@ __global__ void __launch_bounds__(TD_THREADS) coef_seq_time_kernel(const Dims D,
 
 }  // namespace
 
-cudaError_t BV_CAT(launch_seq_big_nc, BV_NC)(const Dims& D, const DevPtrs& P, const double* Pfac, double* hscr, size_t smem, cudaStream_t st) {
+cudaError_t BV_CAT(launch_seq_big_nc, BV_NC)(const Dims& D, const DevPtrs& P, const double* Pfac, double* hscr, size_t smem, cudaStream_t st,
+                                             const double* Rres) {
   if (D.sv) {
     cudaFuncSetAttribute(coef_seq_big_kernel<true, BV_NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    coef_seq_big_kernel<true, BV_NC><<<D.U, CB_THREADS, smem, st>>>(D, P, Pfac, hscr);
+    coef_seq_big_kernel<true, BV_NC><<<D.U, CB_THREADS, smem, st>>>(D, P, Pfac, hscr, nullptr);
   } else {
     cudaFuncSetAttribute(coef_seq_big_kernel<false, BV_NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    coef_seq_big_kernel<false, BV_NC><<<D.U, CB_THREADS, smem, st>>>(D, P, Pfac, hscr);
+    coef_seq_big_kernel<false, BV_NC><<<D.U, CB_THREADS, smem, st>>>(D, P, Pfac, hscr, Rres);
   }
   return cudaGetLastError();
 }
