@@ -129,8 +129,8 @@ __device__ __forceinline__ double log1p_sum(const double* __restrict__ x, int n,
 // MAXT = 512: the 16-warp launch of long coefficient vectors; MAXT = 256: four CTAs per SM (64 registers; measured 2 / 3 /
 // 4 / 6 CTAs: 0.36 / 0.31 / 0.29 / 0.30 ms at C3 - the kernel is latency-bound: one
 // CTA per unit, serial reductions and rejection samplers)
-template <int MAXT>
-__global__ void __launch_bounds__(MAXT, (MAXT == 256 ? 4 : 2)) prior_kernel(const Dims D, const DevPtrs P, const PriorConst C, const int side) {
+template <int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) prior_kernel(const Dims D, const DevPtrs P, const PriorConst C, const int side) {
   __shared__ double red[40];
   __shared__ double gridbuf[512];
   __shared__ double gsm[3][64];  // per-group scratch (G <= 64)
@@ -612,8 +612,16 @@ cudaError_t launch_prior(const Dims& D, const DevPtrs& P, const PriorConst& C, i
   if (D.prior == 1) return cudaSuccess;
   // one CTA per unit; large coefficient vectors (k = 100, d = 301: N = 30 000) get 16 warps
   const int threads = (side == 0 ? D.N : D.q) >= 8192 ? 512 : 256;
-  if (threads == 512) prior_kernel<512><<<D.U, 512, 0, st>>>(D, P, C, side);
-  else prior_kernel<256><<<D.U, 256, 0, st>>>(D, P, C, side);
+  // batches of at most two CTAs per SM run as one wave whatever the register budget: they get the 128-register instance
+  // (no spills, shortest single-CTA latency - the strong-scaling case of 128 chains per GPU); larger batches the 64-register one
+  static int sms = 0;
+  if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+  const bool one_wave = D.U <= 2 * sms;
+  if (threads == 512) {
+    if (D.U <= sms) prior_kernel<512, 1><<<D.U, 512, 0, st>>>(D, P, C, side);
+    else prior_kernel<512, 2><<<D.U, 512, 0, st>>>(D, P, C, side);
+  } else if (one_wave) prior_kernel<256, 2><<<D.U, 256, 0, st>>>(D, P, C, side);
+  else prior_kernel<256, 4><<<D.U, 256, 0, st>>>(D, P, C, side);
   return cudaGetLastError();
 }
 
