@@ -682,6 +682,30 @@ int build(const bvhar_fit_desc* d, bvhar_fit** out) {
     const bvhar_chain_init& in0 = d->init[0];
     lvol_explicit = !(d->lvol_from_init || !in0.lvol);
   }
+  // explicit lvol inits: the chains' n x k blocks are gathered into one page-locked staging buffer by a few host threads
+  // WHILE the unit loop below fills the other staging vectors (both are memory-bound host work on disjoint data)
+  std::thread lvol_gather;
+  struct JoinGuard { std::thread& t; ~JoinGuard() { if (t.joinable()) t.join(); } } lvol_gather_guard{lvol_gather};
+  if (D.sv && lvol_explicit) {
+    const size_t blk = (size_t)k * F->win_n[0];
+    // staged in a page-locked buffer that lives as long as the process (grow-only, engine construction is serialised):
+    // a fresh pageable vector of this size costs more in page faults than the copy itself (66 ms for 164 MB at C3)
+    hlv_stage = lvol_stage_buffer((size_t)D.C * blk);
+    if (!hlv_stage) { hlv.resize((size_t)D.C * blk); hlv_stage = hlv.data(); }
+    double* dst = hlv_stage;
+    const int nchain = D.C;
+    const bvhar_chain_init* inits = d->init;
+    lvol_gather = std::thread([dst, blk, nchain, inits] {
+      const int nthr = std::max(1, std::min(8, nchain / 32));
+      std::vector<std::thread> pool;
+      for (int th = 0; th < nthr; ++th)
+        pool.emplace_back([=] {
+          for (int c = th; c < nchain; c += nthr)
+            if (inits[c].lvol) std::memcpy(dst + (size_t)c * blk, inits[c].lvol, sizeof(double) * blk);
+        });
+      for (auto& t : pool) t.join();
+    });
+  }
   {
     // units write disjoint slices of the host staging vectors: a few host threads share the loop (22 ms on one thread for
     // the 1 024 chains of C3: a third of create's time)
@@ -701,21 +725,17 @@ int build(const bvhar_fit_desc* d, bvhar_fit** out) {
     if (err_code) return fail(err_code, err_msg);
   }
   lap("host init loops");
-  if (D.sv && lvol_explicit) {  // gather the chains' n x k lvol blocks into one staging buffer, a few host threads
-    const size_t blk = (size_t)k * F->win_n[0];
-    // staged in a page-locked buffer that lives as long as the process (grow-only, engine construction is serialised):
-    // a fresh pageable vector of this size costs more in page faults than the copy itself (66 ms for 164 MB at C3)
-    hlv_stage = lvol_stage_buffer((size_t)D.C * blk);
-    if (!hlv_stage) { hlv.resize((size_t)D.C * blk); hlv_stage = hlv.data(); }
-    const int nthr = std::max(1, std::min(8, D.C / 32));
-    std::vector<std::thread> pool;
-    for (int th = 0; th < nthr; ++th)
-      pool.emplace_back([&, th] {
-        for (int c = th; c < D.C; c += nthr) std::memcpy(hlv_stage + (size_t)c * blk, d->init[c].lvol, sizeof(double) * blk);
-      });
-    for (auto& t : pool) t.join();
-  }
+  if (lvol_gather.joinable()) lvol_gather.join();
   lap("lvol gather");
+  // the one large transfer (page-locked source: a true asynchronous DMA) goes first, so that the pageable uploads below
+  // stage on the host while it is in flight
+  DevBuf<double> lv_stage;
+  if (D.sv && lvol_explicit) {
+    const size_t cnt = (size_t)D.C * k * F->win_n[0];
+    lv_stage.n = cnt;
+    CU(cudaMallocAsync(&lv_stage.p, cnt * sizeof(double), 0));  // fully overwritten: no memset
+    CU(cudaMemcpyAsync(lv_stage.p, hlv_stage, cnt * sizeof(double), cudaMemcpyHostToDevice, 0));
+  }
   CU(F->Acoef.upload(hA)); CU(F->alpha.upload(halpha)); CU(F->cvec.upload(hc)); CU(F->prec.upload(hprec));
   CU(F->contem.upload(hcontem)); CU(F->L.upload(hL)); CU(F->chol_prec.upload(hcp));
   CU(F->sparse_coef.alloc((size_t)U * dd * k)); CU(F->sparse_contem.alloc((size_t)U * q)); CU(F->znorm.alloc((size_t)2 * U * k));  // [U][k] column norms of Z, then [U][k] per-series sums of squared lvol increments
@@ -723,21 +743,16 @@ int build(const bvhar_fit_desc* d, bvhar_fit** out) {
   if (D.sv) {
     CU(F->H.alloc((size_t)tm_total)); CU(F->lvol_init.upload(hli)); CU(F->lvol_sig.upload(hls));
     {
-      DevBuf<double> stage;
       const int n0 = F->win_n[0];
-      if (lvol_explicit) {
-        const size_t cnt = (size_t)D.C * k * n0;
-        CU(stage.alloc(cnt));
-        CU(cudaMemcpyAsync(stage.p, hlv_stage, cnt * sizeof(double), cudaMemcpyHostToDevice, 0));  // completes before the sync below
-      }
       for (int w = 0; w < D.W; ++w) {
         if (lvol_explicit) {  // every window starts from the chains' lvol blocks (forecaster.h:867-872)
-          CU(launch_scatter_lvol(stage.p, F->H.p + F->win_off[w], F->win_n[w], D.M, D.ldM, n0, 0));
+          CU(launch_scatter_lvol(lv_stage.p, F->H.p + F->win_off[w], F->win_n[w], D.M, D.ldM, n0, 0));
         } else {  // SvInits(init, num_design): lvol_init replicated over time (config.h:416-420) = rows of length 1
           CU(launch_scatter_lvol(F->lvol_init.p + (size_t)w * D.M, F->H.p + F->win_off[w], F->win_n[w], D.M, D.ldM, 0, 0));
         }
       }
       CU(cudaDeviceSynchronize());
+      lv_stage.release();
     }
     lap("coef uploads + lvol upload / scatter");
     CU(F->Dinv.alloc((size_t)tm_total)); CU(F->YLD.alloc((size_t)tm_total)); CU(F->Zn.alloc((size_t)tm_total));
