@@ -93,3 +93,43 @@ def test_descriptor_validation_is_host_side():
     bad["param_init"] = kw["param_init"][:1]
     with pytest.raises(ValueError):
         _abi.PackedFit(**bad)
+
+
+@pytest.mark.parametrize("prior", ["Minnesota", "HMN", "SSVS", "Horseshoe", "NG", "DL", "GDP"])
+@pytest.mark.parametrize("sv", [True, False])
+def test_chain_init_table_matches_the_inputs(prior, sv):
+    """PackedFit fills bvhar_chain_init column by column through numpy views of the struct array (thousands of chains): every
+    pointer field must address exactly the array the chain passed (no copy for float64 vectors, same values otherwise) and
+    every scalar field must carry the chain's value - read back here through the ctypes field descriptors."""
+    import problems as pr
+    kw, _ = pr.make_problem(prior=prior, sv=sv, dim=3, T=40, chains=5)
+    pk = _abi.PackedFit(**kw)
+    inits = C.cast(pk.desc.init, C.POINTER(_abi.ChainInit))
+    ptr_keys = {"init_coef": "init_coef", "init_contem": "init_contem", "init_diag": "init_diag", "lvol_init": "lvol_init",
+                "lvol": "lvol", "lvol_sig": "lvol_sig", "coef_dummy": "init_coef_dummy", "coef_mixture": "coef_mixture",
+                "chol_mixture": "chol_mixture", "coef_slab": "coef_slab", "contem_slab": "contem_slab",
+                "local_sparsity": "local_sparsity", "group_sparsity": "group_sparsity",
+                "contem_local_sparsity": "contem_local_sparsity", "local_shape": "local_shape", "group_rate": "group_rate",
+                "contem_rate": "contem_rate"}
+    scalar_keys = ["own_lambda", "cross_lambda", "contem_lambda", "coef_spike_scl", "chol_spike_scl", "global_sparsity",
+                   "contem_global_sparsity", "contem_shape", "gamma_shape", "gamma_rate", "contem_gamma_shape", "contem_gamma_rate"]
+    used = 0
+    for c, ini in enumerate(kw["param_init"]):
+        I = inits[c]
+        for field, key in ptr_keys.items():
+            p = getattr(I, field)
+            if key not in ini:
+                continue
+            if not p:  # a key the prior / covariance model does not read stays NULL
+                continue
+            a = np.asarray(ini[key], dtype=np.float64)
+            got = np.ctypeslib.as_array(p, shape=(a.size,))
+            np.testing.assert_array_equal(got, a.reshape(-1, order="F"))
+            if isinstance(ini[key], np.ndarray) and ini[key].dtype == np.float64 and ini[key].ndim == 1:
+                assert C.addressof(p.contents) == ini[key].__array_interface__["data"][0]  # passed through, not copied
+            used += 1
+        for field in scalar_keys:
+            if field in ini and getattr(I, field) != 0.0:
+                assert getattr(I, field) == float(np.asarray(ini[field], dtype=np.float64).reshape(-1)[0])
+                used += 1
+    assert used >= 2 * 5
