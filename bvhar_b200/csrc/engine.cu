@@ -176,6 +176,8 @@ struct bvhar_fit {
   std::vector<RecordSpec> rec_order;
   GemmArgs g1{}, g2{}, g3{}, gz{}, g4{};  // gz: Z'Z per unit (LDLT contemporaneous draw + state); g4: R = X'Y - X'X A (LDLT, large designs)
   DevBuf<double> XtXf, Rres;              // full X'X per window (pitch even(d)) and R [W][d][ldM]
+  DevBuf<double> ws1, ws2;                // split-K slices of G1 / G2 (small batches)
+  long long g1_count = 0, g2_count = 0;   // doubles of C the slices cover
   DevBuf<long long> g4_a, g4_y;
   bool ldlt_res = false;                  // the large-design LDLT sequential kernel starts from R instead of k symmetric products
   bool g3_aligned = true;
@@ -292,9 +294,13 @@ struct bvhar_fit {
       // (updateSv, stage 3, was already done at the end of the previous sweep - see below - or at create time)
       if (fork) { CU(cudaEventRecord(evf[2], st)); CU(cudaStreamWaitEvent(s3, evf[2], 0)); }
       if (direct_p) LAUNCH("sv_wmix", launch_sv_wmix(D, P, Wt.p, st));
-      else LAUNCH("gram_C_dmma", launch_dgemm_tn(g2, sg));
+      else {
+        LAUNCH("gram_C_dmma", [&] { const cudaError_t e = launch_dgemm_tn(g2, sg); return e != cudaSuccess ? e : launch_splitk_reduce(g2, g2_count, sg); }());
+        if (g2.ksplit > 1) ++nl;
+      }
       if (fork) CU(cudaEventRecord(evf[3], s3));
-      LAUNCH("gram_S_dmma", launch_dgemm_tn(g1, st));
+      LAUNCH("gram_S_dmma", [&] { const cudaError_t e = launch_dgemm_tn(g1, st); return e != cudaSuccess ? e : launch_splitk_reduce(g1, g1_count, st); }());
+      if (g1.ksplit > 1) ++nl;
     }
     if (coef_big) {
       if (D.sv && !direct_p) LAUNCH("coef_pbuild", launch_coef_v2(0, D, P, Pfac.p, Qn.p, smem_limit, st));
@@ -838,6 +844,26 @@ int build(const bvhar_fit_desc* d, bvhar_fit** out) {
   if (F->direct_p) {
     if (!F->coef_big) return fail(BVHAR_ERR_CUDA, "internal: direct precision build without the large-design path");
     F->g1.A = F->Wt.p; F->g1.C = F->Pfac.p;
+  }
+  if (D.sv) {
+    // Small batches (a few dozen chains: fewer output tiles than SMs) leave most of the GPU idle in the two time contractions
+    // and each tile's K loop is a serial chain of k-tiles: cut K into slices that run as separate work items of the
+    // persistent kernel and add the slices in a fixed order afterwards (deterministic: no atomics).
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, F->device);
+    auto split = [&](GemmArgs& g, DevBuf<double>& ws, long long count) -> int {
+      const long long tiles = (long long)((g.M + GBM - 1) / GBM) * ((g.N + GBN - 1) / GBN) * g.groups;
+      const int S = g.aligned16 ? gemm_choose_ksplit(tiles, D.nmax, sms) : 1;
+      if (S > 1) {
+        CU(ws.alloc((size_t)S * (size_t)count));
+        g.ksplit = S; g.ws = ws.p; g.ws_stride = count;
+      }
+      return 0;
+    };
+    F->g1_count = (long long)U * k * D.ldS;
+    F->g2_count = (long long)U * k * D.ldX;
+    if (int rc = split(F->g1, F->ws1, F->g1_count)) return rc;
+    if (!F->direct_p) { if (int rc = split(F->g2, F->ws2, F->g2_count)) return rc; }
   }
   if (F->coef_big) CU(F->hscr.alloc(D.sv ? seq_time_scratch_doubles(D) : (size_t)U * k * dd));
   if (F->coef_v2 && coef_pipe_fits(D, F->smem_limit) && getenv("BVHAR_COEF_NOPIPE") == nullptr) CU(F->Qn.alloc((size_t)U * k * D.ldS));
@@ -1423,6 +1449,7 @@ int bvhar_cuda_fit_run_stage(bvhar_fit* fit, int stage, int iter) {
     case 4:
       if (D.sv && fit->direct_p) { CU(launch_sv_wmix(D, fit->P, fit->Wt.p, fit->st)); CU(launch_dgemm_tn(fit->g1, fit->st)); }
       else if (D.sv) { CU(launch_dgemm_tn(fit->g1, fit->st)); CU(launch_dgemm_tn(fit->g2, fit->st)); }
+      if (D.sv) { CU(launch_splitk_reduce(fit->g1, fit->g1_count, fit->st)); if (!fit->direct_p) CU(launch_splitk_reduce(fit->g2, fit->g2_count, fit->st)); }
       if (fit->coef_big) {
         if (D.sv && !fit->direct_p) CU(launch_coef_v2(0, D, fit->P, fit->Pfac.p, fit->Qn.p, fit->smem_limit, fit->st));
         CU(launch_coef_big(1, D, fit->P, fit->Pfac.p, fit->hscr.p, fit->smem_limit, fit->st));
@@ -1955,7 +1982,19 @@ int bvhar_cuda_dgemm_tn(int device, int64_t M, int64_t N, int64_t K, const doubl
   GemmArgs g{};
   g.A = dA.p; g.B = dB.p; g.C = dC.p; g.M = (int)M; g.N = (int)N; g.K = (int)K; g.lda = (int)la; g.ldb = (int)lb; g.ldc = (int)ldc;
   g.groups = 1; g.epi = EPI_STORE; g.aligned16 = 1;
+  DevBuf<double> ws;
+  {  // few output tiles and a long K: the split-K path of the persistent kernel, as the engine uses it for small batches
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    const long long tiles = ((M + GBM - 1) / GBM) * ((N + GBN - 1) / GBN);
+    const int S = gemm_choose_ksplit(tiles, (int)K, sms);
+    if (S > 1) {
+      CU(ws.alloc((size_t)S * M * ldc));
+      g.ksplit = S; g.ws = ws.p; g.ws_stride = (long long)M * ldc;
+    }
+  }
   CU(launch_dgemm_tn(g, 0));
+  CU(launch_splitk_reduce(g, (long long)M * ldc, 0));
   CU(cudaDeviceSynchronize());
   CU(cudaMemcpy(C, dC.p, (size_t)M * ldc * sizeof(double), cudaMemcpyDeviceToHost));
   return 0;

@@ -1,5 +1,8 @@
 // gemm_tn.cu - the grouped fp64 "TN" contraction kernel (DMMA) declared in gemm_tn.cuh: G1 / G2 / G3 of the sweep, the
 // X'X / X'Y set-up products of the LDLT models and the companion-matrix squarings of the stability filter.
+#include <algorithm>
+#include <cstdlib>
+
 #include "gemm_tn.cuh"
 
 #include <cstdlib>
@@ -202,7 +205,7 @@ __device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, unsign
                ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
-struct TileCoord { int grp, m0, n0, M, K, sub; };
+struct TileCoord { int grp, m0, n0, M, K, sub, k0, slice; };
 // Work item w of the persistent schedule -> (group, row tile, column tile), column tiles fastest: the CTAs running at
 // one time share a few A row panels and the whole (L2-resident) B.  Items below `split_from` are whole 128 x 128
 // tiles.  The tiles of the last, partial round (2 400 tiles on 148 SMs = 16 full rounds + 32 tiles) would leave most
@@ -217,10 +220,21 @@ __device__ __forceinline__ int work_decode(const GemmArgs& g, int w, int mtiles,
     t.sub = q & 3;
   }
   if (tile >= total) return 0;
+  t.slice = 0;
+  if (g.ksplit > 1) {  // K slices fastest: the slices of one output tile run side by side on different SMs
+    t.slice = tile % g.ksplit;
+    tile /= g.ksplit;
+  }
   const int nt = tile % ntiles, rest = tile / ntiles;
   const int mt = rest % mtiles;
   t.grp = rest / mtiles;
   t.K = g.Kg ? g.Kg[t.grp] : g.K;
+  t.k0 = 0;
+  if (g.ksplit > 1) {  // slice = a whole number of k-tiles; trailing slices may be empty (they store zeros)
+    const int per = ((t.K + GBK - 1) / GBK + g.ksplit - 1) / g.ksplit * GBK;
+    t.k0 = t.slice * per;
+    t.K = max(0, min(per, t.K - t.k0));
+  }
   t.M = g.Mg ? g.Mg[t.grp] : g.M;
   t.m0 = mt * GBM;
   t.n0 = nt * GBN + (t.sub > 0 ? t.sub * 32 : 0);
@@ -276,7 +290,7 @@ __global__ void __launch_bounds__(TB_THREADS, 1) dgemm_tn_bulk_kernel(const Gemm
         __syncwarp();
         if (lane == 0) mbar_arrive_expect_tx(full + s, (unsigned)rows * (bytesA + bytesB));
         __syncwarp();
-        if (r < rows) bulk_copy_g2s(dst, src + (size_t)(k0 + r) * ld, mybytes, full + s);
+        if (r < rows) bulk_copy_g2s(dst, src + (size_t)(t.k0 + k0 + r) * ld, mybytes, full + s);
       }
     }
     return;
@@ -292,7 +306,7 @@ __global__ void __launch_bounds__(TB_THREADS, 1) dgemm_tn_bulk_kernel(const Gemm
     if (kind == 0) break;
     if (kind == 1) continue;
     const int M = t.M, m0 = t.m0, n0 = t.n0;
-    double* C = g.C + (g.c_off ? g.c_off[t.grp] : 0);
+    double* C = (g.ksplit > 1 ? g.ws + (size_t)t.slice * g.ws_stride : g.C) + (g.c_off ? g.c_off[t.grp] : 0);
     const long long yoff = (g.epi == EPI_Y_MINUS && g.y_off) ? g.y_off[t.grp] : 0;
     // (ym0, ym1: col % ymod and (col + 1) % ymod, computed once per column pair of the tile - the runtime modulo cost as
     // much as the rest of the epilogue when it was evaluated per stored element)
@@ -423,10 +437,37 @@ __global__ void __launch_bounds__(TB_THREADS, 1) dgemm_tn_bulk_kernel(const Gemm
   }
 }
 
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const double* __restrict__ ws, const int S, const long long stride, double* __restrict__ C,
+                                                            const long long count) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x) {
+    double s = 0.0;
+    for (int q = 0; q < S; ++q) s += ws[(size_t)q * stride + i];  // fixed order: bit-reproducible
+    C[i] = s;
+  }
+}
+
 // BVHAR_GEMM_LEGACY=1 keeps the sm_80-style cp.async kernel for every shape (A/B comparisons in the profiles).
 static bool gemm_force_legacy() {
   static const bool v = [] { const char* e = getenv("BVHAR_GEMM_LEGACY"); return e && e[0] == '1'; }();
   return v;
+}
+
+int gemm_choose_ksplit(long long tiles, int kmax, int sms) {
+  static const bool off = [] {
+    const char* e = getenv("BVHAR_GEMM_NO_SPLITK");
+    const char* l = getenv("BVHAR_GEMM_LEGACY");  // the cp.async kernel has no slices
+    return (e && e[0] == '1') || (l && l[0] == '1');
+  }();
+  if (off || tiles <= 0 || 2 * tiles > sms) return 1;  // at least half a wave of tiles: no split
+  const int by_sms = (int)(sms / tiles), by_k = kmax / (8 * GBK);  // keep >= 8 k-tiles per slice
+  const int s = std::min(std::min(by_sms, by_k), 16);
+  return s < 2 ? 1 : s;
+}
+cudaError_t launch_splitk_reduce(const GemmArgs& g, long long count, cudaStream_t st) {
+  if (g.ksplit <= 1) return cudaSuccess;
+  const int blocks = (int)std::min<long long>((count + 255) / 256, 148 * 8);
+  splitk_reduce_kernel<<<blocks, 256, 0, st>>>(g.ws, g.ksplit, g.ws_stride, g.C, count);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_dgemm_tn(const GemmArgs& g, cudaStream_t st) {
@@ -442,7 +483,7 @@ cudaError_t launch_dgemm_tn(const GemmArgs& g, cudaStream_t st) {
       cudaFuncSetAttribute(dgemm_tn_bulk_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TB_SMEM);
     }
     const int mtiles = (g.M + GBM - 1) / GBM, ntiles = (g.N + GBN - 1) / GBN;
-    const long long total = (long long)mtiles * ntiles * g.groups;
+    const long long total = (long long)mtiles * ntiles * g.groups * (g.ksplit > 1 ? g.ksplit : 1);
     const int grid = (int)(total < sms ? total : sms);
     // tiles of the last partial round are split into column quarters when that round would fill at most half the SMs
     const long long rem = total % grid;

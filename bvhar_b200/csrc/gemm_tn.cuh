@@ -37,6 +37,12 @@ struct GemmArgs {
   const long long* y_off;
   int ldy, ymod;
   int aligned16;           // all of A/B offsets and leading dimensions are even (16-byte chunks legal)
+  // split-K (small batches: fewer tiles than SMs).  ksplit > 1: the K range of every tile is cut into ksplit slices that run
+  // as separate work items and store their partial products to ws + slice * ws_stride (same layout as C); the caller then
+  // sums the slices in a fixed order (launch_splitk_reduce).  EPI_STORE only.
+  int ksplit;
+  double* ws;
+  long long ws_stride;
 };
 
 constexpr int GBM = 128, GBN = 128, GBK = 16, GSTAGES = 3, GPAD = 4;
@@ -64,5 +70,9 @@ __device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, do
 // The contraction kernel itself lives in ONE translation unit, gemm_tn.cu (it used to be instantiated by every file
 // that included this header: ten copies, a 41 MB library and a 4-minute rebuild).
 cudaError_t launch_dgemm_tn(const GemmArgs& g, cudaStream_t st);
+// K slices for a contraction of `tiles` output tiles and K <= kmax on a device with `sms` SMs (1 = no split)
+int gemm_choose_ksplit(long long tiles, int kmax, int sms);
+// C[i] = sum over the slices of ws[s * ws_stride + i], i < count, slices added in order
+cudaError_t launch_splitk_reduce(const GemmArgs& g, long long count, cudaStream_t st);
 
 }  // namespace bvhar

