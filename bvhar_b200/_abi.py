@@ -408,6 +408,7 @@ def load_library():
     L.bvhar_cuda_draw_coef_batched.argtypes = [C.c_int, C.c_int64, C.c_int32, c_dp, c_dp, c_dp, c_dp]
     L.bvhar_cuda_mniw_run.argtypes = [C.POINTER(MniwDesc), c_dp, c_dp, c_dp, c_dp, C.POINTER(C.c_uint8)]
     L.bvhar_cuda_bench_fp64_peak.argtypes = [C.c_int, C.c_int, c_dp]
+    L.bvhar_cuda_bench_fp64_latency.argtypes = [C.c_int, C.c_int, c_dp]
     L.bvhar_cuda_bench_dgemm_tn.argtypes = [C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_int, c_dp]
     if L.bvhar_cuda_abi_version() != ABI_VERSION:
         raise RuntimeError("bvhar_b200: libbvhar_b200.so was built against a different ABI version; rebuild it")

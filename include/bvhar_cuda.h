@@ -434,6 +434,9 @@ int bvhar_cuda_draw_coef_batched(int device, int64_t batch, int32_t d, const dou
 /* ---- device-resident micro-benchmarks (roofline denominators; bench.py) ---------------------- */
 /* mode 0: fp64 FMA issue peak, mode 1: fp64 DMMA (mma.sync.m8n8k4) issue peak, in TFLOP/s. */
 int bvhar_cuda_bench_fp64_peak(int device, int mode, double* tflops);
+/* cycles per DEPENDENT fp64 operation, one warp: kind 0 DFMA, 1 DMMA m8n8k4 accumulator chain, 2 rsqrt, 3 reciprocal, 4 DFMA through a
+ * 64-bit shuffle.  Diagnostic (profiles/r02_fp64_peaks.md): the latency-bound kernels of the sweep are chains of these. */
+int bvhar_cuda_bench_fp64_latency(int device, int kind, double* cycles);
 /* The TN contraction kernel alone on synthetic device-resident operands, CUDA-event timed. */
 int bvhar_cuda_bench_dgemm_tn(int device, int64_t M, int64_t N, int64_t K, int iters, double* ms_per_launch);
 
