@@ -48,18 +48,27 @@ __global__ void __launch_bounds__(256) dmma_peak_kernel(double* out, int iters) 
 // Cholesky, tridiagonal recurrences, substitution steps): one warp, one chain, clock64 around `iters` dependent operations.
 // kind 0: DFMA, 1: DMMA m8n8k4 (accumulator chain), 2: rsqrt(double), 3: 1.0 / x, 4: a DFMA chain through a 64-bit shuffle
 // (the step of the register-block substitutions).  out[0] = cycles per operation.
-__global__ void __launch_bounds__(32) fp64_latency_kernel(double* out, int iters, int kind, double seed) {
+// One warp, ONE dependent chain, straight-line: 64 operations per loop trip so that the loop branch does not count.
+template <int KIND>
+__global__ void __launch_bounds__(32) fp64_latency_kernel(double* out, int trips, double seed) {
   double a = seed, b = 1.0 + 1e-9 * seed, c0 = 0.0, c1 = 0.0;
+  const double e = 1e-9 * seed;
+  const int src = (threadIdx.x + 1) & 31;
   const long long t0 = clock64();
-  for (int it = 0; it < iters; ++it) {
-    if (kind == 0) a = fma(a, b, 1e-9);
-    else if (kind == 1) dmma_m8n8k4(c0, c1, b, a);
-    else if (kind == 2) a = rsqrt(a) + 1.5;
-    else if (kind == 3) a = 1.0 / a + 0.5;
-    else a = fma(__shfl_sync(0xffffffffu, a, (threadIdx.x + 1) & 31), b, 1e-9);
+  for (int it = 0; it < trips; ++it) {
+#pragma unroll
+    for (int r = 0; r < 64; ++r) {
+      if (KIND == 0) a = fma(a, b, e);
+      else if (KIND == 1) dmma_m8n8k4(c0, c1, b, a);
+      else if (KIND == 2) a = rsqrt(a) + 1.5;
+      else if (KIND == 3) a = 1.0 / a + 0.5;
+      else if (KIND == 4) a = fma(__shfl_sync(0xffffffffu, a, src), b, e);
+      else if (KIND == 5) a = a + e;
+      else a = a * b;
+    }
   }
   const long long t1 = clock64();
-  if (threadIdx.x == 0) { out[0] = (double)(t1 - t0) / iters; out[1] = a + c0 + c1; }
+  if (threadIdx.x == 0) { out[0] = (double)(t1 - t0) / (64.0 * trips); out[1] = a + c0 + c1; }
 }
 __global__ void fill_kernel(double* p, size_t n, double scale) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
@@ -96,14 +105,22 @@ int bvhar_cuda_bench_fp64_peak(int device, int mode, double* tflops) {
   return cudaGetLastError() == cudaSuccess ? 0 : BVHAR_ERR_CUDA;
 }
 
-// cycles per dependent fp64 operation (see fp64_latency_kernel); kind 0..4
+// cycles per dependent fp64 operation (see fp64_latency_kernel); kind 0..6
 int bvhar_cuda_bench_fp64_latency(int device, int kind, double* cycles) {
   if (cudaSetDevice(device) != cudaSuccess) return BVHAR_ERR_CUDA;
   double* out;
   if (cudaMalloc(&out, 2 * sizeof(double)) != cudaSuccess) return BVHAR_ERR_CUDA;
   double h[2] = {0.0, 0.0};
   for (int rep = 0; rep < 2; ++rep) {
-    fp64_latency_kernel<<<1, 32>>>(out, 20000, kind, 1.25);
+    switch (kind) {
+      case 0: fp64_latency_kernel<0><<<1, 32>>>(out, 400, 1.25); break;
+      case 1: fp64_latency_kernel<1><<<1, 32>>>(out, 400, 1.25); break;
+      case 2: fp64_latency_kernel<2><<<1, 32>>>(out, 400, 1.25); break;
+      case 3: fp64_latency_kernel<3><<<1, 32>>>(out, 400, 1.25); break;
+      case 4: fp64_latency_kernel<4><<<1, 32>>>(out, 400, 1.25); break;
+      case 5: fp64_latency_kernel<5><<<1, 32>>>(out, 400, 1.25); break;
+      default: fp64_latency_kernel<6><<<1, 32>>>(out, 400, 1.25); break;
+    }
     if (cudaMemcpy(h, out, sizeof h, cudaMemcpyDeviceToHost) != cudaSuccess) { cudaFree(out); return BVHAR_ERR_CUDA; }
   }
   *cycles = h[0];
