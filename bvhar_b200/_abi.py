@@ -273,11 +273,26 @@ class PackedFit:
         pcols: Dict[str, List[int]] = {}
         scols: Dict[str, List[float]] = {}
 
+        addressof, from_buffer = C.addressof, C.c_char.from_buffer
+
         def setp(field, arr):
-            pcols.setdefault(field, []).append(arr.__array_interface__["data"][0] if arr is not None else 0)
+            if arr is None:
+                ptr = 0
+            else:
+                try:  # a third of the cost of arr.__array_interface__ (which builds a dict per call); needs a writable buffer
+                    ptr = addressof(from_buffer(arr))
+                except (TypeError, ValueError):  # read-only or empty array
+                    ptr = arr.__array_interface__["data"][0]
+            col = pcols.get(field)
+            if col is None:
+                col = pcols[field] = []
+            col.append(ptr)
 
         def sets(field, v):
-            scols.setdefault(field, []).append(float(v) if type(v) is float else _scalar(v))
+            col = scols.get(field)
+            if col is None:
+                col = scols[field] = []
+            col.append(v if type(v) is float else _scalar(v))
 
         f8 = np.float64
         for c, ini in enumerate(param_init):

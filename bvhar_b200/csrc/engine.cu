@@ -18,6 +18,7 @@
 #include <set>
 #include <string>
 #include <thread>
+#include <atomic>
 #include <vector>
 
 #include "../../include/bvhar_cuda.h"
@@ -85,6 +86,24 @@ struct NvtxRange {
 struct HostStagePool {
   std::mutex m;
   std::vector<std::vector<double>> free;
+  // Blocks of pooled vectors are page-locked once (cudaHostRegister) and stay so while the pool owns them: the set-up's
+  // uploads become true asynchronous DMAs at the link's rate (a pageable 10 MB cudaMemcpyAsync is staged through the driver's
+  // bounce buffer at a third of it, and blocks the host meanwhile).  BVHAR_NO_PIN_STAGE=1 keeps them pageable.
+  std::map<const double*, size_t> pinned;
+  const bool pin_enabled = getenv("BVHAR_NO_PIN_STAGE") == nullptr;
+  void pin(std::vector<double>& v) {
+    if (!pin_enabled || v.capacity() < (1u << 16)) return;
+    std::lock_guard<std::mutex> lk(m);
+    if (pinned.count(v.data())) return;
+    if (cudaHostRegister(v.data(), v.capacity() * sizeof(double), cudaHostRegisterPortable) == cudaSuccess) pinned[v.data()] = v.capacity();
+    else cudaGetLastError();  // stays pageable
+  }
+  void unpin_locked(const std::vector<double>& v) {
+    auto it = pinned.find(v.data());
+    if (it == pinned.end()) return;
+    cudaHostUnregister(const_cast<double*>(it->first));
+    pinned.erase(it);
+  }
   // a vector of n elements; `fill`: every element is set to `value`, otherwise the contents are unspecified (caller overwrites all)
   std::vector<double> take(size_t n, bool fill, double value = 0.0) {
     std::vector<double> v;
@@ -97,18 +116,24 @@ struct HostStagePool {
     }
     if (fill) v.assign(n, value);
     else v.resize(n);
+    pin(v);
     return v;
   }
   void give(std::vector<double>&& v) {
-    if (v.capacity() < (1u << 16)) return;
     std::lock_guard<std::mutex> lk(m);
-    if (free.size() < 12) free.push_back(std::move(v));
+    if (v.capacity() >= (1u << 16) && free.size() < 12) { free.push_back(std::move(v)); return; }
+    unpin_locked(v);  // leaves the pool: its block is freed by the caller's vector
   }
 };
-inline HostStagePool& host_stage_pool() { static HostStagePool p; return p; }
+// never destroyed: the blocks stay registered until the process ends (unregistering during static destruction would race
+// the CUDA runtime's own teardown)
+inline HostStagePool& host_stage_pool() { static HostStagePool* p = new HostStagePool; return *p; }
 struct HostStageReturn {  // hands the listed vectors back when the set-up leaves scope (any exit path)
   std::vector<std::vector<double>*> vs;
-  ~HostStageReturn() { for (auto* v : vs) host_stage_pool().give(std::move(*v)); }
+  ~HostStageReturn() {
+    cudaDeviceSynchronize();  // page-locked sources: no transfer may still be reading them (a no-op on the normal path)
+    for (auto* v : vs) host_stage_pool().give(std::move(*v));
+  }
 };
 
 template <typename T>
@@ -690,6 +715,10 @@ int build(const bvhar_fit_desc* d, bvhar_fit** out) {
   }
   // explicit lvol inits: the chains' n x k blocks are gathered into one page-locked staging buffer by a few host threads
   // WHILE the unit loop below fills the other staging vectors (both are memory-bound host work on disjoint data)
+  // and each finished slice goes to the device at once (page-locked source: a true asynchronous DMA on stream 0), so the
+  // one large transfer of the set-up (164 MB at C3: 6.5 ms of PCIe time) runs under the unit loop instead of after it
+  DevBuf<double> lv_stage;  // declared before the thread's guard: on an early return the guard joins first, then this is freed
+  std::atomic<int> lvol_copy_err{0};
   std::thread lvol_gather;
   struct JoinGuard { std::thread& t; ~JoinGuard() { if (t.joinable()) t.join(); } } lvol_gather_guard{lvol_gather};
   if (D.sv && lvol_explicit) {
@@ -698,16 +727,28 @@ int build(const bvhar_fit_desc* d, bvhar_fit** out) {
     // a fresh pageable vector of this size costs more in page faults than the copy itself (66 ms for 164 MB at C3)
     hlv_stage = lvol_stage_buffer((size_t)D.C * blk);
     if (!hlv_stage) { hlv.resize((size_t)D.C * blk); hlv_stage = hlv.data(); }
+    lv_stage.n = (size_t)D.C * blk;
+    CU(cudaMallocAsync(&lv_stage.p, lv_stage.n * sizeof(double), 0));  // fully overwritten: no memset
     double* dst = hlv_stage;
-    const int nchain = D.C;
+    double* ddst = lv_stage.p;
+    const int nchain = D.C, dev = F->device;
     const bvhar_chain_init* inits = d->init;
-    lvol_gather = std::thread([dst, blk, nchain, inits] {
+    std::atomic<int>* cerr = &lvol_copy_err;
+    lvol_gather = std::thread([dst, ddst, blk, nchain, inits, dev, cerr] {
       const int nthr = std::max(1, std::min(8, nchain / 32));
+      const int slice = 16;  // chains per transfer
       std::vector<std::thread> pool;
       for (int th = 0; th < nthr; ++th)
         pool.emplace_back([=] {
-          for (int c = th; c < nchain; c += nthr)
-            if (inits[c].lvol) std::memcpy(dst + (size_t)c * blk, inits[c].lvol, sizeof(double) * blk);
+          if (cudaSetDevice(dev) != cudaSuccess) { cerr->store(1); return; }
+          for (int c0 = th * slice; c0 < nchain; c0 += nthr * slice) {
+            const int c1 = std::min(nchain, c0 + slice);
+            for (int c = c0; c < c1; ++c)
+              if (inits[c].lvol) std::memcpy(dst + (size_t)c * blk, inits[c].lvol, sizeof(double) * blk);
+            if (cudaMemcpyAsync(ddst + (size_t)c0 * blk, dst + (size_t)c0 * blk, sizeof(double) * blk * (size_t)(c1 - c0), cudaMemcpyHostToDevice, 0) !=
+                cudaSuccess)
+              cerr->store(1);
+          }
         });
       for (auto& t : pool) t.join();
     });
@@ -721,8 +762,9 @@ int build(const bvhar_fit_desc* d, bvhar_fit** out) {
     } else {
       std::vector<std::thread> pool;
       for (int th = 0; th < nthr; ++th)
-        pool.emplace_back([&, th] {
-          for (int u = th; u < U; u += nthr) {
+        pool.emplace_back([&, th] {  // contiguous unit ranges: neighbouring units share cache lines of the [a][unit, j] coefficient rows
+          const int per = (U + nthr - 1) / nthr;
+          for (int u = th * per; u < std::min(U, (th + 1) * per); ++u) {
             if (init_unit(u / D.C, u % D.C)) return;
           }
         });
@@ -733,15 +775,7 @@ int build(const bvhar_fit_desc* d, bvhar_fit** out) {
   lap("host init loops");
   if (lvol_gather.joinable()) lvol_gather.join();
   lap("lvol gather");
-  // the one large transfer (page-locked source: a true asynchronous DMA) goes first, so that the pageable uploads below
-  // stage on the host while it is in flight
-  DevBuf<double> lv_stage;
-  if (D.sv && lvol_explicit) {
-    const size_t cnt = (size_t)D.C * k * F->win_n[0];
-    lv_stage.n = cnt;
-    CU(cudaMallocAsync(&lv_stage.p, cnt * sizeof(double), 0));  // fully overwritten: no memset
-    CU(cudaMemcpyAsync(lv_stage.p, hlv_stage, cnt * sizeof(double), cudaMemcpyHostToDevice, 0));
-  }
+  if (lvol_copy_err.load()) return fail(BVHAR_ERR_CUDA, "upload of the log-volatility inits failed");
   CU(F->Acoef.upload(hA)); CU(F->alpha.upload(halpha)); CU(F->cvec.upload(hc)); CU(F->prec.upload(hprec));
   CU(F->contem.upload(hcontem)); CU(F->L.upload(hL)); CU(F->chol_prec.upload(hcp));
   CU(F->sparse_coef.alloc((size_t)U * dd * k)); CU(F->sparse_contem.alloc((size_t)U * q)); CU(F->znorm.alloc((size_t)2 * U * k));  // [U][k] column norms of Z, then [U][k] per-series sums of squared lvol increments
