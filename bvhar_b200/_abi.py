@@ -279,8 +279,9 @@ class PackedFit:
             if arr is None:
                 ptr = 0
             else:
-                try:  # a third of the cost of arr.__array_interface__ (which builds a dict per call); needs a writable buffer
-                    ptr = addressof(from_buffer(arr))
+                try:  # a third of the cost of arr.__array_interface__ (which builds a dict per call); needs a writable,
+                    # C-contiguous buffer: the column-major matrices are passed as their transposed view (same memory)
+                    ptr = addressof(from_buffer(arr if arr.ndim == 1 else arr.T))
                 except (TypeError, ValueError):  # read-only or empty array
                     ptr = arr.__array_interface__["data"][0]
             col = pcols.get(field)
