@@ -133,3 +133,28 @@ def test_chain_init_table_matches_the_inputs(prior, sv):
                 assert getattr(I, field) == float(np.asarray(ini[field], dtype=np.float64).reshape(-1)[0])
                 used += 1
     assert used >= 2 * 5
+
+
+def test_chain_init_pointers_for_awkward_arrays():
+    """The pointer columns are read through the buffer protocol (writable, C-contiguous buffers) with a fallback for the
+    rest: read-only vectors, row-major or column-major matrices, Python lists and float32 inputs must all end up as
+    pointers to the right values."""
+    import problems as pr
+    kw, _ = pr.make_problem(prior="Horseshoe", sv=True, dim=3, T=40, chains=4)
+    inits_in = kw["param_init"]
+    ro = np.array(inits_in[0]["lvol_init"], dtype=np.float64)
+    ro.setflags(write=False)
+    inits_in[0]["lvol_init"] = ro                                                        # read-only: fallback path
+    inits_in[1]["init_coef"] = np.ascontiguousarray(inits_in[1]["init_coef"])           # row-major matrix: copied to column-major
+    inits_in[2]["init_coef"] = np.asfortranarray(inits_in[2]["init_coef"])              # column-major: passed through
+    inits_in[3]["init_contem"] = [float(v) for v in np.asarray(inits_in[3]["init_contem"]).reshape(-1)]  # list
+    inits_in[3]["local_sparsity"] = np.asarray(inits_in[3]["local_sparsity"], dtype=np.float32)         # float32
+    pk = _abi.PackedFit(**kw)
+    inits = C.cast(pk.desc.init, C.POINTER(_abi.ChainInit))
+    for c, ini in enumerate(inits_in):
+        for field in ("lvol_init", "init_coef", "init_contem", "local_sparsity", "lvol"):
+            a = np.asarray(ini[field], dtype=np.float64)
+            got = np.ctypeslib.as_array(getattr(inits[c], field), shape=(a.size,))
+            np.testing.assert_array_equal(got, a.reshape(-1, order="F"), err_msg=f"chain {c} field {field}")
+    assert C.addressof(inits[0].lvol_init.contents) == ro.__array_interface__["data"][0]
+    assert C.addressof(inits[2].init_coef.contents) == inits_in[2]["init_coef"].__array_interface__["data"][0]
